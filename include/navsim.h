@@ -1,0 +1,148 @@
+/* navsim.h — C-ABI of the B200 batched LiDAR-navigation simulator.
+ *
+ * This is the drop-in boundary for the reference's environment: one handle simulates N
+ * independent agents, each of which behaves exactly like one instance of
+ *     project_ppo/src/environment_new.py  class Env            (:26-382)
+ * with the Gazebo/ROS process underneath it (cmd_vel -> diff-drive -> ray sensor -> scan,
+ * environment_new.py:279-286) replaced by fused sm_100a kernels.  Each entry point names
+ * the reference call it replaces.  The Python classes navbot_ppo_b200.Env / VecEnv bind
+ * these symbols through ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *  - plain C, no exceptions: every call returns 0 or a negative NAVSIM_E* code and
+ *    nav_last_error() holds a message for the calling thread;
+ *  - "dev" pointers are device memory owned by the caller (torch tensors), fp32/uint8,
+ *    contiguous, and must stay alive until `stream` reaches the call; "host" pointers are
+ *    ordinary host memory;
+ *  - all work is enqueued on the given cudaStream_t (passed as void*), no hidden syncs
+ *    except in the *_host entry points, which block until their outputs are in host memory;
+ *  - one handle per device; a handle is not thread-safe, separate handles are independent;
+ *  - the step/reset calls are CUDA-graph capturable.
+ */
+#ifndef NAVSIM_H_
+#define NAVSIM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NAVSIM_OK 0
+#define NAVSIM_EINVAL (-22)
+#define NAVSIM_ENOMEM (-12)
+#define NAVSIM_ECUDA (-5)
+#define NAVSIM_ENODEV (-19)
+
+#define NAVSIM_OBS_DIM 16      /* environment_new.py:296-304: 10 lidar + 2 past action + 4 goal */
+#define NAVSIM_ACT_DIM 2       /* main.py:19 */
+#define NAVSIM_LIDAR_FEATS 10  /* environment_new.py:293 */
+#define NAVSIM_MAX_RECTS 8
+#define NAVSIM_MAX_BEAMS 360
+
+typedef struct navsim navsim_t;
+
+/* Simulator configuration.  navsim_default_cfg() fills in the reference's numbers. */
+typedef struct navsim_cfg {
+  int32_t num_agents;        /* N */
+  int32_t num_beams;         /* gazebo.xacro:111 <samples>10 */
+  int32_t max_episode_steps; /* ppo.py:552 max_timesteps_per_episode (500 on the main.py path) */
+  int32_t auto_reset;        /* 1: VecEnv semantics (ppo.py:553-593 reset folded into step) */
+  int32_t device;            /* CUDA ordinal */
+  int32_t n_reset_rects;     /* goal rejection boxes used by Env.reset  (:340-343) */
+  int32_t n_respawn_rects;   /* goal rejection boxes used on arrival    (:248-251) */
+  int32_t reserved0;
+  uint64_t seed;             /* Philox key for goal sampling */
+  int64_t agent_id_offset;   /* global id of agent 0 (rank * N when sharded) */
+  double dt;                 /* 1 / 5 Hz LiDAR, gazebo.xacro:107 */
+  double lidar_offset_x;     /* urdf.xacro:134-138 (-0.032) */
+  double lidar_min, lidar_max;     /* gazebo.xacro:117-119 */
+  double fov_min, fov_max;         /* gazebo.xacro:113-114 */
+  double collision_range;    /* environment_new.py:188 min_range */
+  double arrive_threshold;   /* :44-47 (0.2 training, 0.4 test) */
+  double reward_scale;       /* :213  500 */
+  double reward_collide;     /* :217  -100 */
+  double reward_arrive;      /* :221  +120 */
+  double diag_norm;          /* :21   sqrt(2) * 7.6 */
+  double goal_lo, goal_hi;   /* :337  uniform(-3.6, 3.6) */
+  double start_x, start_y, start_theta; /* turtlebot3_stage_1.launch:3-5 */
+  double reset_rects[NAVSIM_MAX_RECTS * 4];   /* {xlo, xhi, ylo, yhi} each */
+  double respawn_rects[NAVSIM_MAX_RECTS * 4];
+} navsim_cfg;
+
+/* Per-agent state fields for navsim_get_state / navsim_set_state (host arrays of N). */
+enum navsim_field {
+  NAVSIM_F_X = 0,         /* double */
+  NAVSIM_F_Y = 1,         /* double */
+  NAVSIM_F_THETA = 2,     /* double, wrapped to (-pi, pi] */
+  NAVSIM_F_GOAL_X = 3,    /* double */
+  NAVSIM_F_GOAL_Y = 4,    /* double */
+  NAVSIM_F_PAST_DIST = 5, /* double, Env.past_distance */
+  NAVSIM_F_PREV_A0 = 6,   /* float, previous action (environment_new.py:299-300) */
+  NAVSIM_F_PREV_A1 = 7,   /* float */
+  NAVSIM_F_STEPS = 8,     /* int32, one_round counter of ppo.py:489,549 */
+  NAVSIM_F_DRAWS = 9,     /* uint32, goal-sampler draws consumed */
+  NAVSIM_F_EP_RETURN = 10,/* float, running episode return (ppo.py:544) */
+  NAVSIM_F_EP_PATH = 11,  /* float, running path length (ppo.py:535-538) */
+  NAVSIM_F_LAST_MOVE = 12 /* float, displacement of the latest step (not yet in EP_PATH) */
+};
+
+/* Episode statistics accumulated on device (ppo.py:558-580 iteration metrics). */
+typedef struct navsim_stats {
+  uint64_t episodes, successes, collisions, timeouts, steps;
+  double return_sum, length_sum, path_sum;
+} navsim_stats;
+
+const char* nav_last_error(void);
+int navsim_abi_version(void);
+
+/* Fill cfg with the reference constants for `num_agents` agents, 10 beams. */
+int navsim_default_cfg(navsim_cfg* cfg, int32_t num_agents);
+
+/* Env.__init__ (environment_new.py:27-47): allocate per-agent state on cfg->device. */
+int navsim_create(navsim_t** out, const navsim_cfg* cfg);
+int navsim_destroy(navsim_t* h);
+
+/* Static obstacle map = what the .world file gives Gazebo (turtlebot3_stage_1.launch:8).
+ * seg_host: S rows of {x0, y0, x1, y1} in metres (host doubles). */
+int navsim_set_map(navsim_t* h, const double* seg_host, int32_t num_segments);
+
+/* Env.reset (environment_new.py:312-382) for every agent whose mask byte is non-zero
+ * (mask_dev == NULL: all agents).  Writes obs[N,16] rows of the agents that were reset. */
+int navsim_reset(navsim_t* h, const uint8_t* mask_dev, float* obs_dev, void* stream);
+
+/* Env.step (environment_new.py:272-310) for all agents.
+ * act_dev[N,2] float; obs_dev[N,16], rew_dev[N] float; done_dev/arrive_dev/trunc_dev[N]
+ * uint8 (trunc_dev may be NULL).  With cfg.auto_reset the episode protocol of
+ * PPO.rollout (ppo.py:552-593) is applied in the same launch: on done|arrive|timeout the
+ * agent is reset and obs holds the first observation of its next episode. */
+int navsim_step(navsim_t* h, const float* act_dev, float* obs_dev, float* rew_dev,
+                uint8_t* done_dev, uint8_t* arrive_dev, uint8_t* trunc_dev, void* stream);
+
+/* Same two calls with HOST buffers: pinned staging, H2D, kernel, D2H, synchronise. */
+int navsim_reset_host(navsim_t* h, const uint8_t* mask_host, float* obs_host);
+int navsim_step_host(navsim_t* h, const float* act_host, float* obs_host, float* rew_host,
+                     uint8_t* done_host, uint8_t* arrive_host, uint8_t* trunc_host);
+
+/* Scripted-action driver used by benchmarks: `num_steps` consecutive steps in one launch
+ * sequence with actions a0~U[0,1], a1~U[-1,1] drawn on device (Philox, key action_seed). */
+int navsim_step_scripted(navsim_t* h, int32_t num_steps, uint64_t action_seed, float* obs_dev,
+                         float* rew_dev, uint8_t* done_dev, uint8_t* arrive_dev, void* stream);
+
+/* LiDAR ranges of the current pose, ranges_dev[N, num_beams] doubles (+-inf gated),
+ * i.e. the LaserScan message of environment_new.py:284 — exposed for parity tests. */
+int navsim_scan(navsim_t* h, double* ranges_dev, void* stream);
+
+/* Parity injection / inspection (blocking copies to/from host arrays of N elements). */
+int navsim_get_state(navsim_t* h, int32_t field, void* host_out);
+int navsim_set_state(navsim_t* h, int32_t field, const void* host_in);
+
+int navsim_get_stats(navsim_t* h, navsim_stats* out, int32_t clear);
+int navsim_num_agents(const navsim_t* h);
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t navsim_launch_count(const navsim_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NAVSIM_H_ */

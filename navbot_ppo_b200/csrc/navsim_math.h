@@ -1,0 +1,213 @@
+// navsim_math.h — deterministic fp64 math + rigid-body / LiDAR physics shared by the
+// sm_100a kernels (navsim_kernels.cu) and by the CPU shim that stands in for Gazebo
+// underneath the reference's Env (oracle/).
+//
+// Why this file exists: the reference quantises yaw to whole degrees, goal offsets to
+// 0.1 m and bearing angles to 0.01 deg with Python round() (environment_new.py:142,
+// 149-150,169,172-176).  A one-ulp pose difference across such a boundary moves an
+// observation feature by up to 0.5, so the GPU simulator and the CPU stand-in for the
+// un-vendored Gazebo plugins must produce *bit-identical* poses and ranges.  Everything
+// here therefore uses only IEEE-754 correctly rounded primitives (+ - * / sqrt fma rint)
+// in a fixed order.  Build rules: device side with `-fmad=false`, host side with
+// `-ffp-contract=off`; never with fast-math.
+//
+// Physics rows:
+//   K  differential drive, midpoint form       turtlebot3_fake.cpp:117-118,157-163
+//      (v, w) mapping                          environment_new.py:273-278
+//      dt = 1 / LiDAR update rate (5 Hz)       turtlebot3_burger.gazebo.xacro:107
+//   R  planar ray sensor                       turtlebot3_burger.gazebo.xacro:104-127
+//      sensor mount x = -0.032 m               turtlebot3_burger.urdf.xacro:134-138
+#ifndef NAVSIM_MATH_H_
+#define NAVSIM_MATH_H_
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define NV_HD __host__ __device__ __forceinline__
+#else
+#define NV_HD static inline
+#endif
+
+#define NV_PI        3.141592653589793238462643383279502884
+#define NV_TWO_PI    6.283185307179586476925286766559005768
+#define NV_RAD2DEG   0x1.ca5dc1a63c1f8p+5 /* 180.0 / pi, as CPython's math.degrees uses */
+#define NV_INF       (__builtin_huge_val())
+
+// ---------------------------------------------------------------------------------------
+// sin/cos for |x| <= ~8: Cody-Waite reduction by pi/2 (two-term) + degree-13/12 minimax
+// kernels on [-pi/4, pi/4].  About 1 ulp; the point is determinism, not the last bit.
+// ---------------------------------------------------------------------------------------
+NV_HD double nv_ksin(double r) {
+  const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
+               S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
+               S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+  double z = r * r;
+  double p = S2 + z * (S3 + z * (S4 + z * (S5 + z * S6)));
+  return r + (z * r) * (S1 + z * p);
+}
+
+NV_HD double nv_kcos(double r) {
+  const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
+               C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
+               C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+  double z = r * r;
+  double p = z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6)))));
+  return (1.0 - 0.5 * z) + z * p;
+}
+
+NV_HD void nv_sincos(double x, double* s, double* c) {
+  const double INV_PIO2 = 6.36619772367581382433e-01;
+  const double PIO2_HI = 1.57079632673412561417e+00;  // high 33 bits of pi/2
+  const double PIO2_LO = 6.07710050650619224932e-11;  // pi/2 - PIO2_HI
+  double k = rint(x * INV_PIO2);
+  double r = (x - k * PIO2_HI) - k * PIO2_LO;
+  double sr = nv_ksin(r), cr = nv_kcos(r);
+  int q = ((int)k) & 3;
+  double ss = (q & 1) ? cr : sr;
+  double cc = (q & 1) ? sr : cr;
+  *s = (q & 2) ? -ss : ss;
+  *c = ((q + 1) & 2) ? -cc : cc;
+}
+
+// ---------------------------------------------------------------------------------------
+// atan(x): four-breakpoint reduction + odd minimax polynomial (the classic table of
+// atan(0.5), atan(1), atan(1.5), atan(inf) split into hi/lo parts).
+// ---------------------------------------------------------------------------------------
+NV_HD double nv_atan(double x) {
+  const double HI0 = 4.63647609000806093515e-01, LO0 = 2.26987774529616870924e-17;
+  const double HI1 = 7.85398163397448278999e-01, LO1 = 3.06161699786838301793e-17;
+  const double HI2 = 9.82793723247329054082e-01, LO2 = 1.39033110312309984516e-17;
+  const double HI3 = 1.57079632679489655800e+00, LO3 = 6.12323399573676603587e-17;
+  const double T0 = 3.33333333333329318027e-01, T1 = -1.99999999998764832476e-01,
+               T2 = 1.42857142725034663711e-01, T3 = -1.11111104054623557880e-01,
+               T4 = 9.09088713343650656196e-02, T5 = -7.69187620504482999495e-02,
+               T6 = 6.66107313738753120669e-02, T7 = -5.83357013379057348645e-02,
+               T8 = 4.97687799461593236017e-02, T9 = -3.65315727442169155270e-02,
+               T10 = 1.62858201153657823623e-02;
+  double ax = fabs(x);
+  double hi, lo, t;
+  int id;
+  if (ax < 0.4375) {
+    id = -1; t = ax; hi = 0.0; lo = 0.0;
+  } else if (ax < 0.6875) {
+    id = 0; t = (2.0 * ax - 1.0) / (2.0 + ax); hi = HI0; lo = LO0;
+  } else if (ax < 1.1875) {
+    id = 1; t = (ax - 1.0) / (ax + 1.0); hi = HI1; lo = LO1;
+  } else if (ax < 2.4375) {
+    id = 2; t = (ax - 1.5) / (1.0 + 1.5 * ax); hi = HI2; lo = LO2;
+  } else {
+    id = 3; t = -1.0 / ax; hi = HI3; lo = LO3;
+  }
+  double z = t * t, w = z * z;
+  double s1 = z * (T0 + w * (T2 + w * (T4 + w * (T6 + w * (T8 + w * T10)))));
+  double s2 = w * (T1 + w * (T3 + w * (T5 + w * (T7 + w * T9))));
+  double r;
+  if (id < 0) r = t - t * (s1 + s2);
+  else        r = hi - ((t * (s1 + s2) - lo) - t);
+  return (x < 0.0) ? -r : r;
+}
+
+// ---------------------------------------------------------------------------------------
+// Python round(x, k) for k in {0,1,2}: round-half-even on the EXACT decimal expansion of
+// the double, result = the double nearest n / 10^k (float.__round__ goes through
+// correctly rounded dtoa/strtod).  x * 10^k is formed exactly as hi + lo with one fma.
+// ---------------------------------------------------------------------------------------
+NV_HD double nv_round_scaled(double x, double scale) {
+  double hi = x * scale;
+  double lo = fma(x, scale, -hi);  // exact: x*scale == hi + lo
+  double n = rint(hi);             // ties-to-even on hi
+  double d = hi - n;               // exact, |d| <= 0.5
+  // |d| < 0.5 implies |d| <= 0.5 - ulp(hi) while |lo| <= ulp(hi)/2, so only an exact
+  // tie in hi can be overturned by the sign of lo.
+  if (d == 0.5 && lo > 0.0) n += 1.0;        // true value just above the tie
+  else if (d == -0.5 && lo < 0.0) n -= 1.0;  // true value just below the tie
+  return n;
+}
+NV_HD double nv_pyround0(double x) { return rint(x); }
+NV_HD double nv_pyround1(double x) { return nv_round_scaled(x, 10.0) / 10.0; }
+NV_HD double nv_pyround2(double x) { return nv_round_scaled(x, 100.0) / 100.0; }
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 counter RNG.  Goal sampling draws are keyed (seed, global agent id) and
+// counted per agent, so results do not depend on how agents are sharded over GPUs.
+// ---------------------------------------------------------------------------------------
+NV_HD void nv_mulhilo32(uint32_t a, uint32_t b, uint32_t* hi, uint32_t* lo) {
+  uint64_t p = (uint64_t)a * (uint64_t)b;
+  *hi = (uint32_t)(p >> 32);
+  *lo = (uint32_t)p;
+}
+
+NV_HD void nv_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                            uint32_t k0, uint32_t k1, uint32_t out[4]) {
+  for (int i = 0; i < 10; ++i) {
+    uint32_t h0, l0, h1, l1;
+    nv_mulhilo32(0xD2511F53u, c0, &h0, &l0);
+    nv_mulhilo32(0xCD9E8D57u, c2, &h1, &l1);
+    uint32_t n0 = h1 ^ c1 ^ k0, n1 = l1, n2 = h0 ^ c3 ^ k1, n3 = l0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// 53-bit uniform in [0,1) from two 32-bit words, the way CPython's random.random() packs
+// its two Mersenne words: (a >> 5) * 2^26 + (b >> 6), scaled by 2^-53.
+NV_HD double nv_u53(uint32_t a, uint32_t b) {
+  return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+// Draw number `draw` of agent `agent`: one (ux, uy) pair per Philox block.
+NV_HD void nv_goal_uniforms(uint64_t seed, uint64_t agent, uint32_t draw, double* ux, double* uy) {
+  uint32_t o[4];
+  nv_philox4x32_10(draw, 0u, (uint32_t)agent, (uint32_t)(agent >> 32),
+                   (uint32_t)seed, (uint32_t)(seed >> 32), o);
+  *ux = nv_u53(o[0], o[1]);
+  *uy = nv_u53(o[2], o[3]);
+}
+
+// ---------------------------------------------------------------------------------------
+// Row K — differential drive over one LiDAR period.  The reference's fake node splits
+// (v, w) into wheel speeds and recombines them (turtlebot3_fake.cpp:117-118,150-151);
+// algebraically ds = v dt, dth = w dt, which is what is integrated here in midpoint form
+// (:157-163).  Heading is kept wrapped to (-pi, pi] so the trig argument stays small.
+// ---------------------------------------------------------------------------------------
+NV_HD void nv_drive(double* x, double* y, double* th, double v, double w, double dt) {
+  double ds = v * dt;
+  double dth = w * dt;
+  double s, c;
+  nv_sincos(*th + dth / 2.0, &s, &c);
+  *x = *x + ds * c;
+  *y = *y + ds * s;
+  double t = *th + dth;
+  if (t > NV_PI) t = t - NV_TWO_PI;
+  else if (t <= -NV_PI) t = t + NV_TWO_PI;
+  *th = t;
+}
+
+// ---------------------------------------------------------------------------------------
+// Row R — one beam against one wall segment p0 -> p1.  Returns the hit distance along the
+// unit ray (ox,oy)+(dx,dy) t, or +inf when the ray misses.
+// ---------------------------------------------------------------------------------------
+NV_HD double nv_ray_segment(double ox, double oy, double dx, double dy,
+                            double x0, double y0, double x1, double y1) {
+  double ex = x1 - x0, ey = y1 - y0;
+  double den = dx * ey - dy * ex;
+  double wx = x0 - ox, wy = y0 - oy;
+  double tn = wx * ey - wy * ex;  // t = tn / den
+  double un = wx * dy - wy * dx;  // u = un / den
+  if (den == 0.0) return NV_INF;
+  if (den < 0.0) { den = -den; tn = -tn; un = -un; }
+  if (tn < 0.0 || un < 0.0 || un > den) return NV_INF;
+  return tn / den;
+}
+
+// Range gates of the Gazebo ray sensor: beyond max -> +inf, below min -> -inf
+// (gazebo.xacro:117-119); the value then travels as a float32 (sensor_msgs/LaserScan).
+NV_HD double nv_range_gate(double t, double rmin, double rmax) {
+  if (t > rmax) return NV_INF;
+  if (t < rmin) return -NV_INF;
+  return (double)(float)t;
+}
+
+#endif  // NAVSIM_MATH_H_

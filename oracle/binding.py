@@ -1,0 +1,128 @@
+"""binding.py — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+numpy-facing wrapper of oracle/liboracle.so (navsim_oracle.c): N reference environments
+stepped on the CPU.  Imported only by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liboracle.so")
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(HERE, "navsim_oracle.c")
+    deps = [src, os.path.join(HERE, "..", "include", "navsim.h"),
+            os.path.join(HERE, "..", "navbot_ppo_b200", "csrc", "navsim_math.h")]
+    stale = force or not os.path.exists(LIB_PATH) or any(
+        os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps)
+    if stale:
+        subprocess.run(["make", "-C", HERE, "-B", "liboracle.so"], check=True, stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+class _State(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in
+                ("x", "y", "th", "gx", "gy", "past", "pa0", "pa1", "steps", "draws", "ep_ret", "ep_path", "last_move")]
+
+
+class _Map(ctypes.Structure):
+    _fields_ = [("seg", ctypes.c_void_p), ("S", ctypes.c_int32), ("bc", ctypes.c_void_p), ("bs", ctypes.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        L = ctypes.CDLL(LIB_PATH)
+        vp, d, i32, u32, u64 = ctypes.c_void_p, ctypes.c_double, ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint64
+        L.oracle_reset.argtypes = [vp, vp, vp, vp, vp]
+        L.oracle_reset.restype = None
+        L.oracle_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int]
+        L.oracle_step.restype = ctypes.c_int
+        L.oracle_scripted_actions.argtypes = [u64, ctypes.c_int64, i32, i32, vp]
+        L.oracle_scripted_actions.restype = None
+        L.shim_beam_table.argtypes = [i32, d, d, vp, vp]
+        L.shim_beam_table.restype = None
+        L.shim_scan.argtypes = [d, d, d, vp, i32, i32, vp, vp, d, d, d, vp]
+        L.shim_scan.restype = None
+        for name in ("oracle_nv_sin", "oracle_nv_cos", "oracle_nv_atan"):
+            getattr(L, name).argtypes = [d]
+            getattr(L, name).restype = d
+        L.oracle_nv_pyround.argtypes = [d, ctypes.c_int]
+        L.oracle_nv_pyround.restype = d
+        L.ref_pyround.argtypes = [d, ctypes.c_int]
+        L.ref_pyround.restype = d
+        L.ref_odometry.argtypes = [d, d, d, d, d, d, vp, vp, vp]
+        L.ref_odometry.restype = None
+        L.oracle_philox.argtypes = [u32, u32, u32, u32, u32, u32, vp]
+        L.oracle_philox.restype = None
+        _lib = L
+    return _lib
+
+
+_FIELDS = [("x", np.float64), ("y", np.float64), ("th", np.float64), ("gx", np.float64), ("gy", np.float64),
+           ("past", np.float64), ("pa0", np.float32), ("pa1", np.float32), ("steps", np.int32),
+           ("draws", np.uint32), ("ep_ret", np.float32), ("ep_path", np.float32), ("last_move", np.float32)]
+
+
+class OracleSim:
+    """N independent reference environments on the CPU (state as numpy SoA arrays)."""
+
+    def __init__(self, cfg, segments, nthreads: int = 1):
+        self.cfg = cfg  # a navbot_ppo_b200._capi.NavsimCfg (the public C struct)
+        self.n = int(cfg.num_agents)
+        self.nthreads = nthreads
+        self.seg = np.ascontiguousarray(segments, dtype=np.float64).reshape(-1, 4)
+        nb = int(cfg.num_beams)
+        self.bc, self.bs = np.zeros(nb), np.zeros(nb)
+        lib().shim_beam_table(nb, cfg.fov_min, cfg.fov_max, self.bc.ctypes.data, self.bs.ctypes.data)
+        self.map = _Map(self.seg.ctypes.data, len(self.seg), self.bc.ctypes.data, self.bs.ctypes.data)
+        self.arr = {name: np.zeros(self.n, dtype=dt) for name, dt in _FIELDS}
+        self.state = _State(*[self.arr[name].ctypes.data for name, _ in _FIELDS])
+        self.stats = None
+
+    def reset(self, mask=None):
+        obs = np.zeros((self.n, 16))
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        lib().oracle_reset(ctypes.byref(self.cfg), ctypes.byref(self.map), ctypes.byref(self.state),
+                           None if m is None else m.ctypes.data, obs.ctypes.data)
+        return obs
+
+    def step(self, act, stats=None):
+        act = np.ascontiguousarray(act, dtype=np.float32).reshape(self.n, 2)
+        obs = np.zeros((self.n, 16))
+        rew = np.zeros(self.n)
+        done = np.zeros(self.n, np.uint8)
+        arrive = np.zeros(self.n, np.uint8)
+        trunc = np.zeros(self.n, np.uint8)
+        lib().oracle_step(ctypes.byref(self.cfg), ctypes.byref(self.map), ctypes.byref(self.state), act.ctypes.data,
+                          obs.ctypes.data, rew.ctypes.data, done.ctypes.data, arrive.ctypes.data, trunc.ctypes.data,
+                          None if stats is None else ctypes.byref(stats), self.nthreads)
+        return obs, rew, done, arrive, trunc
+
+    def scan(self):
+        nb = int(self.cfg.num_beams)
+        out = np.zeros((self.n, nb))
+        c = self.cfg
+        for i in range(self.n):
+            lib().shim_scan(self.arr["x"][i], self.arr["y"][i], self.arr["th"][i], self.seg.ctypes.data, len(self.seg), nb,
+                            self.bc.ctypes.data, self.bs.ctypes.data, c.lidar_offset_x, c.lidar_min, c.lidar_max,
+                            out[i].ctypes.data)
+        return out
+
+
+def scripted_actions(action_seed: int, agent_id_offset: int, step: int, n: int) -> np.ndarray:
+    act = np.zeros((n, 2), np.float32)
+    lib().oracle_scripted_actions(action_seed, agent_id_offset, step, n, act.ctypes.data)
+    return act

@@ -1,0 +1,63 @@
+"""CPU: the C restatement (oracle/navsim_oracle.c) against golden traces produced by the
+reference's own Env code (oracle/make_golden.py).  This is what pins the oracle."""
+import numpy as np
+import pytest
+
+from oracle import binding
+from tests.helpers import cfg_from_golden, golden
+
+
+@pytest.mark.parametrize("name", ["env_rollout_stage_1", "env_rollout_stage_2", "env_rollout_stage_1_eval"])
+def test_oracle_reproduces_reference_rollout(name):
+    g = golden(name)
+    cfg = cfg_from_golden(g, auto_reset=1)
+    sim = binding.OracleSim(cfg, g["segments"])
+    obs0 = sim.reset()
+    np.testing.assert_array_equal(obs0, g["obs0"])
+    T = g["act"].shape[0]
+    for t in range(T):
+        obs, rew, done, arrive, trunc = sim.step(g["act"][t])
+        np.testing.assert_array_equal(done, g["done"][t].astype(np.uint8), err_msg=f"done t={t}")
+        np.testing.assert_array_equal(arrive, g["arrive"][t].astype(np.uint8), err_msg=f"arrive t={t}")
+        np.testing.assert_array_equal(trunc, g["trunc"][t].astype(np.uint8), err_msg=f"trunc t={t}")
+        # same libm, same physics header: the restatement matches the reference bit for bit
+        np.testing.assert_array_equal(obs, g["obs_next"][t], err_msg=f"obs t={t}")
+        np.testing.assert_array_equal(rew, g["rew"][t], err_msg=f"rew t={t}")
+        for k in ("x", "y", "th", "gx", "gy", "past"):
+            np.testing.assert_array_equal(sim.arr[k], g[k][t], err_msg=f"{k} t={t}")
+        np.testing.assert_array_equal(sim.arr["draws"], g["draws"][t])
+
+
+def test_oracle_reproduces_reference_raw_env():
+    """auto_reset off: arrival respawns the goal inside step (environment_new.py:245-267),
+    collisions are followed by an explicit Env.reset()."""
+    g = golden("env_raw_stage_1")
+    cfg = cfg_from_golden(g, auto_reset=0)
+    sim = binding.OracleSim(cfg, g["segments"])
+    np.testing.assert_array_equal(sim.reset(), g["obs0"])
+    for t in range(g["act"].shape[0]):
+        obs, rew, done, arrive, _ = sim.step(g["act"][t])
+        np.testing.assert_array_equal(obs, g["obs"][t])
+        np.testing.assert_array_equal(rew, g["rew"][t])
+        np.testing.assert_array_equal(done, g["done"][t].astype(np.uint8))
+        np.testing.assert_array_equal(arrive, g["arrive"][t].astype(np.uint8))
+        mask = g["reset_mask"][t].astype(np.uint8)
+        if mask.any():
+            ro = sim.reset(mask)
+            sel = mask.astype(bool)
+            np.testing.assert_array_equal(ro[sel], g["obs_reset"][t][sel])
+        for k in ("gx", "gy", "past"):
+            np.testing.assert_array_equal(sim.arr[k], g[k][t], err_msg=f"{k} t={t}")
+        np.testing.assert_array_equal(sim.arr["draws"], g["draws"][t])
+
+
+def test_golden_covers_the_edge_cases():
+    g = golden("env_rollout_stage_2")
+    assert g["done"].sum() > 10 and g["arrive"].sum() > 3 and g["trunc"].sum() > 10
+    g1 = golden("env_rollout_stage_1")
+    assert g1["done"].sum() > 10 and g1["arrive"].sum() > 10 and g1["trunc"].sum() > 10
+    # all four quadrants + wrap of the bearing feature were visited
+    rel = g1["obs_next"][..., 14]
+    assert rel.min() < 0.1 and rel.max() > 0.9
+    diff = g1["obs_next"][..., 15]
+    assert diff.min() < -0.9 and diff.max() > 0.9
