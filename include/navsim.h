@@ -104,8 +104,12 @@ int navsim_create(navsim_t** out, const navsim_cfg* cfg);
 int navsim_destroy(navsim_t* h);
 
 /* Static obstacle map = what the .world file gives Gazebo (turtlebot3_stage_1.launch:8).
- * seg_host: S rows of {x0, y0, x1, y1} in metres (host doubles). */
-int navsim_set_map(navsim_t* h, const double* seg_host, int32_t num_segments);
+ * seg_host: S rows of {x0, y0, x1, y1} in metres (host doubles).
+ * flags: NAVSIM_MAP_CLOSED_BOXES when the segments are the counter-clockwise edges of closed
+ * convex obstacles (SDF collision boxes): walls seen from behind are then skipped.  Pass 0
+ * for free-standing two-sided walls. */
+#define NAVSIM_MAP_CLOSED_BOXES 1
+int navsim_set_map(navsim_t* h, const double* seg_host, int32_t num_segments, int32_t flags);
 
 /* Env.reset (environment_new.py:312-382) for every agent whose mask byte is non-zero
  * (mask_dev == NULL: all agents).  Writes obs[N,16] rows of the agents that were reset. */

@@ -12,6 +12,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libnavbot_b200.so")
 
 MAX_RECTS = 8
+MAP_CLOSED_BOXES = 1
 OBS_DIM = 16
 ACT_DIM = 2
 
@@ -66,7 +67,7 @@ NAVSIM_SYMBOLS = {
     "navsim_default_cfg": (ctypes.c_int, [ctypes.POINTER(NavsimCfg), _i32]),
     "navsim_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.POINTER(NavsimCfg)]),
     "navsim_destroy": (ctypes.c_int, [_vp]),
-    "navsim_set_map": (ctypes.c_int, [_vp, _vp, _i32]),
+    "navsim_set_map": (ctypes.c_int, [_vp, _vp, _i32, _i32]),
     "navsim_reset": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "navsim_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "navsim_reset_host": (ctypes.c_int, [_vp, _vp, _vp]),

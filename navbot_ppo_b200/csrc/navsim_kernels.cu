@@ -51,7 +51,7 @@ int fail(int code, const std::string& msg) {
 
 // Scalars the kernels need, passed by value (fits the 4 KB kernel-parameter window).
 struct SimConst {
-  int32_t N, B, S, max_steps, auto_reset, n_reset_rects, n_respawn_rects;
+  int32_t N, B, S, max_steps, auto_reset, n_reset_rects, n_respawn_rects, closed_boxes;
   uint64_t seed;
   int64_t agent_off;
   double dt, off_x, rmin, rmax, collide, arrive_thr, r_scale, r_collide, r_arrive, diag;
@@ -82,6 +82,12 @@ struct Agent {
 
 constexpr int kObsPad = NAVSIM_OBS_DIM + 1;  // +1 float: conflict-free column access
 
+// Obstacle set as staged into shared memory: S packed wall records (8 floats each), then the
+// beam table (B cosines, B sines), fp32, padded to the 16-byte granule of cp.async.bulk.
+__host__ __device__ inline uint32_t map_bytes_of(int B, int S) {
+  return (uint32_t)(((size_t)(NV_SEG_FLOATS * S + 2 * B) * sizeof(float) + 15) & ~(size_t)15);
+}
+
 // ----------------------------------------------------------------------------------------
 // TMA bulk copy of the obstacle set (global -> shared), completion on an mbarrier.
 // ----------------------------------------------------------------------------------------
@@ -89,7 +95,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
-__device__ __forceinline__ void stage_map(double* s_map, const double* g_map, uint32_t bytes, uint64_t* bar) {
+__device__ __forceinline__ void stage_map(float* s_map, const float* g_map, uint32_t bytes, uint64_t* bar) {
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -147,37 +153,71 @@ __device__ __forceinline__ void odom_features(double x, double y, double th, dou
 }
 
 // LaserScan of the pose + getState + observation assembly (:183-207, :289-301).
-// s_bc/s_bs: beam direction table, s_seg: S x {x0,y0,x1,y1}, all in shared memory.
-__device__ __forceinline__ void observe(const SimConst& c, const double* s_bc, const double* s_bs,
-                                        const double* s_seg, const Agent& a, float pa0, float pa1,
+// s_seg: S packed wall records (navsim_math.h), s_bc/s_bs: beam direction table, fp32, all in
+// shared memory.
+// KB > 0: beam count known at compile time -> segment-major loop with the per-beam best
+// inverse hit distances in registers (the per-wall setup and culling run once per wall);
+// KB == 0: any beam count, beam-major.  Both orders visit a beam's segments 0..S-1 in the
+// same order with the same arithmetic, so they agree bit for bit with the host build.
+template <int KB>
+__device__ __forceinline__ void observe(const SimConst& c, const float* s_seg, const float* s_bc, const float* s_bs,
+                                        const Agent& a, float pa0, float pa1,
                                         float* obs /* kObsPad row in smem */, bool* done, bool* arrive,
                                         double* dist) {
   double s, co;
   nv_sincos(a.th, &s, &co);
-  const double ox = a.x + c.off_x * co, oy = a.y + c.off_x * s;
-  double mn = NV_INF;
-  int pick = 0;                                     // next lidar feature to emit
-  int next_idx = 0;                                 // int(pick * L / 10), :293
-  for (int b = 0; b < c.B; ++b) {
-    const double bc = s_bc[b], bs = s_bs[b];
-    const double dx = co * bc - s * bs;
-    const double dy = s * bc + co * bs;
-    double best = NV_INF;
-    for (int k = 0; k < c.S; ++k) {
-      const double t = nv_ray_segment(ox, oy, dx, dy, s_seg[4 * k], s_seg[4 * k + 1], s_seg[4 * k + 2],
-                                      s_seg[4 * k + 3]);
-      best = (t < best) ? t : best;
+  const float ox = (float)(a.x + c.off_x * co), oy = (float)(a.y + c.off_x * s);
+  const float ch = (float)co, sh = (float)s;
+  const float rmin = (float)c.rmin, rmax = (float)c.rmax;
+  float mn = NV_INF_F;
+  if (KB > 0) {
+    float dx[KB > 0 ? KB : 1], dy[KB > 0 ? KB : 1], q[KB > 0 ? KB : 1];
+#pragma unroll
+    for (int b = 0; b < KB; ++b) {
+      nv_beam_dir(ch, sh, s_bc[b], s_bs[b], &dx[b], &dy[b]);
+      q[b] = 0.0f;
     }
-    double r = nv_range_gate(best, c.rmin, c.rmax);
-    if (r == NV_INF) r = 3.5;                       // :193-194
-    mn = (r < mn) ? r : mn;
-    while (pick < NAVSIM_LIDAR_FEATS && next_idx == b) {
-      obs[pick] = (float)(r / 3.5);                 // :289
-      ++pick;
-      next_idx = (int)((double)(pick * c.B) / 10.0);
+    for (int k = 0; k < c.S; ++k) {
+      nv_seg_view v;
+      if (!nv_seg_setup(s_seg + NV_SEG_FLOATS * k, ox, oy, c.closed_boxes, &v)) continue;
+#pragma unroll
+      for (int b = 0; b < KB; ++b) q[b] = nv_ray_q(&v, dx[b], dy[b], q[b]);
+    }
+#pragma unroll
+    for (int b = 0; b < KB; ++b) {
+      float r = nv_range_from_q(q[b], rmin, rmax);
+      if (r == NV_INF_F) r = 3.5f;                  // :193-194
+      mn = (r < mn) ? r : mn;
+      if (KB == NAVSIM_LIDAR_FEATS) obs[b] = r / 3.5f;  // :289, idx_i == i when L == 10
+      else q[b] = r;
+    }
+    if (KB != NAVSIM_LIDAR_FEATS) {
+#pragma unroll
+      for (int i = 0; i < NAVSIM_LIDAR_FEATS; ++i) {
+        const int idx = (int)((double)(i * KB) / 10.0);  // :293
+        float r = 0.f;
+#pragma unroll
+        for (int b = 0; b < KB; ++b) r = (b == idx) ? q[b] : r;
+        obs[i] = r / 3.5f;
+      }
+    }
+  } else {
+    int pick = 0;                                   // next lidar feature to emit
+    int next_idx = 0;                               // int(pick * L / 10), :293
+    for (int b = 0; b < c.B; ++b) {
+      float dxb, dyb;
+      nv_beam_dir(ch, sh, s_bc[b], s_bs[b], &dxb, &dyb);
+      float r = nv_range_from_q(nv_beam_q(ox, oy, dxb, dyb, s_seg, c.S, c.closed_boxes), rmin, rmax);
+      if (r == NV_INF_F) r = 3.5f;                  // :193-194
+      mn = (r < mn) ? r : mn;
+      while (pick < NAVSIM_LIDAR_FEATS && next_idx == b) {
+        obs[pick] = r / 3.5f;                       // :289
+        ++pick;
+        next_idx = (int)((double)(pick * c.B) / 10.0);
+      }
     }
   }
-  *done = (c.collide > mn) && (mn > 0.0);           // :200
+  *done = (c.collide > (double)mn) && (mn > 0.0f);  // :200
   const double ddx = a.gx - a.x, ddy = a.gy - a.y;
   const double d = sqrt(ddx * ddx + ddy * ddy);     // :203
   *arrive = (d <= c.arrive_thr);                    // :204
@@ -186,10 +226,10 @@ __device__ __forceinline__ void observe(const SimConst& c, const double* s_bc, c
   odom_features(a.x, a.y, a.th, a.gx, a.gy, &yaw, &rel_theta, &diff);
   obs[10] = pa0;                                    // :299-300
   obs[11] = pa1;
-  obs[12] = (float)(d / c.diag);                    // :301
-  obs[13] = (float)(yaw / 360.0);
-  obs[14] = (float)(rel_theta / 360.0);
-  obs[15] = (float)(diff / 180.0);
+  obs[12] = (float)d / (float)c.diag;               // :301
+  obs[13] = (float)yaw / 360.0f;
+  obs[14] = (float)rel_theta / 360.0f;
+  obs[15] = (float)diff / 180.0f;
 }
 
 __device__ __forceinline__ bool in_rects(const double* r, int n, double gx, double gy) {
@@ -213,8 +253,9 @@ __device__ __forceinline__ void sample_goal(const SimConst& c, const double* rec
 }
 
 // Env.reset (:312-382) for one agent; obs row filled with the first observation.
-__device__ __forceinline__ void reset_agent(const SimConst& c, const double* s_bc, const double* s_bs,
-                                            const double* s_seg, uint64_t agent, Agent* a, float* obs) {
+template <int KB>
+__device__ __forceinline__ void reset_agent(const SimConst& c, const float* s_seg, const float* s_bc,
+                                            const float* s_bs, uint64_t agent, Agent* a, float* obs) {
   a->x = c.sx; a->y = c.sy; a->th = c.sth;                       // reset_world, :325
   sample_goal(c, c.reset_rects, c.n_reset_rects, agent, a);
   const double dx = a->gx - a->x, dy = a->gy - a->y;
@@ -222,7 +263,7 @@ __device__ __forceinline__ void reset_agent(const SimConst& c, const double* s_b
   a->pa0 = 0.f; a->pa1 = 0.f; a->steps = 0;
   a->ep_ret = 0.f; a->ep_path = 0.f; a->last_move = 0.f;
   bool done, arrive; double d;
-  observe(c, s_bc, s_bs, s_seg, *a, 0.f, 0.f, obs, &done, &arrive, &d);
+  observe<KB>(c, s_seg, s_bc, s_bs, *a, 0.f, 0.f, obs, &done, &arrive, &d);
 }
 
 __device__ __forceinline__ void load_agent(const SimState& st, int i, Agent* a) {
@@ -260,22 +301,22 @@ extern __shared__ __align__(16) unsigned char dyn_smem[];
 // ----------------------------------------------------------------------------------------
 // Env.step for all agents.  SCRIPTED: actions drawn on device (benchmark driver).
 // ----------------------------------------------------------------------------------------
-template <bool SCRIPTED>
-__global__ void __launch_bounds__(128) navsim_step_kernel(SimConst c, SimState st, const double* __restrict__ g_map,
+template <bool SCRIPTED, int KB>
+__global__ void __launch_bounds__(128) navsim_step_kernel(SimConst c, SimState st, const float* __restrict__ g_map,
                                                           const float* __restrict__ act, float* __restrict__ obs,
                                                           float* __restrict__ rew, uint8_t* __restrict__ done_o,
                                                           uint8_t* __restrict__ arrive_o,
                                                           uint8_t* __restrict__ trunc_o, DevStats* stats,
                                                           uint64_t action_seed, uint32_t script_step) {
-  // shared: [mbarrier 16 B][map: 2B + 4S doubles][obs tile: blockDim x kObsPad floats]
+  // shared: [mbarrier 16 B][map: 8S + 2B floats, padded to 16 B][obs tile: blockDim x kObsPad floats]
   uint64_t* bar = reinterpret_cast<uint64_t*>(dyn_smem);
-  double* s_map = reinterpret_cast<double*>(dyn_smem + 16);
-  const uint32_t map_bytes = (uint32_t)((2 * c.B + 4 * c.S) * sizeof(double));
-  float* s_obs = reinterpret_cast<float*>(dyn_smem + 16 + ((map_bytes + 15u) & ~15u));
+  float* s_map = reinterpret_cast<float*>(dyn_smem + 16);
+  const uint32_t map_bytes = map_bytes_of(c.B, c.S);
+  float* s_obs = reinterpret_cast<float*>(dyn_smem + 16 + map_bytes);
   stage_map(s_map, g_map, map_bytes, bar);
-  const double* s_bc = s_map;
-  const double* s_bs = s_map + c.B;
-  const double* s_seg = s_map + 2 * c.B;
+  const float* s_seg = s_map;
+  const float* s_bc = s_map + NV_SEG_FLOATS * c.S;
+  const float* s_bs = s_bc + c.B;
 
   const int row0 = blockIdx.x * blockDim.x;
   const int i = row0 + threadIdx.x;
@@ -301,10 +342,10 @@ __global__ void __launch_bounds__(128) navsim_step_kernel(SimConst c, SimState s
     nv_drive(&a.x, &a.y, &a.th, (double)a0 / 4.0, (double)a1, c.dt);  // :276-286
     {
       const double mx = a.x - px, my = a.y - py;
-      a.last_move = (float)sqrt(mx * mx + my * my);
+      a.last_move = sqrtf((float)(mx * mx + my * my));
     }
     bool done, arrive; double d;
-    observe(c, s_bc, s_bs, s_seg, a, a.pa0, a.pa1, my_obs, &done, &arrive, &d);  // :288-301
+    observe<KB>(c, s_seg, s_bc, s_bs, a, a.pa0, a.pa1, my_obs, &done, &arrive, &d);  // :288-301
     double reward = c.r_scale * (a.past - d);                        // :211-213
     a.past = d;                                                      // :214
     if (done) reward = c.r_collide;                                  // :216-217
@@ -330,7 +371,7 @@ __global__ void __launch_bounds__(128) navsim_step_kernel(SimConst c, SimState s
         atomicAdd(&stats->return_sum, (double)a.ep_ret);
         atomicAdd(&stats->length_sum, (double)a.steps);
         atomicAdd(&stats->path_sum, (double)a.ep_path);
-        reset_agent(c, s_bc, s_bs, s_seg, agent, &a, my_obs);
+        reset_agent<KB>(c, s_seg, s_bc, s_bs, agent, &a, my_obs);
         goal_changed = true;
       }
     } else if (arrive) {                                             // :245-267
@@ -348,13 +389,13 @@ __global__ void __launch_bounds__(128) navsim_step_kernel(SimConst c, SimState s
 }
 
 // Env.reset for the masked agents.
-__global__ void __launch_bounds__(128) navsim_reset_kernel(SimConst c, SimState st, const double* __restrict__ g_map,
+__global__ void __launch_bounds__(128) navsim_reset_kernel(SimConst c, SimState st, const float* __restrict__ g_map,
                                                            const uint8_t* __restrict__ mask,
                                                            float* __restrict__ obs) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(dyn_smem);
-  double* s_map = reinterpret_cast<double*>(dyn_smem + 16);
-  const uint32_t map_bytes = (uint32_t)((2 * c.B + 4 * c.S) * sizeof(double));
-  float* s_obs = reinterpret_cast<float*>(dyn_smem + 16 + ((map_bytes + 15u) & ~15u));
+  float* s_map = reinterpret_cast<float*>(dyn_smem + 16);
+  const uint32_t map_bytes = map_bytes_of(c.B, c.S);
+  float* s_obs = reinterpret_cast<float*>(dyn_smem + 16 + map_bytes);
   stage_map(s_map, g_map, map_bytes, bar);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.N) return;
@@ -362,7 +403,8 @@ __global__ void __launch_bounds__(128) navsim_reset_kernel(SimConst c, SimState 
   float* my_obs = s_obs + threadIdx.x * kObsPad;
   Agent a;
   load_agent(st, i, &a);
-  reset_agent(c, s_map, s_map + c.B, s_map + 2 * c.B, (uint64_t)(c.agent_off + i), &a, my_obs);
+  reset_agent<0>(c, s_map, s_map + NV_SEG_FLOATS * c.S, s_map + NV_SEG_FLOATS * c.S + c.B,
+                 (uint64_t)(c.agent_off + i), &a, my_obs);
   store_agent(st, i, a, true);
   if (obs) {
     float4* dst = reinterpret_cast<float4*>(obs + (size_t)i * NAVSIM_OBS_DIM);
@@ -371,27 +413,23 @@ __global__ void __launch_bounds__(128) navsim_reset_kernel(SimConst c, SimState 
 }
 
 // LaserScan only (parity tests of row R): ranges[N, B] doubles with the +-inf gates.
-__global__ void __launch_bounds__(128) navsim_scan_kernel(SimConst c, SimState st, const double* __restrict__ g_map,
+__global__ void __launch_bounds__(128) navsim_scan_kernel(SimConst c, SimState st, const float* __restrict__ g_map,
                                                           double* __restrict__ ranges) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(dyn_smem);
-  double* s_map = reinterpret_cast<double*>(dyn_smem + 16);
-  const uint32_t map_bytes = (uint32_t)((2 * c.B + 4 * c.S) * sizeof(double));
-  stage_map(s_map, g_map, map_bytes, bar);
-  const double* s_bc = s_map; const double* s_bs = s_map + c.B; const double* s_seg = s_map + 2 * c.B;
+  float* s_map = reinterpret_cast<float*>(dyn_smem + 16);
+  stage_map(s_map, g_map, map_bytes_of(c.B, c.S), bar);
+  const float* s_seg = s_map; const float* s_bc = s_map + NV_SEG_FLOATS * c.S; const float* s_bs = s_bc + c.B;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.N) return;
   double s, co;
   nv_sincos(st.th[i], &s, &co);
-  const double ox = st.x[i] + c.off_x * co, oy = st.y[i] + c.off_x * s;
+  const float ox = (float)(st.x[i] + c.off_x * co), oy = (float)(st.y[i] + c.off_x * s);
+  const float ch = (float)co, sh = (float)s;
   for (int b = 0; b < c.B; ++b) {
-    const double dx = co * s_bc[b] - s * s_bs[b];
-    const double dy = s * s_bc[b] + co * s_bs[b];
-    double best = NV_INF;
-    for (int k = 0; k < c.S; ++k) {
-      const double t = nv_ray_segment(ox, oy, dx, dy, s_seg[4 * k], s_seg[4 * k + 1], s_seg[4 * k + 2], s_seg[4 * k + 3]);
-      best = (t < best) ? t : best;
-    }
-    ranges[(size_t)i * c.B + b] = nv_range_gate(best, c.rmin, c.rmax);
+    float dx, dy;
+    nv_beam_dir(ch, sh, s_bc[b], s_bs[b], &dx, &dy);
+    ranges[(size_t)i * c.B + b] = (double)nv_range_from_q(nv_beam_q(ox, oy, dx, dy, s_seg, c.S, c.closed_boxes),
+                                                          (float)c.rmin, (float)c.rmax);
   }
 }
 
@@ -404,7 +442,7 @@ struct navsim {
   navsim_cfg cfg;
   SimConst c;
   SimState st;
-  double* d_map = nullptr;       // [2B + 4S] doubles: beam cos, beam sin, segments
+  float* d_map = nullptr;        // [8S + 2B] floats: packed wall records, beam cos, beam sin
   int32_t S = 0;
   DevStats* d_stats = nullptr;
   cudaStream_t own_stream = nullptr;
@@ -421,8 +459,7 @@ struct navsim {
 namespace {
 
 size_t smem_bytes(const navsim* h) {
-  const size_t map_bytes = (size_t)(2 * h->c.B + 4 * h->c.S) * sizeof(double);
-  return 16 + ((map_bytes + 15) & ~(size_t)15) + (size_t)h->block * kObsPad * sizeof(float);
+  return 16 + (size_t)map_bytes_of(h->c.B, h->c.S) + (size_t)h->block * kObsPad * sizeof(float);
 }
 
 int grid_of(const navsim* h) { return (h->c.N + h->block - 1) / h->block; }
@@ -436,12 +473,15 @@ int check_ready(const navsim* h) {
 int launch_step(navsim* h, const float* act, float* obs, float* rew, uint8_t* done, uint8_t* arrive, uint8_t* trunc,
                 cudaStream_t s, bool scripted, uint64_t action_seed) {
   const size_t smem = smem_bytes(h);
-  if (scripted)
-    navsim_step_kernel<true><<<grid_of(h), h->block, smem, s>>>(h->c, h->st, h->d_map, act, obs, rew, done, arrive,
-                                                                trunc, h->d_stats, action_seed, h->script_step++);
-  else
-    navsim_step_kernel<false><<<grid_of(h), h->block, smem, s>>>(h->c, h->st, h->d_map, act, obs, rew, done, arrive,
-                                                                 trunc, h->d_stats, 0ull, 0u);
+  const dim3 grid(grid_of(h)), block(h->block);
+#define NAVSIM_LAUNCH(SCR, KB)                                                                               \
+  navsim_step_kernel<SCR, KB><<<grid, block, smem, s>>>(h->c, h->st, h->d_map, act, obs, rew, done, arrive, trunc, \
+                                                        h->d_stats, action_seed, script_step)
+  const uint32_t script_step = scripted ? h->script_step++ : 0u;
+  const bool ten = (h->c.B == 10);  // the reference's sensor (gazebo.xacro:111) gets the unrolled path
+  if (scripted) { if (ten) NAVSIM_LAUNCH(true, 10); else NAVSIM_LAUNCH(true, 0); }
+  else          { if (ten) NAVSIM_LAUNCH(false, 10); else NAVSIM_LAUNCH(false, 0); }
+#undef NAVSIM_LAUNCH
   h->launches++;
   CUDA_TRY(cudaGetLastError());
   return NAVSIM_OK;
@@ -583,33 +623,39 @@ int navsim_destroy(navsim_t* h) {
   return NAVSIM_OK;
 }
 
-int navsim_set_map(navsim_t* h, const double* seg_host, int32_t num_segments) {
+int navsim_set_map(navsim_t* h, const double* seg_host, int32_t num_segments, int32_t flags) {
   if (!h || !seg_host) return fail(NAVSIM_EINVAL, "null argument");
   if (num_segments < 1) return fail(NAVSIM_EINVAL, "a map needs at least one segment");
   const int B = h->c.B;
-  const size_t n = (size_t)2 * B + (size_t)4 * num_segments;
-  if (16 + n * sizeof(double) + 16 + (size_t)h->block * kObsPad * sizeof(float) > 200 * 1024)
+  const size_t bytes = map_bytes_of(B, num_segments);
+  if (16 + bytes + (size_t)h->block * kObsPad * sizeof(float) > 200 * 1024)
     return fail(NAVSIM_EINVAL, "map does not fit in shared memory");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
-  double* host = new (std::nothrow) double[n];
+  float* host = new (std::nothrow) float[bytes / sizeof(float)]();
   if (!host) return fail(NAVSIM_ENOMEM, "host allocation failed");
+  for (int k = 0; k < num_segments; ++k) nv_pack_segment(seg_host + 4 * k, h->cfg.lidar_max, host + NV_SEG_FLOATS * k);
   // beam direction table, gazebo.xacro:111-114: B samples over [fov_min, fov_max] inclusive
   for (int i = 0; i < B; ++i) {
     const double a = (B > 1) ? h->cfg.fov_min + (double)i * ((h->cfg.fov_max - h->cfg.fov_min) / (double)(B - 1))
                              : 0.5 * (h->cfg.fov_min + h->cfg.fov_max);
-    nv_sincos(a, &host[B + i], &host[i]);
+    double sn, cs;
+    nv_sincos(a, &sn, &cs);
+    host[NV_SEG_FLOATS * num_segments + i] = (float)cs;
+    host[NV_SEG_FLOATS * num_segments + B + i] = (float)sn;
   }
-  memcpy(host + 2 * B, seg_host, (size_t)4 * num_segments * sizeof(double));
   if (h->d_map) { cudaFree(h->d_map); h->d_map = nullptr; }
-  cudaError_t e = cudaMalloc(&h->d_map, ((n * sizeof(double) + 15) & ~(size_t)15));
-  if (e == cudaSuccess) e = cudaMemcpy(h->d_map, host, n * sizeof(double), cudaMemcpyHostToDevice);
+  cudaError_t e = cudaMalloc(&h->d_map, bytes);
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_map, host, bytes, cudaMemcpyHostToDevice);
   delete[] host;
   if (e != cudaSuccess) return fail(NAVSIM_ECUDA, std::string("set_map: ") + cudaGetErrorString(e));
   h->S = num_segments;
   h->c.S = num_segments;
+  h->c.closed_boxes = (flags & NAVSIM_MAP_CLOSED_BOXES) ? 1 : 0;
   const size_t smem = smem_bytes(h);
-  CUDA_TRY(cudaFuncSetAttribute(navsim_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CUDA_TRY(cudaFuncSetAttribute(navsim_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(cudaFuncSetAttribute(navsim_step_kernel<false, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(cudaFuncSetAttribute(navsim_step_kernel<true, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(cudaFuncSetAttribute(navsim_step_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(cudaFuncSetAttribute(navsim_step_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CUDA_TRY(cudaFuncSetAttribute(navsim_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CUDA_TRY(cudaFuncSetAttribute(navsim_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return NAVSIM_OK;

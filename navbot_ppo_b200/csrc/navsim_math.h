@@ -186,28 +186,96 @@ NV_HD void nv_drive(double* x, double* y, double* th, double v, double w, double
 }
 
 // ---------------------------------------------------------------------------------------
-// Row R — one beam against one wall segment p0 -> p1.  Returns the hit distance along the
-// unit ray (ox,oy)+(dx,dy) t, or +inf when the ray misses.
+// Row R — planar ray sensor, in fp32 like the float32 ranges a LaserScan carries (the
+// sensor's own resolution is 15 mm, gazebo.xacro:120).  The robot pose stays fp64; only
+// the sensor origin, the beam directions and the wall segments are rounded to fp32.
+//
+// A wall segment p0 -> p1 is packed as 8 floats
+//     {x0, y0, ex, ey,  mx, my, R2, lim}      e = p1 - p0, m = midpoint,
+//     R2 = (rmax + |e|/2)^2 (bounding-circle reach), lim = rmax * |e| (line reach).
+// For a ray o + t d:  w = p0 - o,  tn = w x e,  den = d x e,  un = w x d,
+//                     t = tn / den,  u = un / den, hit iff t >= 0 and 0 <= u <= 1.
+// tn (= |e| * signed distance from o to the wall's line) does not depend on the beam, so
+// the per-segment setup is done once for all beams:
+//   * range cull   — |tn| > lim or |m - o|^2 > R2: every hit would lie beyond rmax and be
+//                    gated to +inf anyway, so skipping the wall cannot change a scan;
+//   * back faces   — for maps made of closed convex boxes (edges counter-clockwise) a wall
+//                    seen from behind (tn >= 0) is always preceded by a front face;
+//   * orientation  — (w, e) are flipped so tn > 0 and a hit needs den > 0, and 1/tn is
+//                    formed once, so a beam tracks the nearest hit as the LARGEST inverse
+//                    distance q = den / tn with one multiply and one max per test.
+// u is accepted on [-eps, 1 + eps] so a ray through the shared corner of two box edges
+// cannot slip between them.  All products that feed a difference are explicit fmaf so the
+// host and device builds round identically whatever the contraction flags.
 // ---------------------------------------------------------------------------------------
-NV_HD double nv_ray_segment(double ox, double oy, double dx, double dy,
-                            double x0, double y0, double x1, double y1) {
-  double ex = x1 - x0, ey = y1 - y0;
-  double den = dx * ey - dy * ex;
-  double wx = x0 - ox, wy = y0 - oy;
-  double tn = wx * ey - wy * ex;  // t = tn / den
-  double un = wx * dy - wy * dx;  // u = un / den
-  if (den == 0.0) return NV_INF;
-  if (den < 0.0) { den = -den; tn = -tn; un = -un; }
-  if (tn < 0.0 || un < 0.0 || un > den) return NV_INF;
-  return tn / den;
+#define NV_SEG_FLOATS 8
+#define NV_SEG_EPS 1.0e-6f
+#define NV_INF_F (__builtin_huge_valf())
+#define NV_MAP_CLOSED_BOXES 1
+
+// {x0,y0,x1,y1} metres (double) -> packed fp32 record.
+NV_HD void nv_pack_segment(const double* xyxy, double rmax, float* out) {
+  double ex = xyxy[2] - xyxy[0], ey = xyxy[3] - xyxy[1];
+  double len = sqrt(ex * ex + ey * ey);
+  double reach = rmax * 1.001 + 0.5 * len + 1.0e-3;   // conservative by construction
+  out[0] = (float)xyxy[0];
+  out[1] = (float)xyxy[1];
+  out[2] = (float)ex;
+  out[3] = (float)ey;
+  out[4] = (float)(0.5 * (xyxy[0] + xyxy[2]));
+  out[5] = (float)(0.5 * (xyxy[1] + xyxy[3]));
+  out[6] = (float)(reach * reach);
+  out[7] = (float)((rmax * 1.001 + 1.0e-3) * len);
 }
 
-// Range gates of the Gazebo ray sensor: beyond max -> +inf, below min -> -inf
-// (gazebo.xacro:117-119); the value then travels as a float32 (sensor_msgs/LaserScan).
-NV_HD double nv_range_gate(double t, double rmin, double rmax) {
-  if (t > rmax) return NV_INF;
-  if (t < rmin) return -NV_INF;
-  return (double)(float)t;
+typedef struct nv_seg_view { float wx, wy, ex, ey, inv_tn; } nv_seg_view;
+
+// Per-segment setup for a sensor origin.  Returns 0 when no beam can see the wall.
+NV_HD int nv_seg_setup(const float* sg, float ox, float oy, int closed_boxes, nv_seg_view* v) {
+  float cx = sg[4] - ox, cy = sg[5] - oy;
+  if (fmaf(cx, cx, cy * cy) > sg[6]) return 0;
+  float wx = sg[0] - ox, wy = sg[1] - oy, ex = sg[2], ey = sg[3];
+  float tn = fmaf(wx, ey, -(wy * ex));
+  if (closed_boxes && tn >= 0.0f) return 0;
+  if (tn < 0.0f) { tn = -tn; wx = -wx; wy = -wy; ex = -ex; ey = -ey; }
+  if (tn > sg[7] || tn == 0.0f) return 0;
+  v->wx = wx; v->wy = wy; v->ex = ex; v->ey = ey;
+  v->inv_tn = 1.0f / tn;
+  return 1;
+}
+
+// One beam against one prepared wall: returns max(best_q, q) when the beam hits it.
+NV_HD float nv_ray_q(const nv_seg_view* v, float dx, float dy, float best_q) {
+  float den = fmaf(dx, v->ey, -(dy * v->ex));
+  float un = fmaf(v->wx, dy, -(v->wy * dx));
+  float q = den * v->inv_tn;
+  int ok = (fmaf(den, NV_SEG_EPS, un) >= 0.0f) && (fmaf(den, -NV_SEG_EPS, un) <= den) && (q > best_q);
+  return ok ? q : best_q;
+}
+
+// One beam against all S walls (beam-major form): inverse distance of the nearest hit.
+NV_HD float nv_beam_q(float ox, float oy, float dx, float dy, const float* seg, int S, int closed_boxes) {
+  float best_q = 0.0f;
+  for (int k = 0; k < S; ++k) {
+    nv_seg_view v;
+    if (nv_seg_setup(seg + NV_SEG_FLOATS * k, ox, oy, closed_boxes, &v)) best_q = nv_ray_q(&v, dx, dy, best_q);
+  }
+  return best_q;
+}
+
+// Beam direction = heading rotated by the beam's table entry (cos, sin of its offset).
+NV_HD void nv_beam_dir(float ch, float sh, float bc, float bs, float* dx, float* dy) {
+  *dx = fmaf(ch, bc, -(sh * bs));
+  *dy = fmaf(sh, bc, ch * bs);
+}
+
+// Inverse distance -> range with the gates of the Gazebo ray sensor: no hit or beyond
+// max -> +inf, below min -> -inf (gazebo.xacro:117-119).
+NV_HD float nv_range_from_q(float q, float rmin, float rmax) {
+  float t = 1.0f / q;  // q == 0 (no hit) gives +inf
+  if (t > rmax) return NV_INF_F;
+  if (t < rmin) return -NV_INF_F;
+  return t;
 }
 
 #endif  // NAVSIM_MATH_H_

@@ -1,0 +1,203 @@
+"""Host-side mirror of the reference's environment interface.
+
+  Env     — same constructor / reset() / step(action, past_action) surface as
+            project_ppo/src/environment_new.py:26-382 (one robot, numpy in/out), so the
+            reference's main.py / ppo.py drop in by re-pointing one import (main.py:433).
+  VecEnv  — N robots per GPU; torch tensors in/out on the device, auto-reset with the
+            rollout's episode protocol (ppo.py:549-593) folded into the step kernel.
+
+Both are thin: every number comes out of libnavbot_b200.so (csrc/navsim_kernels.cu).
+"""
+from __future__ import annotations
+
+import ctypes
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import _capi, maps
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class VecEnv:
+    """N agents of the reference Env stepped by one kernel launch per step."""
+
+    obs_dim = _capi.OBS_DIM
+    act_dim = _capi.ACT_DIM
+
+    def __init__(self, num_envs: int, map: str | np.ndarray = "stage_1", device: int | str | torch.device = 0,
+                 seed: int = 0, max_episode_steps: int = 500, auto_reset: bool = True, is_training: bool = True,
+                 num_beams: int = 10, agent_id_offset: int = 0, cfg: _capi.NavsimCfg | None = None,
+                 closed_boxes: bool = True):
+        self._h = ctypes.c_void_p()
+        L = _capi.lib()
+        dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        if dev.type != "cuda":
+            raise ValueError("VecEnv runs on a CUDA device; there is no CPU path")
+        self.device = dev
+        if cfg is None:
+            cfg = _capi.default_cfg(num_envs)
+            cfg.seed = seed
+            cfg.max_episode_steps = max_episode_steps
+            cfg.auto_reset = 1 if auto_reset else 0
+            cfg.num_beams = num_beams
+            cfg.agent_id_offset = agent_id_offset
+            # environment_new.py:44-47
+            cfg.arrive_threshold = 0.2 if is_training else 0.4
+        cfg.device = dev.index if dev.index is not None else torch.cuda.current_device()
+        self.cfg = cfg
+        self.num_envs = int(cfg.num_agents)
+        _capi.check(L.navsim_create(ctypes.byref(self._h), ctypes.byref(cfg)))
+        seg = maps.get_map(map) if isinstance(map, str) else np.asarray(map)
+        self.segments = np.ascontiguousarray(seg, dtype=np.float64).reshape(-1, 4)
+        # maps.get_map()/boxes_to_segments() emit counter-clockwise box edges; pass closed_boxes=False
+        # for hand-made free-standing walls
+        self.closed_boxes = bool(closed_boxes)
+        _capi.check(L.navsim_set_map(self._h, self.segments.ctypes.data, len(self.segments),
+                                     _capi.MAP_CLOSED_BOXES if closed_boxes else 0))
+        n = self.num_envs
+        self.obs = torch.zeros((n, self.obs_dim), dtype=torch.float32, device=dev)
+        self.rew = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.arrive = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.trunc = torch.zeros(n, dtype=torch.uint8, device=dev)
+
+    # -- lifecycle ----------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            _capi.lib().navsim_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- device API ---------------------------------------------------------------------
+    def reset(self, mask: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+        obs = self.obs if out is None else out
+        mptr = None
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            mptr = mask.data_ptr()
+        _capi.check(_capi.lib().navsim_reset(self._h, mptr, obs.data_ptr(), _stream_ptr(self.device)))
+        return obs
+
+    def step(self, actions: torch.Tensor, out_obs: torch.Tensor | None = None, out_rew: torch.Tensor | None = None,
+             out_done: torch.Tensor | None = None, out_arrive: torch.Tensor | None = None,
+             out_trunc: torch.Tensor | None = None):
+        """actions[N,2] float32 on the device -> (obs[N,16], rew[N], done[N], arrive[N]) (+ self.trunc)."""
+        if actions.dtype != torch.float32 or not actions.is_contiguous() or actions.device != self.device:
+            actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        if actions.numel() != self.num_envs * 2:
+            raise ValueError(f"actions must have shape [{self.num_envs}, 2]")
+        obs = self.obs if out_obs is None else out_obs
+        rew = self.rew if out_rew is None else out_rew
+        done = self.done if out_done is None else out_done
+        arrive = self.arrive if out_arrive is None else out_arrive
+        trunc = self.trunc if out_trunc is None else out_trunc
+        _capi.check(_capi.lib().navsim_step(self._h, actions.data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
+                                            arrive.data_ptr(), trunc.data_ptr(), _stream_ptr(self.device)))
+        return obs, rew, done, arrive
+
+    def step_scripted(self, num_steps: int, action_seed: int = 0):
+        _capi.check(_capi.lib().navsim_step_scripted(self._h, num_steps, action_seed, self.obs.data_ptr(),
+                                                     self.rew.data_ptr(), self.done.data_ptr(), self.arrive.data_ptr(),
+                                                     _stream_ptr(self.device)))
+        return self.obs, self.rew, self.done, self.arrive
+
+    def scan(self) -> torch.Tensor:
+        out = torch.empty((self.num_envs, int(self.cfg.num_beams)), dtype=torch.float64, device=self.device)
+        _capi.check(_capi.lib().navsim_scan(self._h, out.data_ptr(), _stream_ptr(self.device)))
+        return out
+
+    # -- host API (pinned staging inside the library) -------------------------------------
+    def reset_host(self, mask: np.ndarray | None = None) -> np.ndarray:
+        obs = np.zeros((self.num_envs, self.obs_dim), np.float32)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        _capi.check(_capi.lib().navsim_reset_host(self._h, None if m is None else m.ctypes.data, obs.ctypes.data))
+        return obs
+
+    def step_host(self, actions: np.ndarray):
+        a = np.ascontiguousarray(actions, np.float32).reshape(self.num_envs, 2)
+        n = self.num_envs
+        obs = np.empty((n, self.obs_dim), np.float32)
+        rew = np.empty(n, np.float32)
+        done = np.empty(n, np.uint8)
+        arrive = np.empty(n, np.uint8)
+        trunc = np.empty(n, np.uint8)
+        _capi.check(_capi.lib().navsim_step_host(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data,
+                                                 done.ctypes.data, arrive.ctypes.data, trunc.ctypes.data))
+        return obs, rew, done, arrive, trunc
+
+    # -- state inspection / injection ------------------------------------------------------
+    def get_state(self, field: int) -> np.ndarray:
+        out = np.empty(self.num_envs, dtype=_capi.FIELD_DTYPES[field])
+        _capi.check(_capi.lib().navsim_get_state(self._h, field, out.ctypes.data))
+        return out
+
+    def set_state(self, field: int, values) -> None:
+        v = np.ascontiguousarray(values, dtype=_capi.FIELD_DTYPES[field]).reshape(self.num_envs)
+        _capi.check(_capi.lib().navsim_set_state(self._h, field, v.ctypes.data))
+
+    def stats(self, clear: bool = False) -> _capi.NavsimStats:
+        s = _capi.NavsimStats()
+        _capi.check(_capi.lib().navsim_get_stats(self._h, ctypes.byref(s), 1 if clear else 0))
+        return s
+
+    @property
+    def launch_count(self) -> int:
+        return int(_capi.lib().navsim_launch_count(self._h))
+
+
+class Env:
+    """Drop-in for environment_new.Env: one robot, numpy in / numpy out.
+
+    reset() -> ndarray(16,); step(action, past_action) -> (ndarray(16,), float, bool, bool)
+    (environment_new.py:272-310, 312-382).  `past_action` is what the caller passes — the
+    action *before* the one being executed (ppo.py:541-543) — and is copied into the
+    observation exactly as the reference does; the simulator's own copy is overwritten
+    with it first so both bookkeeping schemes agree.
+    """
+
+    def __init__(self, is_training, use_vision=False, vision_dim=64, map="stage_1", device=0, seed=0):
+        if use_vision:
+            raise NotImplementedError("the camera path is outside the LiDAR hot path (SURVEY.md section 2, row 9)")
+        self.use_vision = False
+        self.vision_dim = vision_dim
+        self._vec = VecEnv(1, map=map, device=device, seed=seed, auto_reset=False, is_training=is_training,
+                           max_episode_steps=1 << 30)
+        self.threshold_arrive = 0.2 if is_training else 0.4
+        self.position = SimpleNamespace(x=0.0, y=0.0, z=0.0)
+        self.goal_position = SimpleNamespace(position=SimpleNamespace(x=0.0, y=0.0, z=0.01))
+        self.past_distance = 0.0
+
+    def _sync_public_state(self):
+        v = self._vec
+        self.position.x = float(v.get_state(_capi.F_X)[0])
+        self.position.y = float(v.get_state(_capi.F_Y)[0])
+        self.goal_position.position.x = float(v.get_state(_capi.F_GOAL_X)[0])
+        self.goal_position.position.y = float(v.get_state(_capi.F_GOAL_Y)[0])
+        self.past_distance = float(v.get_state(_capi.F_PAST_DIST)[0])
+
+    def getLatestImage(self):
+        return None
+
+    def reset(self):
+        obs = self._vec.reset_host()[0].astype(np.float64)
+        self._sync_public_state()
+        return obs
+
+    def step(self, action, past_action):
+        v = self._vec
+        pa = np.asarray(past_action, dtype=np.float32).reshape(2)
+        v.set_state(_capi.F_PREV_A0, pa[:1])
+        v.set_state(_capi.F_PREV_A1, pa[1:])
+        obs, rew, done, arrive, _ = v.step_host(np.asarray(action, dtype=np.float32).reshape(1, 2))
+        self._sync_public_state()
+        return obs[0].astype(np.float64), float(rew[0]), bool(done[0]), bool(arrive[0])

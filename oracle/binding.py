@@ -33,7 +33,8 @@ class _State(ctypes.Structure):
 
 
 class _Map(ctypes.Structure):
-    _fields_ = [("seg", ctypes.c_void_p), ("S", ctypes.c_int32), ("bc", ctypes.c_void_p), ("bs", ctypes.c_void_p)]
+    _fields_ = [("seg", ctypes.c_void_p), ("S", ctypes.c_int32), ("closed_boxes", ctypes.c_int32),
+                ("bc", ctypes.c_void_p), ("bs", ctypes.c_void_p)]
 
 
 _lib = None
@@ -54,8 +55,10 @@ def lib():
         L.oracle_scripted_actions.restype = None
         L.shim_beam_table.argtypes = [i32, d, d, vp, vp]
         L.shim_beam_table.restype = None
-        L.shim_scan.argtypes = [d, d, d, vp, i32, i32, vp, vp, d, d, d, vp]
+        L.shim_scan.argtypes = [d, d, d, vp, i32, i32, i32, vp, vp, d, d, d, vp]
         L.shim_scan.restype = None
+        L.shim_pack_segments.argtypes = [vp, i32, d, vp]
+        L.shim_pack_segments.restype = None
         for name in ("oracle_nv_sin", "oracle_nv_cos", "oracle_nv_atan"):
             getattr(L, name).argtypes = [d]
             getattr(L, name).restype = d
@@ -79,15 +82,19 @@ _FIELDS = [("x", np.float64), ("y", np.float64), ("th", np.float64), ("gx", np.f
 class OracleSim:
     """N independent reference environments on the CPU (state as numpy SoA arrays)."""
 
-    def __init__(self, cfg, segments, nthreads: int = 1):
+    def __init__(self, cfg, segments, nthreads: int = 1, closed_boxes: bool = True):
         self.cfg = cfg  # a navbot_ppo_b200._capi.NavsimCfg (the public C struct)
         self.n = int(cfg.num_agents)
         self.nthreads = nthreads
         self.seg = np.ascontiguousarray(segments, dtype=np.float64).reshape(-1, 4)
         nb = int(cfg.num_beams)
-        self.bc, self.bs = np.zeros(nb), np.zeros(nb)
+        self.bc, self.bs = np.zeros(nb, np.float32), np.zeros(nb, np.float32)
         lib().shim_beam_table(nb, cfg.fov_min, cfg.fov_max, self.bc.ctypes.data, self.bs.ctypes.data)
-        self.map = _Map(self.seg.ctypes.data, len(self.seg), self.bc.ctypes.data, self.bs.ctypes.data)
+        self.segf = np.zeros((len(self.seg), 8), np.float32)
+        lib().shim_pack_segments(self.seg.ctypes.data, len(self.seg), cfg.lidar_max, self.segf.ctypes.data)
+        self.closed_boxes = 1 if closed_boxes else 0
+        self.map = _Map(self.segf.ctypes.data, len(self.seg), self.closed_boxes, self.bc.ctypes.data,
+                        self.bs.ctypes.data)
         self.arr = {name: np.zeros(self.n, dtype=dt) for name, dt in _FIELDS}
         self.state = _State(*[self.arr[name].ctypes.data for name, _ in _FIELDS])
         self.stats = None
@@ -116,8 +123,8 @@ class OracleSim:
         out = np.zeros((self.n, nb))
         c = self.cfg
         for i in range(self.n):
-            lib().shim_scan(self.arr["x"][i], self.arr["y"][i], self.arr["th"][i], self.seg.ctypes.data, len(self.seg), nb,
-                            self.bc.ctypes.data, self.bs.ctypes.data, c.lidar_offset_x, c.lidar_min, c.lidar_max,
+            lib().shim_scan(self.arr["x"][i], self.arr["y"][i], self.arr["th"][i], self.segf.ctypes.data, len(self.seg),
+                            self.closed_boxes, nb, self.bc.ctypes.data, self.bs.ctypes.data, c.lidar_offset_x, c.lidar_min, c.lidar_max,
                             out[i].ctypes.data)
         return out
 

@@ -48,9 +48,12 @@ def oracle_lib():
         lib.shim_drive.restype = None
         lib.shim_quat.argtypes = [d, pd, pd]
         lib.shim_quat.restype = None
-        lib.shim_beam_table.argtypes = [ctypes.c_int32, d, d, pd, pd]
+        vp = ctypes.c_void_p
+        lib.shim_beam_table.argtypes = [ctypes.c_int32, d, d, vp, vp]
         lib.shim_beam_table.restype = None
-        lib.shim_scan.argtypes = [d, d, d, pd, ctypes.c_int32, ctypes.c_int32, pd, pd, d, d, d, pd]
+        lib.shim_pack_segments.argtypes = [vp, ctypes.c_int32, d, vp]
+        lib.shim_pack_segments.restype = None
+        lib.shim_scan.argtypes = [d, d, d, vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp, vp, d, d, d, pd]
         lib.shim_scan.restype = None
         lib.shim_goal_uniforms.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, pd, pd]
         lib.shim_goal_uniforms.restype = None
@@ -85,13 +88,16 @@ class FakeGazebo:
     """gzserver + libgazebo_ros_diff_drive + libgazebo_ros_laser for one robot."""
 
     def __init__(self, segments, num_beams=10, dt=0.2, lidar_offset_x=-0.032, lidar_min=0.12, lidar_max=3.5,
-                 fov_min=-1.5707975, fov_max=1.5707975, start=(0.0, 0.0, 0.0)):
+                 fov_min=-1.5707975, fov_max=1.5707975, start=(0.0, 0.0, 0.0), closed_boxes=True):
         self.seg = np.ascontiguousarray(segments, dtype=np.float64).reshape(-1, 4)
         self.nb, self.dt, self.off = int(num_beams), float(dt), float(lidar_offset_x)
         self.rmin, self.rmax = float(lidar_min), float(lidar_max)
-        self.bc = np.zeros(self.nb)
-        self.bs = np.zeros(self.nb)
-        oracle_lib().shim_beam_table(self.nb, fov_min, fov_max, _pd(self.bc), _pd(self.bs))
+        self.bc = np.zeros(self.nb, np.float32)
+        self.bs = np.zeros(self.nb, np.float32)
+        oracle_lib().shim_beam_table(self.nb, fov_min, fov_max, self.bc.ctypes.data, self.bs.ctypes.data)
+        self.segf = np.zeros((len(self.seg), 8), np.float32)
+        oracle_lib().shim_pack_segments(self.seg.ctypes.data, len(self.seg), self.rmax, self.segf.ctypes.data)
+        self.closed_boxes = 1 if closed_boxes else 0
         self.start = tuple(float(v) for v in start)
         self.x, self.y, self.th = (ctypes.c_double(v) for v in self.start)
         self.cmd = (0.0, 0.0)
@@ -122,8 +128,8 @@ class FakeGazebo:
         for cb in self.odom_callbacks:
             cb(odom)
         ranges = np.zeros(self.nb)
-        lib.shim_scan(self.x.value, self.y.value, self.th.value, _pd(self.seg), len(self.seg), self.nb,
-                      _pd(self.bc), _pd(self.bs), self.off, self.rmin, self.rmax, _pd(ranges))
+        lib.shim_scan(self.x.value, self.y.value, self.th.value, self.segf.ctypes.data, len(self.seg),
+                      self.closed_boxes, self.nb, self.bc.ctypes.data, self.bs.ctypes.data, self.off, self.rmin, self.rmax, _pd(ranges))
         scan = _Msg()
         scan.ranges = [float(r) for r in ranges]
         return scan

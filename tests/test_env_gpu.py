@@ -1,0 +1,276 @@
+"""GPU parity tests of the simulator, all through the C-ABI (navbot_ppo_b200.VecEnv / Env
+are ctypes shims over libnavbot_b200.so).  Checker = the CPU oracle and the golden traces
+recorded from the reference's own Env.  Bar: done/arrive/timeout bit-exact, pose/goal state
+bit-exact, obs and reward within 1e-5 (they leave the kernel as fp32)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from navbot_ppo_b200 import _capi, maps
+from navbot_ppo_b200.env import Env, VecEnv
+from oracle import binding
+from tests.helpers import OBS_ATOL, REW_ATOL, cfg_from_golden, golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _vec_from_cfg(cfg, segments):
+    return VecEnv(cfg.num_agents, map=segments, device=0, cfg=cfg)
+
+
+@pytest.mark.parametrize("name", ["env_rollout_stage_1", "env_rollout_stage_2", "env_rollout_stage_1_eval"])
+def test_step_matches_reference_golden_rollout(name):
+    g = golden(name)
+    env = _vec_from_cfg(cfg_from_golden(g, auto_reset=1), g["segments"])
+    obs0 = env.reset().cpu().numpy()
+    np.testing.assert_allclose(obs0, g["obs0"], atol=OBS_ATOL, rtol=0)
+    for t in range(g["act"].shape[0]):
+        obs, rew, done, arrive = env.step(torch.from_numpy(g["act"][t]).cuda())
+        np.testing.assert_array_equal(done.cpu().numpy(), g["done"][t].astype(np.uint8), err_msg=f"done t={t}")
+        np.testing.assert_array_equal(arrive.cpu().numpy(), g["arrive"][t].astype(np.uint8), err_msg=f"arrive t={t}")
+        np.testing.assert_array_equal(env.trunc.cpu().numpy(), g["trunc"][t].astype(np.uint8), err_msg=f"trunc t={t}")
+        np.testing.assert_allclose(obs.cpu().numpy(), g["obs_next"][t], atol=OBS_ATOL, rtol=0, err_msg=f"obs t={t}")
+        np.testing.assert_allclose(rew.cpu().numpy(), g["rew"][t], atol=REW_ATOL, rtol=0, err_msg=f"rew t={t}")
+    # poses integrate bit-identically (shared physics header); goals are the same Philox draws
+    for k, f in (("x", _capi.F_X), ("y", _capi.F_Y), ("th", _capi.F_THETA), ("gx", _capi.F_GOAL_X),
+                 ("gy", _capi.F_GOAL_Y)):
+        np.testing.assert_array_equal(env.get_state(f), g[k][-1], err_msg=k)
+    np.testing.assert_array_equal(env.get_state(_capi.F_DRAWS), g["draws"][-1].astype(np.uint32))
+    np.testing.assert_allclose(env.get_state(_capi.F_PAST_DIST), g["past"][-1], rtol=1e-15)
+
+
+def test_raw_env_protocol_matches_reference_golden():
+    """auto_reset off: goal respawn inside step on arrival (environment_new.py:245-267),
+    explicit masked reset after collisions."""
+    g = golden("env_raw_stage_1")
+    env = _vec_from_cfg(cfg_from_golden(g, auto_reset=0), g["segments"])
+    np.testing.assert_allclose(env.reset().cpu().numpy(), g["obs0"], atol=OBS_ATOL, rtol=0)
+    for t in range(g["act"].shape[0]):
+        obs, rew, done, arrive = env.step(torch.from_numpy(g["act"][t]).cuda())
+        np.testing.assert_allclose(obs.cpu().numpy(), g["obs"][t], atol=OBS_ATOL, rtol=0, err_msg=f"obs t={t}")
+        np.testing.assert_allclose(rew.cpu().numpy(), g["rew"][t], atol=REW_ATOL, rtol=0)
+        np.testing.assert_array_equal(done.cpu().numpy(), g["done"][t].astype(np.uint8))
+        np.testing.assert_array_equal(arrive.cpu().numpy(), g["arrive"][t].astype(np.uint8))
+        mask = g["reset_mask"][t].astype(np.uint8)
+        if mask.any():
+            ro = env.reset(torch.from_numpy(mask).cuda()).cpu().numpy()
+            sel = mask.astype(bool)
+            np.testing.assert_allclose(ro[sel], g["obs_reset"][t][sel], atol=OBS_ATOL, rtol=0)
+        np.testing.assert_array_equal(env.get_state(_capi.F_GOAL_X), g["gx"][t])
+        np.testing.assert_array_equal(env.get_state(_capi.F_DRAWS), g["draws"][t].astype(np.uint32))
+
+
+def test_single_env_dropin_matches_reference_golden():
+    """navbot_ppo_b200.Env (the class main.py would import, main.py:433) on agent 0's trace."""
+    g = golden("env_raw_stage_1")
+    env = Env(True, seed=int(g["seed"]), map=g["segments"])
+    obs = env.reset()
+    assert obs.shape == (16,) and obs.dtype == np.float64
+    np.testing.assert_allclose(obs, g["obs0"][0], atol=OBS_ATOL, rtol=0)
+    past = np.zeros(2, np.float32)
+    for t in range(120):
+        act = g["act"][t][0]
+        o, r, d, a = env.step(act, past)
+        past = act
+        assert isinstance(r, float) and isinstance(d, bool) and isinstance(a, bool)
+        np.testing.assert_allclose(o, g["obs"][t][0], atol=OBS_ATOL, rtol=0, err_msg=f"t={t}")
+        assert abs(r - g["rew"][t][0]) <= REW_ATOL and d == bool(g["done"][t][0]) and a == bool(g["arrive"][t][0])
+        assert env.goal_position.position.x == g["gx"][t][0]
+        if g["reset_mask"][t][0]:
+            np.testing.assert_allclose(env.reset(), g["obs_reset"][t][0], atol=OBS_ATOL, rtol=0)
+            past = np.zeros(2, np.float32)
+
+
+@pytest.mark.parametrize("n,map_name,steps", [(8192, "stage_1", 160), (16384, "stage_2", 60), (1000, "stage_2", 70),
+                                              (1, "stage_1", 30)])
+def test_step_matches_oracle_at_config_sizes(n, map_name, steps):
+    """BASELINE.json configs[1] / configs[2] sizes against the C oracle with scripted actions."""
+    cfg = _capi.default_cfg(n)
+    cfg.seed = 11
+    cfg.max_episode_steps = 50
+    seg = maps.get_map(map_name)
+    env = _vec_from_cfg(cfg, seg)
+    sim = binding.OracleSim(cfg, seg, nthreads=8)
+    np.testing.assert_allclose(env.reset().cpu().numpy(), sim.reset(), atol=OBS_ATOL, rtol=0)
+    tot = dict(done=0, arrive=0, trunc=0)
+    for t in range(steps):
+        act = binding.scripted_actions(3, 0, t, n)
+        if t % 2:  # every other step: full speed to provoke collisions
+            act[: n // 2, 0] = 1.0
+        o_ref, r_ref, d_ref, a_ref, tr_ref = sim.step(act)
+        obs, rew, done, arrive = env.step(torch.from_numpy(act).cuda())
+        np.testing.assert_array_equal(done.cpu().numpy(), d_ref, err_msg=f"done t={t}")
+        np.testing.assert_array_equal(arrive.cpu().numpy(), a_ref, err_msg=f"arrive t={t}")
+        np.testing.assert_array_equal(env.trunc.cpu().numpy(), tr_ref, err_msg=f"trunc t={t}")
+        np.testing.assert_allclose(obs.cpu().numpy(), o_ref, atol=OBS_ATOL, rtol=0, err_msg=f"obs t={t}")
+        np.testing.assert_allclose(rew.cpu().numpy(), r_ref, atol=REW_ATOL, rtol=0, err_msg=f"rew t={t}")
+        tot["done"] += int(d_ref.sum()); tot["arrive"] += int(a_ref.sum()); tot["trunc"] += int(tr_ref.sum())
+    for k, f in (("x", _capi.F_X), ("y", _capi.F_Y), ("th", _capi.F_THETA), ("gx", _capi.F_GOAL_X),
+                 ("gy", _capi.F_GOAL_Y)):
+        np.testing.assert_array_equal(env.get_state(f), sim.arr[k], err_msg=k)
+    np.testing.assert_array_equal(env.get_state(_capi.F_DRAWS), sim.arr["draws"])
+    np.testing.assert_array_equal(env.get_state(_capi.F_STEPS), sim.arr["steps"])
+    np.testing.assert_allclose(env.get_state(_capi.F_EP_RETURN), sim.arr["ep_ret"], rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(env.get_state(_capi.F_EP_PATH), sim.arr["ep_path"], rtol=1e-5, atol=1e-5)
+    if n >= 1000:
+        assert tot["trunc"] > 0 and tot["done"] + tot["arrive"] > 0
+
+
+def test_scripted_device_actions_match_oracle_stream():
+    """navsim_step_scripted (the benchmark driver) draws the same actions as the oracle."""
+    n = 4096
+    cfg = _capi.default_cfg(n)
+    cfg.seed = 5
+    seg = maps.get_map("stage_1")
+    env = _vec_from_cfg(cfg, seg)
+    sim = binding.OracleSim(cfg, seg, nthreads=8)
+    env.reset(); sim.reset()
+    for t in range(25):
+        o_ref, r_ref, d_ref, a_ref, _ = sim.step(binding.scripted_actions(99, 0, t, n))
+        obs, rew, done, arrive = env.step_scripted(1, action_seed=99)
+        np.testing.assert_array_equal(done.cpu().numpy(), d_ref)
+        np.testing.assert_allclose(obs.cpu().numpy(), o_ref, atol=OBS_ATOL, rtol=0)
+    np.testing.assert_array_equal(env.get_state(_capi.F_X), sim.arr["x"])
+
+
+def test_bearing_feature_exhaustive_over_offset_grid():
+    """rel_theta = round(degrees(atan-with-quadrants), 2) depends only on the two goal
+    offsets rounded to 0.1 m (environment_new.py:149-169): check EVERY pair in
+    [-12.0, 12.0]^2 — the device atan polynomial vs libm — plus yaw at every whole degree."""
+    ks = np.arange(-120, 121)
+    gx, gy = np.meshgrid(ks / 10.0, ks / 10.0, indexing="ij")
+    n = gx.size
+    cfg = _capi.default_cfg(n)
+    cfg.auto_reset = 0
+    cfg.max_episode_steps = 1 << 30
+    cfg.arrive_threshold = -1.0  # never arrive: keep the injected goals
+    seg = maps.synthetic_map(4, extent=40.0)
+    env = _vec_from_cfg(cfg, seg)
+    sim = binding.OracleSim(cfg, seg, nthreads=8)
+    env.reset(); sim.reset()
+    th = np.deg2rad((np.arange(n) % 721) / 2.0 - 180.0 + 1e-9)
+    th = np.where(th <= -math.pi, th + 2 * math.pi, th)
+    for f, k, v in ((_capi.F_GOAL_X, "gx", gx.ravel()), (_capi.F_GOAL_Y, "gy", gy.ravel()),
+                    (_capi.F_THETA, "th", th)):
+        env.set_state(f, v)
+        sim.arr[k][:] = v
+    act = np.zeros((n, 2), np.float32)
+    o_ref, *_ = sim.step(act)
+    obs, *_ = env.step(torch.from_numpy(act).cuda())
+    got = obs.cpu().numpy()
+    # the three quantised features must agree to fp32 rounding, i.e. no 0.01-degree slips
+    for col, scale in ((13, 360.0), (14, 360.0), (15, 180.0)):
+        err = np.abs(got[:, col].astype(np.float64) - o_ref[:, col]) * scale
+        assert err.max() < 2e-4, (col, err.max())
+
+
+@pytest.mark.parametrize("beams,boxes", [(10, 52), (36, 52), (24, 12)])
+def test_scan_bit_exact_on_dense_maps(beams, boxes):
+    """Row R alone (house-like segment counts, BASELINE configs[4] beam sweep): the device
+    LaserScan equals the host build of the same physics header bit for bit."""
+    n = 512
+    cfg = _capi.default_cfg(n)
+    cfg.num_beams = beams
+    cfg.goal_lo, cfg.goal_hi = -6.0, 6.0
+    seg = maps.synthetic_map(boxes, seed=3)
+    env = _vec_from_cfg(cfg, seg)
+    sim = binding.OracleSim(cfg, seg)
+    env.reset(); sim.reset()
+    rng = np.random.RandomState(0)
+    for f, k, v in ((_capi.F_X, "x", rng.uniform(-6, 6, n)), (_capi.F_Y, "y", rng.uniform(-6, 6, n)),
+                    (_capi.F_THETA, "th", rng.uniform(-3.1, 3.1, n))):
+        env.set_state(f, v)
+        sim.arr[k][:] = v
+    got = env.scan().cpu().numpy()
+    want = sim.scan()
+    np.testing.assert_array_equal(got, want)
+    assert np.isinf(want).any() and np.isfinite(want).any()
+    act = binding.scripted_actions(1, 0, 0, n)
+    o_ref, r_ref, d_ref, a_ref, _ = sim.step(act)
+    obs, rew, done, arrive = env.step(torch.from_numpy(act).cuda())
+    np.testing.assert_array_equal(done.cpu().numpy(), d_ref)
+    np.testing.assert_allclose(obs.cpu().numpy(), o_ref, atol=OBS_ATOL, rtol=0)
+
+
+def test_host_buffer_entry_points_equal_device_entry_points():
+    n = 2048
+    a = VecEnv(n, seed=2); b = VecEnv(n, seed=2)
+    oa = a.reset().cpu().numpy(); ob = b.reset_host()
+    np.testing.assert_array_equal(oa, ob)
+    for t in range(10):
+        act = binding.scripted_actions(8, 0, t, n)
+        obs, rew, done, arrive = a.step(torch.from_numpy(act).cuda())
+        hobs, hrew, hdone, harr, htr = b.step_host(act)
+        np.testing.assert_array_equal(obs.cpu().numpy(), hobs)
+        np.testing.assert_array_equal(rew.cpu().numpy(), hrew)
+        np.testing.assert_array_equal(done.cpu().numpy(), hdone)
+        np.testing.assert_array_equal(a.trunc.cpu().numpy(), htr)
+
+
+def test_partition_invariance_and_statistics():
+    """Sharding contract: agents [0,N) on one handle == two handles of N/2 with
+    agent_id_offset, so multi-GPU runs reproduce the single-GPU episode stream exactly."""
+    n = 8192
+    whole = VecEnv(n, seed=9, max_episode_steps=40)
+    lo = VecEnv(n // 2, seed=9, max_episode_steps=40)
+    hi = VecEnv(n // 2, seed=9, max_episode_steps=40, agent_id_offset=n // 2)
+    whole.reset(); lo.reset(); hi.reset()
+    for t in range(90):
+        act = torch.from_numpy(binding.scripted_actions(4, 0, t, n)).cuda()
+        o, r, d, a = whole.step(act)
+        o1, r1, d1, a1 = lo.step(act[: n // 2].contiguous())
+        o2, r2, d2, a2 = hi.step(act[n // 2:].contiguous())
+        assert torch.equal(o, torch.cat([o1, o2])) and torch.equal(r, torch.cat([r1, r2]))
+        assert torch.equal(d, torch.cat([d1, d2])) and torch.equal(a, torch.cat([a1, a2]))
+    s, s1, s2 = whole.stats(), lo.stats(), hi.stats()
+    assert s.episodes == s1.episodes + s2.episodes > 0
+    assert s.episodes == s.successes + s.collisions + s.timeouts
+    assert s.steps == 90 * n
+    assert abs(s.return_sum - (s1.return_sum + s2.return_sum)) < 1e-6 * max(1.0, abs(s.return_sum))
+
+
+def test_million_agent_batch_invariants():
+    """Full-scale properties that need no oracle: ranges normalised, flags consistent with
+    the observation, auto-reset restores the spawn observation pattern."""
+    n = 1 << 20
+    env = VecEnv(n, seed=1, max_episode_steps=25)
+    env.reset()
+    env.step_scripted(29, action_seed=2)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    act = torch.rand(n, 2, device="cuda", generator=g) * torch.tensor([1.0, 2.0], device="cuda") - \
+        torch.tensor([0.0, 1.0], device="cuda")
+    obs, rew, done, arrive = env.step(act)
+    o = obs.cpu().numpy(); r = rew.cpu().numpy()
+    d = done.cpu().numpy().astype(bool); a = arrive.cpu().numpy().astype(bool); tr = env.trunc.cpu().numpy().astype(bool)
+    assert np.isfinite(o).all() and (o[:, :10] >= 0).all() and (o[:, :10] <= 1).all()
+    assert (o[:, 13] >= 0).all() and (o[:, 13] < 1).all() and (np.abs(o[:, 15]) <= 1).all()
+    assert (r[a] == 120.0).all() and (r[d & ~a] == -100.0).all()
+    assert not (tr & (d | a)).any()
+    term = d | a | tr
+    assert term.any() and tr.any()
+    # a freshly reset agent sits at the origin with zero past action and yaw 0
+    assert (o[term, 10] == 0).all() and (o[term, 11] == 0).all() and (o[term, 13] == 0).all()
+    steps = env.get_state(_capi.F_STEPS)
+    assert (steps[term] == 0).all() and (steps[~term] > 0).all()
+    s = env.stats()
+    assert s.steps == 30 * n and s.episodes == s.successes + s.collisions + s.timeouts > 0
+
+
+def test_error_paths():
+    cfg = _capi.default_cfg(0)
+    with pytest.raises(_capi.NavError):
+        VecEnv(0, cfg=cfg)
+    env = VecEnv(8)
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(7, 2, device="cuda"))
+    import ctypes
+    h = ctypes.c_void_p()
+    cfg = _capi.default_cfg(8)
+    _capi.check(_capi.lib().navsim_create(ctypes.byref(h), ctypes.byref(cfg)))
+    # step before set_map is refused, not a crash
+    rc = _capi.lib().navsim_step(h, env.obs.data_ptr(), env.obs.data_ptr(), env.rew.data_ptr(), env.done.data_ptr(),
+                                 env.arrive.data_ptr(), None, None)
+    assert rc == -22 and b"set_map" in _capi.lib().nav_last_error()
+    _capi.lib().navsim_destroy(h)
