@@ -1,0 +1,135 @@
+/* navppo.h — C-ABI of the B200 PPO trainer kernels (policy / value residual MLPs, sampling,
+ * reward-to-go, clipped-surrogate + value loss, backward, Adam).
+ *
+ * Drop-in boundary for the tensor work of the reference's trainer,
+ *     project_ppo/src/ppo.py      class PPO                 (:37-946)
+ *     project_ppo/src/net_actor.py / net_critic.py          (NetActor / NetCritic)
+ * which the reference issues as ~30 separate PyTorch ops per epoch.  Each entry point names
+ * the reference lines it replaces.  navbot_ppo_b200.PPO binds these through ctypes
+ * (INTEGRATION.md shows the stub).
+ *
+ * Conventions (same as navsim.h): plain C, returns 0 or a negative NAVSIM_E* code with
+ * nav_last_error() set; every array is DEVICE memory owned by the caller (torch tensors),
+ * fp32 contiguous unless stated; work is enqueued on `stream` with no host synchronisation;
+ * calls are CUDA-graph capturable.
+ *
+ * Parameters: both networks live in ONE flat fp32 vector of NAVPPO_FLAT elements,
+ *     [0, 50290)               actor  (order: navbot_ppo_b200/layout.py ACTOR_SPEC)
+ *     [50290, 50304)           zero padding (keeps the critic 128-byte aligned)
+ *     [50304, 50304 + 50257)   critic (CRITIC_SPEC)
+ *     [.., NAVPPO_FLAT)        zero padding
+ * Gradients and the two Adam moment vectors use the same layout, so the data-parallel
+ * gradient exchange of a multi-GPU run is one all-reduce over NAVPPO_FLAT floats.
+ */
+#ifndef NAVPPO_H_
+#define NAVPPO_H_
+
+#include <stdint.h>
+
+#include "navsim.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NAVPPO_HIDDEN 512          /* ResBlock n_neurons, net_actor.py:21 */
+#define NAVPPO_ACTOR_PARAMS 50290
+#define NAVPPO_CRITIC_PARAMS 50257
+#define NAVPPO_CRITIC_OFFSET 50304
+#define NAVPPO_FLAT 100608
+#define NAVPPO_NUM_METRICS 8
+
+/* slots of one metrics row (doubles) */
+enum navppo_metric {
+  NAVPPO_M_ACTOR_LOSS = 0,   /* ppo.py:342 */
+  NAVPPO_M_CRITIC_LOSS = 1,  /* ppo.py:343 */
+  NAVPPO_M_APPROX_KL = 2,    /* ppo.py:326 */
+  NAVPPO_M_CLIP_FRAC = 3,    /* ppo.py:335 */
+  NAVPPO_M_ACTOR_GRAD_SQ = 4,  /* squared L2 norm of the actor gradient  (ppo.py:352) */
+  NAVPPO_M_CRITIC_GRAD_SQ = 5  /* squared L2 norm of the critic gradient (ppo.py:389) */
+};
+
+/* arithmetic of the MLP GEMMs */
+enum navppo_precision {
+  NAVPPO_FP32 = 0,   /* CUDA-core FFMA, the reference's fp32 arithmetic */
+  NAVPPO_TF32X3 = 1, /* tcgen05 tensor cores, 3-pass split TF32 (fp32-level accuracy) */
+  NAVPPO_TF32 = 2    /* tcgen05 tensor cores, single-pass TF32 */
+};
+
+typedef struct navppo navppo_t;
+
+typedef struct navppo_cfg {
+  int32_t device;
+  int32_t max_samples;  /* largest T of any call (sizes the gradient workspace) */
+  int32_t precision;    /* enum navppo_precision */
+  int32_t reserved0;
+  double lr;            /* ppo.py:769  3e-4 on the main.py path */
+  double beta1, beta2, adam_eps; /* torch.optim.Adam defaults, ppo.py:116-117 */
+  double clip;          /* ppo.py:771  0.2 */
+} navppo_cfg;
+
+int navppo_default_cfg(navppo_cfg* cfg);
+int navppo_create(navppo_t** out, const navppo_cfg* cfg);
+int navppo_destroy(navppo_t* h);
+/* kernels this handle has launched so far */
+int64_t navppo_launch_count(const navppo_t* h);
+
+/* PPO.compute_rtgs (ppo.py:643-671) on the time-major [H, N] rollout layout: one reverse
+ * scan per agent, R_t = r_t + gamma R_{t+1}, restarted where term[t, n] != 0 (last step of an
+ * episode: done | arrive | timeout, ppo.py:552-553) and at t = H-1 (no bootstrap, ppo.py:601).
+ * With values != NULL it computes GAE(gamma, lam) advantages instead (delta_t = r_t + gamma
+ * V_{t+1} - V_t, last_value[N] = V_H or NULL for 0); lam = 1 and zero values give rtg - V.
+ * Accumulates in fp64 like the reference's Python floats, stores fp32 (ppo.py:669). */
+int navppo_rtg_scan(const float* rew, const uint8_t* term, const float* values, const float* last_value, double gamma,
+                    double lam, float* out, int32_t H, int32_t N, void* stream);
+
+/* NetActor.forward / NetCritic.forward (net_actor.py:94-144, net_critic.py:83-130) on T rows.
+ * mu[T,2] and / or v[T] may be NULL. */
+int navppo_forward(navppo_t* h, const float* params, const float* obs, int32_t T, float* mu, float* v, void* stream);
+
+/* PPO.get_action (ppo.py:673-706) for N agents at once: mean = actor(obs); a = mean +
+ * sqrt(var) * eps; clamp a0 to [0,1], a1 to [-1,1]; log-prob of the CLAMPED action.
+ * eps ~ N(0, I) is drawn on device from Philox4x32-10 keyed (seed, agent_id_offset + i) at
+ * counter `draw`, unless noise_in[N,2] is given (parity tests).  mu_out[N,2] may be NULL. */
+int navppo_act(navppo_t* h, const float* params, const float* obs, int32_t N, double var, uint64_t seed,
+               int64_t agent_id_offset, uint32_t draw, const float* noise_in, float* act, float* logp, float* mu_out,
+               void* stream);
+
+/* PPO.evaluate (ppo.py:708-737): V[T] = critic(obs), logp[T] = N(actor(obs), var I).log_prob(act). */
+int navppo_evaluate(navppo_t* h, const float* params, const float* obs, const float* act, int32_t T, double var,
+                    float* v, float* logp, void* stream);
+
+/* Advantage, ppo.py:277,284, in two halves so a multi-GPU run can all-reduce the three
+ * doubles in between: stats[0..2] += (sum, sum of squares, count) of A = rtg - v over T rows;
+ * then adv = (A - mean) / (unbiased std + 1e-10). */
+int navppo_adv_stats(const float* rtg, const float* v, int32_t T, double* stats, void* stream);
+int navppo_adv_normalize(const float* rtg, const float* v, int32_t T, const double* stats, float* adv, void* stream);
+
+/* One epoch body of PPO.learn (ppo.py:307-349,386): forward of both networks, ratio, clipped
+ * surrogate and MSE losses, both backward passes.  grad[NAVPPO_FLAT] is OVERWRITTEN with the
+ * gradient of (actor_loss, critic_loss) w.r.t. the flat parameters, every per-sample term
+ * divided by n_global (= T on one GPU; the global batch when samples are sharded, so that the
+ * all-reduced sum equals the reference's .mean() gradient).  metrics[0..3] are overwritten
+ * with this rank's share of the four batch means. */
+int navppo_grad(navppo_t* h, const float* params, const float* obs, const float* act, const float* logp_old,
+                const float* adv, const float* rtg, int32_t T, int64_t n_global, double var, float* grad,
+                double* metrics, void* stream);
+
+/* actor_optim.step(); critic_optim.step() (ppo.py:381,392): torch.optim.Adam, step counter
+ * `step` (1-based) shared by both networks.  Also writes the squared gradient norms of the two
+ * networks into metrics[4], metrics[5] (the clip_grad_norm_(.., inf) measurements). */
+int navppo_adam(navppo_t* h, float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int32_t step,
+                double* metrics, void* stream);
+
+/* The whole update of one PPO.learn iteration on one GPU (ppo.py:275-397): evaluate ->
+ * advantage -> `epochs` x (navppo_grad, navppo_adam), enqueued back to back with no host
+ * round trip.  adv_ws[T], v_ws[T]: caller-provided scratch; metrics[epochs, 8] doubles;
+ * step0 = Adam steps taken before this call. */
+int navppo_update(navppo_t* h, float* params, float* exp_avg, float* exp_avg_sq, int32_t step0, const float* obs,
+                  const float* act, const float* logp_old, const float* rtg, int32_t T, double var, int32_t epochs,
+                  float* adv_ws, float* v_ws, double* metrics, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NAVPPO_H_ */

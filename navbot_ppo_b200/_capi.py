@@ -60,6 +60,7 @@ class NavError(RuntimeError):
 
 _vp, _i32, _i64, _u64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64
 
+
 # name -> (restype, argtypes); every symbol include/navsim.h declares
 NAVSIM_SYMBOLS = {
     "nav_last_error": (ctypes.c_char_p, []),
@@ -81,7 +82,39 @@ NAVSIM_SYMBOLS = {
     "navsim_launch_count": (_i64, [_vp]),
 }
 
-NAVPPO_SYMBOLS: dict = {}  # filled in by _capi_ppo (include/navppo.h)
+class NavppoCfg(ctypes.Structure):
+    _fields_ = [
+        ("device", ctypes.c_int32), ("max_samples", ctypes.c_int32), ("precision", ctypes.c_int32),
+        ("reserved0", ctypes.c_int32),
+        ("lr", ctypes.c_double), ("beta1", ctypes.c_double), ("beta2", ctypes.c_double), ("adam_eps", ctypes.c_double),
+        ("clip", ctypes.c_double),
+    ]
+
+
+# include/navppo.h constants
+PPO_ACTOR_PARAMS, PPO_CRITIC_PARAMS, PPO_CRITIC_OFFSET, PPO_FLAT, PPO_NUM_METRICS = 50290, 50257, 50304, 100608, 8
+M_ACTOR_LOSS, M_CRITIC_LOSS, M_APPROX_KL, M_CLIP_FRAC, M_ACTOR_GRAD_SQ, M_CRITIC_GRAD_SQ = range(6)
+PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
+
+_f64 = ctypes.c_double
+_u32 = ctypes.c_uint32
+
+# name -> (restype, argtypes); every symbol include/navppo.h declares
+NAVPPO_SYMBOLS = {
+    "navppo_default_cfg": (ctypes.c_int, [ctypes.POINTER(NavppoCfg)]),
+    "navppo_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.POINTER(NavppoCfg)]),
+    "navppo_destroy": (ctypes.c_int, [_vp]),
+    "navppo_launch_count": (_i64, [_vp]),
+    "navppo_rtg_scan": (ctypes.c_int, [_vp, _vp, _vp, _vp, _f64, _f64, _vp, _i32, _i32, _vp]),
+    "navppo_forward": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "navppo_act": (ctypes.c_int, [_vp, _vp, _vp, _i32, _f64, _u64, _i64, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "navppo_evaluate": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _f64, _vp, _vp, _vp]),
+    "navppo_adv_stats": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp]),
+    "navppo_adv_normalize": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp]),
+    "navppo_grad": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _f64, _vp, _vp, _vp]),
+    "navppo_adam": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "navppo_update": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _f64, _i32, _vp, _vp, _vp, _vp]),
+}
 
 _lib = None
 
@@ -107,6 +140,12 @@ def check(rc: int) -> None:
     if rc != 0:
         msg = lib().nav_last_error()
         raise NavError(rc, msg.decode() if msg else "unknown error")
+
+
+def default_ppo_cfg() -> NavppoCfg:
+    cfg = NavppoCfg()
+    check(lib().navppo_default_cfg(ctypes.byref(cfg)))
+    return cfg
 
 
 def default_cfg(num_agents: int) -> NavsimCfg:

@@ -1,0 +1,874 @@
+// navppo_kernels.cu — PPO trainer kernels for sm_100a + their C-ABI (include/navppo.h).
+//
+// What the reference does with ~30 PyTorch ops per epoch (project_ppo/src/ppo.py:305-393)
+// plus a Python double loop (compute_rtgs, :643-671) becomes:
+//   rtg_scan_kernel      reverse (gamma, lambda) scan per agent over the [H, N] rollout
+//   mlp_infer_kernel     NetActor / NetCritic forward (+ Gaussian sampling / log-prob epilogue)
+//   adv_*_kernel         advantage statistics and normalisation                (ppo.py:277,284)
+//   mlp_grad_kernel      forward + losses + backward of one network per CTA row (ppo.py:307-386)
+//   grad_reduce_kernel   fixed-order sum of the per-CTA gradient partials -> flat gradient
+//   adam_kernel          both torch.optim.Adam steps                            (ppo.py:381,392)
+//
+// This file holds the fp32 CUDA-core arithmetic (NAVPPO_FP32): every product is an FFMA in
+// fp32 like the reference's torch.float32 CPU/GPU path, so results agree with it to
+// reduction-order rounding.  The tcgen05 tensor-core GEMM path lives in navppo_tc.cu.
+//
+// Network (net_actor.py:39-53,138-143; net_critic.py:36-48,127-129), per sample:
+//   z1 = W1a x0 + b1a (512)   h1 = lrelu(z1)   u1 = x0 + W1b h1 + b1b (16)   y1 = lrelu(u1)
+//   x1 = [x0 | y1] (32)
+//   z2 = W2a x1 + b2a (512)   h2 = lrelu(z2)   u2 = x1 + W2b h2 + b2b (32)   y2 = lrelu(u2)
+//   actor: mu = [sigmoid(w_o1 . y2 + c1), tanh(w_o2 . y2 + c2)]     critic: V = w_o . y2 + c
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include <new>
+#include <string>
+
+#include "../../include/navppo.h"
+#include "nav_common.h"
+#include "navsim_math.h"
+
+namespace {
+
+constexpr int OBS = NAVSIM_OBS_DIM;  // 16
+constexpr int X1 = 2 * OBS;          // 32
+constexpr int HID = NAVPPO_HIDDEN;   // 512
+constexpr float LEAK = 0.2f;         // nn.LeakyReLU(negative_slope=0.2), net_actor.py:37
+
+// canonical offsets inside one network's flat vector (navbot_ppo_b200/layout.py)
+constexpr int O_W1A = 0;                      // [512][16]
+constexpr int O_B1A = O_W1A + HID * OBS;      // 8192
+constexpr int O_W1B = O_B1A + HID;            // 8704   [16][512]
+constexpr int O_B1B = O_W1B + OBS * HID;      // 16896
+constexpr int O_W2A = O_B1B + OBS;            // 16912  [512][32]
+constexpr int O_B2A = O_W2A + HID * X1;       // 33296
+constexpr int O_W2B = O_B2A + HID;            // 33808  [32][512]
+constexpr int O_B2B = O_W2B + X1 * HID;       // 50192
+constexpr int O_HEAD = O_B2B + X1;            // 50224
+constexpr int ACTOR_HEAD = 2 * (X1 + 1);      // out1.weight, out1.bias, out2.weight, out2.bias
+constexpr int CRITIC_HEAD = X1 + 1;
+static_assert(O_HEAD + ACTOR_HEAD == NAVPPO_ACTOR_PARAMS, "actor layout");
+static_assert(O_HEAD + CRITIC_HEAD == NAVPPO_CRITIC_PARAMS, "critic layout");
+
+// "kernel layout" of one network: same regions, but the two fc2 matrices are stored
+// transposed ([hidden][out]) so that everything a hidden unit touches is contiguous.
+// canonical index -> kernel-layout index
+__host__ __device__ inline int klayout(int i) {
+  if (i >= O_W1B && i < O_B1B) { const int r = i - O_W1B; return O_W1B + (r % HID) * OBS + r / HID; }
+  if (i >= O_W2B && i < O_B2B) { const int r = i - O_W2B; return O_W2B + (r % HID) * X1 + r / HID; }
+  return i;
+}
+constexpr int NET_ROW = NAVPPO_CRITIC_OFFSET;  // 50304: padded length of one network's vector
+
+__device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : LEAK * x; }
+__device__ __forceinline__ float dlrelu(float x) { return x > 0.f ? 1.f : LEAK; }
+
+extern __shared__ __align__(16) unsigned char ppo_smem[];
+
+// ----------------------------------------------------------------------------------------
+// compute_rtgs / GAE: one thread per agent walks its column backwards.
+// ----------------------------------------------------------------------------------------
+__global__ void rtg_scan_kernel(const float* __restrict__ rew, const uint8_t* __restrict__ term,
+                                const float* __restrict__ values, const float* __restrict__ last_value, double gamma,
+                                double lam, float* __restrict__ out, int H, int N) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double acc = 0.0;
+  double next_v = (values && last_value) ? (double)last_value[n] : 0.0;
+  for (int t = H - 1; t >= 0; --t) {
+    const size_t i = (size_t)t * N + n;
+    const bool boundary = term[i] != 0;
+    if (values) {
+      const double live = boundary ? 0.0 : 1.0;
+      const double v = (double)values[i];
+      const double delta = (double)rew[i] + gamma * next_v * live - v;
+      acc = delta + gamma * lam * live * acc;
+      next_v = v;
+    } else {
+      if (boundary) acc = 0.0;                    // ppo.py:659 discounted_reward = 0
+      acc = (double)rew[i] + acc * gamma;         // ppo.py:664
+    }
+    out[i] = (float)acc;                          // ppo.py:669
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// Inference: thread per sample, the whole network (kernel layout) resident in shared memory
+// and read as warp-wide broadcasts.
+// ----------------------------------------------------------------------------------------
+constexpr int S_W1A = 0, S_W1BT = S_W1A + HID * OBS, S_W2A = S_W1BT + HID * OBS, S_W2BT = S_W2A + HID * X1,
+              S_B1A = S_W2BT + HID * X1, S_B2A = S_B1A + HID, S_B1B = S_B2A + HID, S_B2B = S_B1B + OBS,
+              S_HEAD = S_B2B + X1, S_TOTAL = S_HEAD + ACTOR_HEAD;  // 50290 floats = 201,160 B
+
+__device__ __forceinline__ void stage_network(float* s, const float* __restrict__ p, int head) {
+  for (int i = threadIdx.x; i < HID * OBS; i += blockDim.x) {
+    s[S_W1A + i] = p[O_W1A + i];
+    s[S_W1BT + (i % HID) * OBS + i / HID] = p[O_W1B + i];
+  }
+  for (int i = threadIdx.x; i < HID * X1; i += blockDim.x) {
+    s[S_W2A + i] = p[O_W2A + i];
+    s[S_W2BT + (i % HID) * X1 + i / HID] = p[O_W2B + i];
+  }
+  for (int i = threadIdx.x; i < HID; i += blockDim.x) {
+    s[S_B1A + i] = p[O_B1A + i];
+    s[S_B2A + i] = p[O_B2A + i];
+  }
+  if (threadIdx.x < OBS) s[S_B1B + threadIdx.x] = p[O_B1B + threadIdx.x];
+  if (threadIdx.x < X1) s[S_B2B + threadIdx.x] = p[O_B2B + threadIdx.x];
+  for (int i = threadIdx.x; i < head; i += blockDim.x) s[S_HEAD + i] = p[O_HEAD + i];
+}
+
+// One residual block for one sample: u = x + Wb lrelu(Wa x + ba) + bb, two hidden units per
+// trip for instruction-level parallelism.  Wa rows and WbT rows are IN contiguous floats.
+template <int IN>
+__device__ __forceinline__ void resblock_fwd(const float* __restrict__ sWa, const float* __restrict__ sBa,
+                                             const float* __restrict__ sWbT, const float* __restrict__ sBb,
+                                             const float (&x)[IN], float (&u)[IN], int j0, int j1) {
+#pragma unroll 1
+  for (int j = j0; j < j1; j += 2) {
+    float z0 = sBa[j], z1 = sBa[j + 1];
+    const float4* wa0 = reinterpret_cast<const float4*>(sWa + (size_t)j * IN);
+    const float4* wa1 = reinterpret_cast<const float4*>(sWa + (size_t)(j + 1) * IN);
+#pragma unroll
+    for (int q = 0; q < IN / 4; ++q) {
+      const float4 a = wa0[q], b = wa1[q];
+      z0 = fmaf(a.x, x[4 * q], z0); z1 = fmaf(b.x, x[4 * q], z1);
+      z0 = fmaf(a.y, x[4 * q + 1], z0); z1 = fmaf(b.y, x[4 * q + 1], z1);
+      z0 = fmaf(a.z, x[4 * q + 2], z0); z1 = fmaf(b.z, x[4 * q + 2], z1);
+      z0 = fmaf(a.w, x[4 * q + 3], z0); z1 = fmaf(b.w, x[4 * q + 3], z1);
+    }
+    const float h0 = lrelu(z0), h1 = lrelu(z1);
+    const float4* wb0 = reinterpret_cast<const float4*>(sWbT + (size_t)j * IN);
+    const float4* wb1 = reinterpret_cast<const float4*>(sWbT + (size_t)(j + 1) * IN);
+#pragma unroll
+    for (int q = 0; q < IN / 4; ++q) {
+      const float4 a = wb0[q], b = wb1[q];
+      u[4 * q] = fmaf(a.x, h0, u[4 * q]); u[4 * q + 1] = fmaf(a.y, h0, u[4 * q + 1]);
+      u[4 * q + 2] = fmaf(a.z, h0, u[4 * q + 2]); u[4 * q + 3] = fmaf(a.w, h0, u[4 * q + 3]);
+      u[4 * q] = fmaf(b.x, h1, u[4 * q]); u[4 * q + 1] = fmaf(b.y, h1, u[4 * q + 1]);
+      u[4 * q + 2] = fmaf(b.z, h1, u[4 * q + 2]); u[4 * q + 3] = fmaf(b.w, h1, u[4 * q + 3]);
+    }
+  }
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// log N(a; mu, var I), k = 2: -1/2 |a - mu|^2 / var - ln(2 pi) - ln(var)   (ppo.py:704,735)
+__device__ __forceinline__ float gauss_logp(float a0, float a1, float m0, float m1, float var) {
+  const float d0 = a0 - m0, d1 = a1 - m1;
+  return -0.5f * (d0 * d0 + d1 * d1) / var - 1.8378770664093453f - logf(var);
+}
+
+enum { INFER_FORWARD = 0, INFER_ACT = 1, INFER_EVALUATE = 2 };
+
+struct InferArgs {
+  const float* params;   // flat [actor | critic]
+  const float* obs;      // [T,16]
+  int T;
+  float var;
+  // forward
+  float* mu;             // [T,2] or null
+  float* v;              // [T]   or null
+  // act
+  uint64_t seed;
+  int64_t agent_off;
+  uint32_t draw;
+  const float* noise_in; // [T,2] or null
+  float* act;            // [T,2]
+  float* logp;           // [T]
+  // evaluate
+  const float* act_in;   // [T,2]
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) mlp_infer_kernel(InferArgs a) {
+  const int net = blockIdx.y;  // 0 actor, 1 critic
+  if (MODE == INFER_FORWARD && ((net == 0 && !a.mu) || (net == 1 && !a.v))) return;
+  float* s = reinterpret_cast<float*>(ppo_smem);
+  stage_network(s, a.params + (net ? NAVPPO_CRITIC_OFFSET : 0), net ? CRITIC_HEAD : ACTOR_HEAD);
+  __syncthreads();
+  for (int base = blockIdx.x * blockDim.x; base < a.T; base += gridDim.x * blockDim.x) {
+    const int i = base + threadIdx.x;
+    if (i >= a.T) continue;
+    float x1[X1], u1[OBS], u2[X1];
+    {
+      const float4* o = reinterpret_cast<const float4*>(a.obs + (size_t)i * OBS);
+#pragma unroll
+      for (int q = 0; q < OBS / 4; ++q) {
+        const float4 t = o[q];
+        x1[4 * q] = t.x; x1[4 * q + 1] = t.y; x1[4 * q + 2] = t.z; x1[4 * q + 3] = t.w;
+      }
+    }
+    {
+      float x0[OBS];
+#pragma unroll
+      for (int k = 0; k < OBS; ++k) { x0[k] = x1[k]; u1[k] = x0[k] + s[S_B1B + k]; }
+      resblock_fwd<OBS>(s + S_W1A, s + S_B1A, s + S_W1BT, s + S_B1B, x0, u1, 0, HID);
+    }
+#pragma unroll
+    for (int k = 0; k < OBS; ++k) x1[OBS + k] = lrelu(u1[k]);
+#pragma unroll
+    for (int k = 0; k < X1; ++k) u2[k] = x1[k] + s[S_B2B + k];
+    resblock_fwd<X1>(s + S_W2A, s + S_B2A, s + S_W2BT, s + S_B2B, x1, u2, 0, HID);
+    float o1 = s[S_HEAD + X1], o2 = (net == 0) ? s[S_HEAD + 2 * X1 + 1] : 0.f;
+#pragma unroll
+    for (int k = 0; k < X1; ++k) {
+      const float y = lrelu(u2[k]);
+      o1 = fmaf(s[S_HEAD + k], y, o1);
+      if (net == 0) o2 = fmaf(s[S_HEAD + X1 + 1 + k], y, o2);
+    }
+    if (net == 1) {                      // critic: V = out(X), net_critic.py:129
+      a.v[i] = o1;
+      continue;
+    }
+    const float m0 = sigmoidf_(o1), m1 = tanhf(o2);  // net_actor.py:141-142
+    if (MODE == INFER_FORWARD) {
+      reinterpret_cast<float2*>(a.mu)[i] = make_float2(m0, m1);
+    } else if (MODE == INFER_ACT) {
+      float e0, e1;
+      if (a.noise_in) {
+        const float2 e = reinterpret_cast<const float2*>(a.noise_in)[i];
+        e0 = e.x; e1 = e.y;
+      } else {  // Box-Muller on two Philox words
+        uint32_t r[4];
+        const uint64_t agent = (uint64_t)(a.agent_off + i);
+        nv_philox4x32_10(a.draw, 2u, (uint32_t)agent, (uint32_t)(agent >> 32), (uint32_t)a.seed,
+                         (uint32_t)(a.seed >> 32), r);
+        const float uu = ((float)(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0, 1)
+        const float vv = ((float)(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float rad = sqrtf(-2.0f * logf(uu));
+        float sn, cs;
+        sincosf(6.283185307179586f * vv, &sn, &cs);
+        e0 = rad * cs; e1 = rad * sn;
+      }
+      const float sd = sqrtf(a.var);
+      float a0 = fmaf(sd, e0, m0), a1 = fmaf(sd, e1, m1);       // dist.sample(), ppo.py:698-699
+      a0 = fminf(fmaxf(a0, 0.f), 1.f);                          // ppo.py:701
+      a1 = fminf(fmaxf(a1, -1.f), 1.f);                         // ppo.py:702
+      reinterpret_cast<float2*>(a.act)[i] = make_float2(a0, a1);
+      a.logp[i] = gauss_logp(a0, a1, m0, m1, a.var);            // ppo.py:704 (at the clamped action)
+      if (a.mu) reinterpret_cast<float2*>(a.mu)[i] = make_float2(m0, m1);
+    } else {
+      const float2 av = reinterpret_cast<const float2*>(a.act_in)[i];
+      a.logp[i] = gauss_logp(av.x, av.y, m0, m1, a.var);        // ppo.py:734-735
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// Advantage (ppo.py:277,284)
+// ----------------------------------------------------------------------------------------
+__global__ void adv_stats_kernel(const float* __restrict__ rtg, const float* __restrict__ v, int T, double* stats) {
+  double s = 0.0, q = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T; i += gridDim.x * blockDim.x) {
+    const double a = (double)rtg[i] - (double)v[i];
+    s += a; q += a * a;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_down_sync(0xffffffffu, s, o);
+    q += __shfl_down_sync(0xffffffffu, q, o);
+  }
+  __shared__ double ws[32], wq[32];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { ws[w] = s; wq[w] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tq = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { ts += ws[k]; tq += wq[k]; }
+    atomicAdd(&stats[0], ts);
+    atomicAdd(&stats[1], tq);
+    if (blockIdx.x == 0) atomicAdd(&stats[2], (double)T);
+  }
+}
+
+__global__ void adv_normalize_kernel(const float* __restrict__ rtg, const float* __restrict__ v, int T,
+                                     const double* __restrict__ stats, float* __restrict__ adv) {
+  const double n = stats[2];
+  const double mean = stats[0] / n;
+  double var = (stats[1] - n * mean * mean) / (n - 1.0);   // torch.std: unbiased
+  if (!(var > 0.0)) var = 0.0;
+  const float m = (float)mean, inv = (float)(1.0 / (sqrt(var) + 1e-10));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T; i += gridDim.x * blockDim.x)
+    adv[i] = ((rtg[i] - v[i]) - m) * inv;
+}
+
+// ----------------------------------------------------------------------------------------
+// Gradient kernel: blockIdx.y = network, each CTA walks tiles of GM samples (thread = sample
+// for the per-sample chains, thread = weight patch for the weight-gradient products) and
+// accumulates into its own row of the partial-gradient workspace (kernel layout).
+// ----------------------------------------------------------------------------------------
+constexpr int GM = 128;          // samples per tile == threads per CTA
+constexpr int JC = 32;           // hidden units per chunk
+constexpr int SROW = GM + 1;     // padded row of the [JC][GM] chunk buffers (bank spread)
+
+struct GradArgs {
+  const float* params;
+  const float* obs; const float* act; const float* logp_old; const float* adv; const float* rtg;
+  int T;
+  float inv_n;        // 1 / n_global
+  float var, clip;
+  float* gpart;       // [2][gridDim.x][NET_ROW]
+  double* mpart;      // [2][gridDim.x][4]
+};
+
+// shared-memory carve-up (floats)
+constexpr int G_SX = 0;                       // [GM][32]  x1 = [x0 | y1]
+constexpr int G_SGU = G_SX + GM * X1;         // [GM][32]  g_u2, later g_u1 in [..][0:16]
+constexpr int G_SH = G_SGU + GM * X1;         // [JC][SROW] h of the chunk
+constexpr int G_SG = G_SH + JC * SROW;        // [JC][SROW] g_z of the chunk
+constexpr int G_SWA = G_SG + JC * SROW;       // [JC][32]  fc1 rows of the chunk
+constexpr int G_SWBT = G_SWA + JC * X1;       // [JC][32]  fc2 columns of the chunk
+constexpr int G_SBA = G_SWBT + JC * X1;       // [JC]
+constexpr int G_SRED = G_SBA + JC;            // [4 warps][72] head-gradient partials
+constexpr int G_TOTAL = G_SRED + 4 * 72;
+constexpr size_t GRAD_SMEM = (size_t)G_TOTAL * sizeof(float);
+
+template <int IN>
+__device__ __forceinline__ void stage_chunk(float* s, const float* __restrict__ p, int o_wa, int o_ba, int o_wb, int c) {
+  // fc1 rows c*JC .. c*JC+JC-1 (contiguous in the canonical layout) and the matching fc2 columns
+  for (int i = threadIdx.x; i < JC * IN; i += GM) {
+    s[G_SWA + i] = p[o_wa + c * JC * IN + i];
+    const int jl = i % JC, k = i / JC;        // consecutive threads -> consecutive hidden units
+    s[G_SWBT + jl * IN + k] = p[o_wb + k * HID + c * JC + jl];
+  }
+  if (threadIdx.x < JC) s[G_SBA + threadIdx.x] = p[o_ba + c * JC + threadIdx.x];
+}
+
+template <int IN>
+__device__ __forceinline__ void block_forward(float* s, const float* __restrict__ p, int o_wa, int o_ba, int o_wb,
+                                              const float (&x)[IN], float (&u)[IN]) {
+  for (int c = 0; c < HID / JC; ++c) {
+    stage_chunk<IN>(s, p, o_wa, o_ba, o_wb, c);
+    __syncthreads();
+    resblock_fwd<IN>(s + G_SWA, s + G_SBA, s + G_SWBT, nullptr, x, u, 0, JC);
+    __syncthreads();
+  }
+}
+
+// Backward of one residual block over all hidden chunks.  gu = dL/du of this block (per
+// sample, in registers AND already stored to sGU rows), x = block input (registers AND sX rows).
+// gx accumulates W_a^T g_z (only when WANT_GX).  Weight gradients go to this CTA's gpart row.
+template <int IN, bool WANT_GX>
+__device__ __forceinline__ void block_backward(float* s, const float* __restrict__ p, float* __restrict__ grow, int o_wa,
+                                               int o_ba, int o_wb, const float (&x)[IN], const float (&gu)[IN],
+                                               float (&gx)[IN]) {
+  const int m = threadIdx.x;
+  constexpr int KQ = IN / 4;                  // outputs per thread along k (8 for IN=32, 4 for IN=16)
+  const int pj = m >> 2, pk = (m & 3) * KQ;   // weight patch of this thread in phase B
+  for (int c = 0; c < HID / JC; ++c) {
+    stage_chunk<IN>(s, p, o_wa, o_ba, o_wb, c);
+    __syncthreads();
+    // ---- phase A: per-sample chain through the chunk's hidden units
+#pragma unroll 1
+    for (int jl = 0; jl < JC; ++jl) {
+      float z = s[G_SBA + jl], gh = 0.f;
+      const float4* wa = reinterpret_cast<const float4*>(s + G_SWA + jl * IN);
+      const float4* wb = reinterpret_cast<const float4*>(s + G_SWBT + jl * IN);
+#pragma unroll
+      for (int q = 0; q < IN / 4; ++q) {
+        const float4 a = wa[q], b = wb[q];
+        z = fmaf(a.x, x[4 * q], z); z = fmaf(a.y, x[4 * q + 1], z);
+        z = fmaf(a.z, x[4 * q + 2], z); z = fmaf(a.w, x[4 * q + 3], z);
+        gh = fmaf(b.x, gu[4 * q], gh); gh = fmaf(b.y, gu[4 * q + 1], gh);
+        gh = fmaf(b.z, gu[4 * q + 2], gh); gh = fmaf(b.w, gu[4 * q + 3], gh);
+      }
+      const float gz = gh * dlrelu(z);
+      s[G_SH + jl * SROW + m] = lrelu(z);
+      s[G_SG + jl * SROW + m] = gz;
+      if (WANT_GX) {
+#pragma unroll
+        for (int q = 0; q < IN / 4; ++q) {
+          const float4 a = wa[q];
+          gx[4 * q] = fmaf(a.x, gz, gx[4 * q]); gx[4 * q + 1] = fmaf(a.y, gz, gx[4 * q + 1]);
+          gx[4 * q + 2] = fmaf(a.z, gz, gx[4 * q + 2]); gx[4 * q + 3] = fmaf(a.w, gz, gx[4 * q + 3]);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase B: dWa[j][k] = sum_m g_z[j][m] x[m][k];  dWbT[j][k] = sum_m h[j][m] g_u[m][k]
+    {
+      float da[KQ], db[KQ], dbias = 0.f;
+#pragma unroll
+      for (int i = 0; i < KQ; ++i) { da[i] = 0.f; db[i] = 0.f; }
+      const float* hrow = s + G_SH + pj * SROW;
+      const float* grow_s = s + G_SG + pj * SROW;
+#pragma unroll 4
+      for (int mm = 0; mm < GM; ++mm) {
+        const float g = grow_s[mm], h = hrow[mm];
+        dbias += g;
+        const float4* xv = reinterpret_cast<const float4*>(s + G_SX + mm * X1 + pk);
+        const float4* gv = reinterpret_cast<const float4*>(s + G_SGU + mm * X1 + pk);
+#pragma unroll
+        for (int q = 0; q < KQ / 4; ++q) {
+          const float4 xx = xv[q], gg = gv[q];
+          da[4 * q] = fmaf(g, xx.x, da[4 * q]); da[4 * q + 1] = fmaf(g, xx.y, da[4 * q + 1]);
+          da[4 * q + 2] = fmaf(g, xx.z, da[4 * q + 2]); da[4 * q + 3] = fmaf(g, xx.w, da[4 * q + 3]);
+          db[4 * q] = fmaf(h, gg.x, db[4 * q]); db[4 * q + 1] = fmaf(h, gg.y, db[4 * q + 1]);
+          db[4 * q + 2] = fmaf(h, gg.z, db[4 * q + 2]); db[4 * q + 3] = fmaf(h, gg.w, db[4 * q + 3]);
+        }
+      }
+      const int j = c * JC + pj;
+      float* ga = grow + o_wa + j * IN + pk;
+      float* gb = grow + o_wb + j * IN + pk;   // kernel layout: fc2 transposed
+#pragma unroll
+      for (int i = 0; i < KQ; ++i) { ga[i] += da[i]; gb[i] += db[i]; }
+      if ((m & 3) == 0) grow[o_ba + j] += dbias;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(GM) mlp_grad_kernel(GradArgs a) {
+  float* s = reinterpret_cast<float*>(ppo_smem);
+  const int net = blockIdx.y, m = threadIdx.x, warp = m >> 5, lane = m & 31;
+  const float* __restrict__ p = a.params + (net ? NAVPPO_CRITIC_OFFSET : 0);
+  float* __restrict__ grow = a.gpart + ((size_t)net * gridDim.x + blockIdx.x) * NET_ROW;
+  for (int i = m; i < NET_ROW; i += GM) grow[i] = 0.f;
+  double macc[4] = {0.0, 0.0, 0.0, 0.0};
+  const int ntiles = (a.T + GM - 1) / GM;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int i = tile * GM + m;
+    const bool valid = i < a.T;
+    float x1[X1], u1[OBS], u2[X1];
+    if (valid) {
+      const float4* o = reinterpret_cast<const float4*>(a.obs + (size_t)i * OBS);
+#pragma unroll
+      for (int q = 0; q < OBS / 4; ++q) {
+        const float4 t = o[q];
+        x1[4 * q] = t.x; x1[4 * q + 1] = t.y; x1[4 * q + 2] = t.z; x1[4 * q + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < OBS; ++k) x1[k] = 0.f;
+    }
+    // ---------------- forward
+    {
+      float x0[OBS];
+#pragma unroll
+      for (int k = 0; k < OBS; ++k) { x0[k] = x1[k]; u1[k] = x0[k] + p[O_B1B + k]; }
+      block_forward<OBS>(s, p, O_W1A, O_B1A, O_W1B, x0, u1);
+    }
+#pragma unroll
+    for (int k = 0; k < OBS; ++k) x1[OBS + k] = lrelu(u1[k]);
+#pragma unroll
+    for (int k = 0; k < X1; ++k) u2[k] = x1[k] + p[O_B2B + k];
+    block_forward<X1>(s, p, O_W2A, O_B2A, O_W2B, x1, u2);
+    // ---------------- heads, losses, dL/d(head pre-activations)
+    float y2[X1];
+#pragma unroll
+    for (int k = 0; k < X1; ++k) y2[k] = lrelu(u2[k]);
+    float go1 = 0.f, go2 = 0.f;     // dL/d o1, dL/d o2 (critic: go1 = dL/dV)
+    if (net == 0) {
+      float o1 = p[O_HEAD + X1], o2 = p[O_HEAD + 2 * X1 + 1];
+#pragma unroll
+      for (int k = 0; k < X1; ++k) { o1 = fmaf(p[O_HEAD + k], y2[k], o1); o2 = fmaf(p[O_HEAD + X1 + 1 + k], y2[k], o2); }
+      const float m0 = sigmoidf_(o1), m1 = tanhf(o2);
+      if (valid) {
+        const float2 av = reinterpret_cast<const float2*>(a.act)[i];
+        const float lp = gauss_logp(av.x, av.y, m0, m1, a.var);
+        const float lr = lp - a.logp_old[i];
+        const float ratio = expf(lr);                                          // ppo.py:316
+        const float A = a.adv[i];
+        const float s1 = ratio * A;                                            // ppo.py:319
+        const float s2 = fminf(fmaxf(ratio, 1.f - a.clip), 1.f + a.clip) * A;  // ppo.py:320
+        macc[0] += (double)(-fminf(s1, s2));                                   // ppo.py:342
+        macc[2] += (double)((ratio - 1.f) - lr);                               // ppo.py:326
+        macc[3] += (fabsf(ratio - 1.f) > a.clip) ? 1.0 : 0.0;                  // ppo.py:335
+        // torch.min splits ties and clamp passes gradient on its closed interval:
+        // d(-min(s1, s2))/d ratio = -A where s1 <= s2, 0 where the clipped branch wins
+        const float g_lp = (s1 <= s2 ? -A : 0.f) * a.inv_n * ratio;
+        const float gm0 = g_lp * (av.x - m0) / a.var, gm1 = g_lp * (av.y - m1) / a.var;
+        go1 = gm0 * m0 * (1.f - m0);                                           // sigmoid'
+        go2 = gm1 * (1.f - m1 * m1);                                           // tanh'
+      }
+    } else {
+      float v = p[O_HEAD + X1];
+#pragma unroll
+      for (int k = 0; k < X1; ++k) v = fmaf(p[O_HEAD + k], y2[k], v);
+      if (valid) {
+        const float d = v - a.rtg[i];
+        macc[1] += (double)(d * d);                                            // ppo.py:343 MSELoss
+        go1 = 2.f * d * a.inv_n;
+      }
+    }
+    // head-weight gradients: warp-reduce g_o * y2[k], fixed-order sum over the 4 warps
+    {
+      const int nh = (net == 0) ? 2 : 1;
+      for (int hd = 0; hd < nh; ++hd) {
+        const float g = hd ? go2 : go1;
+        float bsum = g;
+        for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+#pragma unroll
+        for (int k = 0; k < X1; ++k) {
+          float t = g * y2[k];
+          for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+          if (lane == 0) s[G_SRED + warp * 72 + hd * (X1 + 1) + k] = t;
+        }
+        if (lane == 0) s[G_SRED + warp * 72 + hd * (X1 + 1) + X1] = bsum;
+      }
+    }
+    // dL/dy2 -> dL/du2; publish x1 and g_u2 rows for the weight-gradient products
+    float gu2[X1], gx1[X1];
+#pragma unroll
+    for (int k = 0; k < X1; ++k) {
+      const float gy = (net == 0) ? fmaf(p[O_HEAD + k], go1, p[O_HEAD + X1 + 1 + k] * go2) : p[O_HEAD + k] * go1;
+      gu2[k] = gy * dlrelu(u2[k]);
+      gx1[k] = gu2[k];                         // skip connection of the residual block
+    }
+    {
+      float4* sx = reinterpret_cast<float4*>(s + G_SX + m * X1);
+      float4* sg = reinterpret_cast<float4*>(s + G_SGU + m * X1);
+#pragma unroll
+      for (int q = 0; q < X1 / 4; ++q) {
+        sx[q] = make_float4(x1[4 * q], x1[4 * q + 1], x1[4 * q + 2], x1[4 * q + 3]);
+        sg[q] = make_float4(gu2[4 * q], gu2[4 * q + 1], gu2[4 * q + 2], gu2[4 * q + 3]);
+      }
+    }
+    __syncthreads();
+    {
+      const int nhead = (net == 0) ? ACTOR_HEAD : CRITIC_HEAD;
+      if (m < nhead)
+        grow[O_HEAD + m] += ((s[G_SRED + m] + s[G_SRED + 72 + m]) + s[G_SRED + 144 + m]) + s[G_SRED + 216 + m];
+      if (m < X1) {                            // fc2 bias of block 2: sum over samples of g_u2
+        float t = 0.f;
+        for (int mm = 0; mm < GM; ++mm) t += s[G_SGU + mm * X1 + m];
+        grow[O_B2B + m] += t;
+      }
+    }
+    // ---------------- backward, block 2
+    block_backward<X1, true>(s, p, grow, O_W2A, O_B2A, O_W2B, x1, gu2, gx1);
+    // ---------------- backward, block 1 (its input x0 = sX[..][0:16]; no gradient w.r.t. obs needed)
+    float gu1[OBS], x0[OBS], dummy[OBS];
+#pragma unroll
+    for (int k = 0; k < OBS; ++k) { gu1[k] = gx1[OBS + k] * dlrelu(u1[k]); x0[k] = x1[k]; dummy[k] = 0.f; }
+    {
+      float4* sg = reinterpret_cast<float4*>(s + G_SGU + m * X1);
+#pragma unroll
+      for (int q = 0; q < OBS / 4; ++q) sg[q] = make_float4(gu1[4 * q], gu1[4 * q + 1], gu1[4 * q + 2], gu1[4 * q + 3]);
+    }
+    __syncthreads();
+    if (m < OBS) {
+      float t = 0.f;
+      for (int mm = 0; mm < GM; ++mm) t += s[G_SGU + mm * X1 + m];
+      grow[O_B1B + m] += t;
+    }
+    block_backward<OBS, false>(s, p, grow, O_W1A, O_B1A, O_W1B, x0, gu1, dummy);
+  }
+  // per-CTA metric partials: fixed-order sum over the CTA's threads
+  __syncthreads();
+  double* red = reinterpret_cast<double*>(s);  // reuse: [4][GM] doubles = 4 KB
+#pragma unroll
+  for (int q = 0; q < 4; ++q) red[q * GM + m] = macc[q];
+  __syncthreads();
+  if (m < 4) {
+    double t = 0.0;
+    for (int mm = 0; mm < GM; ++mm) t += red[m * GM + mm];
+    a.mpart[((size_t)net * gridDim.x + blockIdx.x) * 4 + m] = t;
+  }
+}
+
+// flat gradient (canonical layout) = fixed-order sum of the CTA rows; block 0 also folds the
+// metric partials.
+__global__ void grad_reduce_kernel(const float* __restrict__ gpart, const double* __restrict__ mpart, int rows,
+                                   float inv_n, float* __restrict__ grad, double* __restrict__ metrics) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < NAVPPO_FLAT) {
+    const int net = i >= NAVPPO_CRITIC_OFFSET;
+    const int li = i - (net ? NAVPPO_CRITIC_OFFSET : 0);
+    const int n = net ? NAVPPO_CRITIC_PARAMS : NAVPPO_ACTOR_PARAMS;
+    float t = 0.f;
+    if (li < n) {
+      const float* col = gpart + (size_t)net * rows * NET_ROW + klayout(li);
+      for (int r = 0; r < rows; ++r) t += col[(size_t)r * NET_ROW];
+    }
+    grad[i] = t;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 4) {
+    const int q = threadIdx.x;
+    const int net = (q == 1) ? 1 : 0;           // critic loss comes from the critic rows
+    double t = 0.0;
+    for (int r = 0; r < rows; ++r) t += mpart[((size_t)net * rows + r) * 4 + q];
+    metrics[q] = t * (double)inv_n;
+  }
+}
+
+// torch.optim.Adam (defaults) on the flat vector; per-block squared-gradient partials.
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m1, float* __restrict__ m2, float lr_over_bc1,
+                                                   float inv_sqrt_bc2, float b1, float b2, float eps,
+                                                   double* __restrict__ sq_part) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double sa = 0.0, sc = 0.0;
+  if (i < NAVPPO_FLAT) {
+    const float gi = g[i];
+    const float m = fmaf(1.f - b1, gi - m1[i], m1[i]);          // exp_avg.lerp_(grad, 1 - beta1)
+    const float v = fmaf(b2, m2[i], (1.f - b2) * gi * gi);      // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
+    m1[i] = m; m2[i] = v;
+    const float denom = sqrtf(v) * inv_sqrt_bc2 + eps;
+    p[i] = p[i] - lr_over_bc1 * (m / denom);
+    if (i < NAVPPO_CRITIC_OFFSET) sa = (double)gi * gi; else sc = (double)gi * gi;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    sa += __shfl_down_sync(0xffffffffu, sa, o);
+    sc += __shfl_down_sync(0xffffffffu, sc, o);
+  }
+  __shared__ double wa[8], wc[8];
+  if ((threadIdx.x & 31) == 0) { wa[threadIdx.x >> 5] = sa; wc[threadIdx.x >> 5] = sc; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ta = 0.0, tc = 0.0;
+    for (int k = 0; k < 8; ++k) { ta += wa[k]; tc += wc[k]; }
+    sq_part[2 * blockIdx.x] = ta;
+    sq_part[2 * blockIdx.x + 1] = tc;
+  }
+}
+
+__global__ void gradnorm_finalize_kernel(const double* __restrict__ sq_part, int nblocks, double* __restrict__ metrics) {
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int b = 0; b < nblocks; ++b) t += sq_part[2 * b + threadIdx.x];
+    metrics[NAVPPO_M_ACTOR_GRAD_SQ + threadIdx.x] = t;
+  }
+}
+
+}  // namespace
+
+// ========================================================================================
+// C-ABI
+// ========================================================================================
+struct navppo {
+  navppo_cfg cfg;
+  int grad_rows = 0;          // CTAs per network of mlp_grad_kernel
+  float* gpart = nullptr;     // [2][grad_rows][NET_ROW]
+  double* mpart = nullptr;    // [2][grad_rows][4]
+  double* sq_part = nullptr;  // [adam blocks][2]
+  double* adv_stats = nullptr;  // [3]
+  float* grad_ws = nullptr;   // [NAVPPO_FLAT] used by navppo_update
+  int sm_count = 148;
+  int64_t launches = 0;
+};
+
+namespace {
+
+constexpr int ADAM_BLOCK = 256;
+constexpr int ADAM_GRID = (NAVPPO_FLAT + ADAM_BLOCK - 1) / ADAM_BLOCK;
+constexpr size_t INFER_SMEM = (size_t)S_TOTAL * sizeof(float);
+
+int check_handle(const navppo* h) {
+  if (!h) return nav_fail(NAVSIM_EINVAL, "null navppo handle");
+  return NAVSIM_OK;
+}
+
+template <int MODE>
+int launch_infer(navppo* h, const InferArgs& a, bool both_nets, cudaStream_t s) {
+  if (a.T <= 0) return nav_fail(NAVSIM_EINVAL, "T must be positive");
+  // small batches (rollout): narrow CTAs so that every SM gets one; large batches: one
+  // 256-thread CTA per SM looping over its tiles
+  int block = 256;
+  if (a.T < h->sm_count * 256) block = (a.T >= h->sm_count * 128) ? 128 : 64;
+  int grid = (a.T + block - 1) / block;
+  if (grid > h->sm_count) grid = h->sm_count;
+  mlp_infer_kernel<MODE><<<dim3(grid, both_nets ? 2 : 1), block, INFER_SMEM, s>>>(a);
+  h->launches++;
+  NAV_CUDA_TRY(cudaGetLastError());
+  return NAVSIM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int navppo_default_cfg(navppo_cfg* cfg) {
+  if (!cfg) return nav_fail(NAVSIM_EINVAL, "cfg is null");
+  cfg->device = 0;
+  cfg->max_samples = 1 << 20;
+  cfg->precision = NAVPPO_FP32;
+  cfg->reserved0 = 0;
+  cfg->lr = 3e-4;         // main.py:472
+  cfg->beta1 = 0.9;       // torch.optim.Adam defaults (ppo.py:116-117)
+  cfg->beta2 = 0.999;
+  cfg->adam_eps = 1e-8;
+  cfg->clip = 0.2;        // main.py:473
+  return NAVSIM_OK;
+}
+
+int navppo_create(navppo_t** out, const navppo_cfg* cfg) {
+  if (!out || !cfg) return nav_fail(NAVSIM_EINVAL, "null argument");
+  *out = nullptr;
+  if (cfg->max_samples <= 0) return nav_fail(NAVSIM_EINVAL, "max_samples must be positive");
+  if (cfg->precision != NAVPPO_FP32) return nav_fail(NAVSIM_EINVAL, "unsupported precision mode");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return nav_fail(NAVSIM_ENODEV, "no CUDA device: the PPO kernels have no CPU fallback");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return nav_fail(NAVSIM_EINVAL, "device ordinal out of range");
+  NAV_CUDA_TRY(cudaSetDevice(cfg->device));
+  navppo* h = new (std::nothrow) navppo();
+  if (!h) return nav_fail(NAVSIM_ENOMEM, "host allocation failed");
+  h->cfg = *cfg;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+  const int tiles = (cfg->max_samples + GM - 1) / GM;
+  // 3 CTAs of the gradient kernel fit one SM (shared memory); the two networks share the grid
+  int rows = (h->sm_count * 3) / 2;
+  if (rows > tiles) rows = tiles;
+  if (rows < 1) rows = 1;
+  h->grad_rows = rows;
+  cudaError_t e = cudaMalloc(&h->gpart, (size_t)2 * rows * NET_ROW * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&h->mpart, (size_t)2 * rows * 4 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&h->sq_part, (size_t)ADAM_GRID * 2 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&h->adv_stats, 3 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&h->grad_ws, (size_t)NAVPPO_FLAT * sizeof(float));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_infer_kernel<INFER_FORWARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INFER_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_infer_kernel<INFER_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INFER_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_infer_kernel<INFER_EVALUATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INFER_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAD_SMEM);
+  if (e != cudaSuccess) {
+    navppo_destroy(h);
+    return nav_fail(e == cudaErrorMemoryAllocation ? NAVSIM_ENOMEM : NAVSIM_ECUDA,
+                    std::string("navppo_create: ") + cudaGetErrorString(e));
+  }
+  *out = h;
+  return NAVSIM_OK;
+}
+
+int navppo_destroy(navppo_t* h) {
+  if (!h) return NAVSIM_OK;
+  cudaSetDevice(h->cfg.device);
+  if (h->gpart) cudaFree(h->gpart);
+  if (h->mpart) cudaFree(h->mpart);
+  if (h->sq_part) cudaFree(h->sq_part);
+  if (h->adv_stats) cudaFree(h->adv_stats);
+  if (h->grad_ws) cudaFree(h->grad_ws);
+  delete h;
+  return NAVSIM_OK;
+}
+
+int64_t navppo_launch_count(const navppo_t* h) { return h ? h->launches : 0; }
+
+int navppo_rtg_scan(const float* rew, const uint8_t* term, const float* values, const float* last_value, double gamma,
+                    double lam, float* out, int32_t H, int32_t N, void* stream) {
+  if (!rew || !term || !out) return nav_fail(NAVSIM_EINVAL, "null buffer");
+  if (H <= 0 || N <= 0) return nav_fail(NAVSIM_EINVAL, "H and N must be positive");
+  rtg_scan_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rew, term, values, last_value, gamma, lam, out, H, N);
+  NAV_CUDA_TRY(cudaGetLastError());
+  return NAVSIM_OK;
+}
+
+int navppo_forward(navppo_t* h, const float* params, const float* obs, int32_t T, float* mu, float* v, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (!params || !obs || (!mu && !v)) return nav_fail(NAVSIM_EINVAL, "null buffer");
+  InferArgs a{};
+  a.params = params; a.obs = obs; a.T = T; a.mu = mu; a.v = v; a.var = 1.f;
+  return launch_infer<INFER_FORWARD>(h, a, v != nullptr, (cudaStream_t)stream);
+}
+
+int navppo_act(navppo_t* h, const float* params, const float* obs, int32_t N, double var, uint64_t seed,
+               int64_t agent_id_offset, uint32_t draw, const float* noise_in, float* act, float* logp, float* mu_out,
+               void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (!params || !obs || !act || !logp) return nav_fail(NAVSIM_EINVAL, "null buffer");
+  if (!(var > 0.0)) return nav_fail(NAVSIM_EINVAL, "var must be positive");
+  InferArgs a{};
+  a.params = params; a.obs = obs; a.T = N; a.var = (float)var; a.seed = seed; a.agent_off = agent_id_offset;
+  a.draw = draw; a.noise_in = noise_in; a.act = act; a.logp = logp; a.mu = mu_out;
+  return launch_infer<INFER_ACT>(h, a, false, (cudaStream_t)stream);
+}
+
+int navppo_evaluate(navppo_t* h, const float* params, const float* obs, const float* act, int32_t T, double var,
+                    float* v, float* logp, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (!params || !obs || !act || !v || !logp) return nav_fail(NAVSIM_EINVAL, "null buffer");
+  if (!(var > 0.0)) return nav_fail(NAVSIM_EINVAL, "var must be positive");
+  InferArgs a{};
+  a.params = params; a.obs = obs; a.T = T; a.var = (float)var; a.act_in = act; a.v = v; a.logp = logp;
+  return launch_infer<INFER_EVALUATE>(h, a, true, (cudaStream_t)stream);
+}
+
+int navppo_adv_stats(const float* rtg, const float* v, int32_t T, double* stats, void* stream) {
+  if (!rtg || !v || !stats) return nav_fail(NAVSIM_EINVAL, "null buffer");
+  if (T <= 0) return nav_fail(NAVSIM_EINVAL, "T must be positive");
+  int grid = (T + 255) / 256;
+  if (grid > 592) grid = 592;
+  adv_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rtg, v, T, stats);
+  NAV_CUDA_TRY(cudaGetLastError());
+  return NAVSIM_OK;
+}
+
+int navppo_adv_normalize(const float* rtg, const float* v, int32_t T, const double* stats, float* adv, void* stream) {
+  if (!rtg || !v || !stats || !adv) return nav_fail(NAVSIM_EINVAL, "null buffer");
+  if (T <= 0) return nav_fail(NAVSIM_EINVAL, "T must be positive");
+  int grid = (T + 255) / 256;
+  if (grid > 1184) grid = 1184;
+  adv_normalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rtg, v, T, stats, adv);
+  NAV_CUDA_TRY(cudaGetLastError());
+  return NAVSIM_OK;
+}
+
+int navppo_grad(navppo_t* h, const float* params, const float* obs, const float* act, const float* logp_old,
+                const float* adv, const float* rtg, int32_t T, int64_t n_global, double var, float* grad,
+                double* metrics, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (!params || !obs || !act || !logp_old || !adv || !rtg || !grad || !metrics) return nav_fail(NAVSIM_EINVAL, "null buffer");
+  if (T <= 0 || T > h->cfg.max_samples) return nav_fail(NAVSIM_EINVAL, "T outside (0, max_samples]");
+  if (n_global < T) return nav_fail(NAVSIM_EINVAL, "n_global must be >= T");
+  if (!(var > 0.0)) return nav_fail(NAVSIM_EINVAL, "var must be positive");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int tiles = (T + GM - 1) / GM;
+  const int rows = tiles < h->grad_rows ? tiles : h->grad_rows;
+  GradArgs a{};
+  a.params = params; a.obs = obs; a.act = act; a.logp_old = logp_old; a.adv = adv; a.rtg = rtg; a.T = T;
+  a.inv_n = (float)(1.0 / (double)n_global); a.var = (float)var; a.clip = (float)h->cfg.clip;
+  a.gpart = h->gpart; a.mpart = h->mpart;
+  mlp_grad_kernel<<<dim3(rows, 2), GM, GRAD_SMEM, s>>>(a);
+  grad_reduce_kernel<<<(NAVPPO_FLAT + 255) / 256, 256, 0, s>>>(h->gpart, h->mpart, rows, a.inv_n, grad, metrics);
+  h->launches += 2;
+  NAV_CUDA_TRY(cudaGetLastError());
+  return NAVSIM_OK;
+}
+
+int navppo_adam(navppo_t* h, float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int32_t step,
+                double* metrics, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (!params || !grad || !exp_avg || !exp_avg_sq) return nav_fail(NAVSIM_EINVAL, "null buffer");
+  if (step < 1) return nav_fail(NAVSIM_EINVAL, "step is 1-based");
+  cudaStream_t s = (cudaStream_t)stream;
+  const double b1 = h->cfg.beta1, b2 = h->cfg.beta2;
+  const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
+  adam_kernel<<<ADAM_GRID, ADAM_BLOCK, 0, s>>>(params, grad, exp_avg, exp_avg_sq, (float)(h->cfg.lr / bc1),
+                                              (float)(1.0 / sqrt(bc2)), (float)b1, (float)b2, (float)h->cfg.adam_eps,
+                                              h->sq_part);
+  h->launches++;
+  if (metrics) {
+    gradnorm_finalize_kernel<<<1, 32, 0, s>>>(h->sq_part, ADAM_GRID, metrics);
+    h->launches++;
+  }
+  NAV_CUDA_TRY(cudaGetLastError());
+  return NAVSIM_OK;
+}
+
+int navppo_update(navppo_t* h, float* params, float* exp_avg, float* exp_avg_sq, int32_t step0, const float* obs,
+                  const float* act, const float* logp_old, const float* rtg, int32_t T, double var, int32_t epochs,
+                  float* adv_ws, float* v_ws, double* metrics, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (!adv_ws || !v_ws || !metrics) return nav_fail(NAVSIM_EINVAL, "null buffer");
+  if (epochs < 0 || step0 < 0) return nav_fail(NAVSIM_EINVAL, "negative epochs / step0");
+  cudaStream_t s = (cudaStream_t)stream;
+  // ppo.py:275-284: V = evaluate(...); A = rtg - V; normalise.  adv_ws doubles as the
+  // throw-away log-prob output of this first evaluate.
+  if (int rc = navppo_evaluate(h, params, obs, act, T, var, v_ws, adv_ws, stream)) return rc;
+  NAV_CUDA_TRY(cudaMemsetAsync(h->adv_stats, 0, 3 * sizeof(double), s));
+  if (int rc = navppo_adv_stats(rtg, v_ws, T, h->adv_stats, stream)) return rc;
+  if (int rc = navppo_adv_normalize(rtg, v_ws, T, h->adv_stats, adv_ws, stream)) return rc;
+  h->launches += 2;
+  for (int e = 0; e < epochs; ++e) {  // ppo.py:305
+    double* mrow = metrics + (size_t)e * NAVPPO_NUM_METRICS;
+    if (int rc = navppo_grad(h, params, obs, act, logp_old, adv_ws, rtg, T, (int64_t)T, var, h->grad_ws, mrow, stream)) return rc;
+    if (int rc = navppo_adam(h, params, h->grad_ws, exp_avg, exp_avg_sq, step0 + e + 1, mrow, stream)) return rc;
+  }
+  return NAVSIM_OK;
+}
+
+}  // extern "C"

@@ -31,16 +31,24 @@
 #include <string>
 
 #include "../../include/navsim.h"
+#include "nav_common.h"
 #include "navsim_math.h"
 
 namespace {
 
 thread_local std::string g_err;
 
-int fail(int code, const std::string& msg) {
+}  // namespace
+
+// shared with navppo_kernels.cu (nav_common.h)
+int nav_fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
 }
+
+namespace {
+
+int fail(int code, const std::string& msg) { return nav_fail(code, msg); }
 
 #define CUDA_TRY(expr)                                                                     \
   do {                                                                                     \
