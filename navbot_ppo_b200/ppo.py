@@ -242,8 +242,9 @@ class PPO:
         ends = np.cumsum([l for l in lens if l > 0]) - 1
         term[ends] = 1
         rew = torch.from_numpy(flat).to(self.device)
+        term_d = torch.from_numpy(term).to(self.device)
         out = torch.empty_like(rew)
-        _capi.check(_capi.lib().navppo_rtg_scan(rew.data_ptr(), torch.from_numpy(term).to(self.device).data_ptr(), None,
+        _capi.check(_capi.lib().navppo_rtg_scan(rew.data_ptr(), term_d.data_ptr(), None,
                                                 None, float(self.gamma), 1.0, out.data_ptr(), flat.size, 1,
                                                 _stream(self.device)))
         return out.cpu()

@@ -54,8 +54,8 @@ def test_rtg_scan_matches_reference_and_oracle():
     g = golden("ppo_rtgs")
     term = np.zeros(len(g["rews"]), np.uint8)
     term[np.cumsum(g["lens"]) - 1] = 1
-    rew = _t(g["rews"]); out = torch.empty_like(rew)
-    _capi.check(_capi.lib().navppo_rtg_scan(rew.data_ptr(), _t(term, torch.uint8).data_ptr(), None, None, float(g["gamma"]),
+    rew = _t(g["rews"]); out = torch.empty_like(rew); term_d = _t(term, torch.uint8)
+    _capi.check(_capi.lib().navppo_rtg_scan(rew.data_ptr(), term_d.data_ptr(), None, None, float(g["gamma"]),
                                             1.0, out.data_ptr(), len(term), 1, _sp()))
     np.testing.assert_allclose(out.cpu().numpy(), g["rtgs"], rtol=2e-6, atol=1e-5)
     # [H, N] layout at rollout size against the oracle scan, incl. GAE form
@@ -117,8 +117,9 @@ def test_act_matches_reference_get_action():
     flat = _flat_from(actor, np.zeros(layout.CRITIC_PARAMS, np.float32))
     n = len(g["obs"])
     act = torch.empty((n, 2), device=DEV); logp = torch.empty(n, device=DEV); mu = torch.empty((n, 2), device=DEV)
-    _capi.check(_capi.lib().navppo_act(_handle(), flat.data_ptr(), _t(g["obs"]).data_ptr(), n, float(g["var"]), 0, 0, 0,
-                                       _t(g["eps"]).data_ptr(), act.data_ptr(), logp.data_ptr(), mu.data_ptr(), _sp()))
+    obs, eps = _t(g["obs"]), _t(g["eps"])       # keep the inputs alive across the launch
+    _capi.check(_capi.lib().navppo_act(_handle(), flat.data_ptr(), obs.data_ptr(), n, float(g["var"]), 0, 0, 0,
+                                       eps.data_ptr(), act.data_ptr(), logp.data_ptr(), mu.data_ptr(), _sp()))
     np.testing.assert_allclose(mu.cpu().numpy(), g["mean"], atol=FWD_ATOL, rtol=0)
     np.testing.assert_allclose(act.cpu().numpy(), g["act"], atol=2e-6, rtol=0)
     np.testing.assert_allclose(logp.cpu().numpy(), g["logp"], atol=1e-5, rtol=1e-6)
@@ -137,7 +138,8 @@ def test_act_device_noise_is_standard_normal_and_partition_invariant():
     def run(lo, hi, draw, seed=5):
         m = hi - lo
         act = torch.empty((m, 2), device=DEV); logp = torch.empty(m, device=DEV); mu = torch.empty((m, 2), device=DEV)
-        _capi.check(_capi.lib().navppo_act(_handle(), flat.data_ptr(), obs[lo:hi].contiguous().data_ptr(), m, var, seed, lo,
+        o = obs[lo:hi].contiguous()
+        _capi.check(_capi.lib().navppo_act(_handle(), flat.data_ptr(), o.data_ptr(), m, var, seed, lo,
                                            draw, None, act.data_ptr(), logp.data_ptr(), mu.data_ptr(), _sp()))
         return act, logp, mu
 
@@ -205,8 +207,13 @@ def test_update_matches_reference_learn_iteration(tag):
                                           lp.data_ptr(), rtg.data_ptr(), T, float(g["var"]), epochs, adv.data_ptr(),
                                           v.data_ptr(), met.data_ptr(), _sp()))
     a, c = _split(flat)
-    np.testing.assert_allclose(a, g["actor_after"], atol=2e-5, rtol=0)
-    np.testing.assert_allclose(c, g["critic_after"], atol=2e-5, rtol=0)
+    # one Adam step moves a parameter by up to lr whatever the gradient's size, so entries whose
+    # gradient is rounding noise may differ by a fraction of lr: bound = lr / 15 (2e-5 at the
+    # reference's lr = 3e-4), and all but a handful must sit within 2e-5 regardless
+    atol = float(g["lr"]) / 15
+    for got, want in ((a, g["actor_after"]), (c, g["critic_after"])):
+        np.testing.assert_allclose(got, want, atol=atol, rtol=0)
+        assert (np.abs(got - want) > 2e-5).mean() < 1e-3
     m = met.cpu().numpy()
     np.testing.assert_allclose(m[:, _capi.M_ACTOR_LOSS], g["actor_losses"], atol=2e-5, rtol=2e-4)
     np.testing.assert_allclose(m[:, _capi.M_CRITIC_LOSS], g["critic_losses"], rtol=2e-4)
@@ -232,9 +239,10 @@ def test_grad_is_additive_over_shards_and_deterministic():
 
     def grad(lo, hi, n_global):
         out = torch.empty(_capi.PPO_FLAT, device=DEV); met = torch.zeros(8, dtype=torch.float64, device=DEV)
-        _capi.check(L.navppo_grad(h, flat.data_ptr(), _t(obs[lo:hi]).data_ptr(), _t(act[lo:hi]).data_ptr(),
-                                  _t(lp[lo:hi]).data_ptr(), _t(adv[lo:hi]).data_ptr(), _t(rtg[lo:hi]).data_ptr(), hi - lo,
-                                  n_global, float(g["var"]), out.data_ptr(), met.data_ptr(), _sp()))
+        o, a_, l_, ad, rt = _t(obs[lo:hi]), _t(act[lo:hi]), _t(lp[lo:hi]), _t(adv[lo:hi]), _t(rtg[lo:hi])
+        _capi.check(L.navppo_grad(h, flat.data_ptr(), o.data_ptr(), a_.data_ptr(), l_.data_ptr(), ad.data_ptr(),
+                                  rt.data_ptr(), hi - lo, n_global, float(g["var"]), out.data_ptr(), met.data_ptr(), _sp()))
+        torch.cuda.synchronize()
         return out, met
 
     full, mfull = grad(0, T, T)
