@@ -41,48 +41,57 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """SM clock / throttle reasons sampled through NVML in a thread DURING the timed region."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index: int, period_s: float = 0.002):
+        self.index, self.period, self.rows, self._stop, self._thr, self.err = index, period_s, [], False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
-                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES; map to the NVML index when it is set
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.err = f"nvml unavailable: {e}"
+            return
+        self._thr = threading.Thread(target=self._pump, daemon=True)
+        self._thr.start()
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        nv = self.nv
+        while not self._stop:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for nme, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:  # noqa: BLE001
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((sm, rs))
+            except Exception as e:  # noqa: BLE001
+                self.err = str(e)
+                return
+            time.sleep(self.period)
+
+    def mark(self):
+        return len(self.rows)
+
+    def stop(self, lo: int = 0, hi: int | None = None):
+        self._stop = True
+        if self._thr is not None:
+            self._thr.join(timeout=1)
+        if self.err and not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err]}
+        rows = self.rows[lo:hi] or self.rows
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                "hw_power_brake_slowdown": 0x80}
+        reasons = sorted(k for k, b in bits.items() if any(r & b for _, r in rows))
+        return {"sm_mhz": float(np.median([c for c, _ in rows])), "sm_max_mhz": self.sm_max, "samples": len(rows),
+                "reasons": reasons}
 
 
 def cpu_port_throughput(n_agents: int, seconds: float, threads: int):
@@ -103,6 +112,52 @@ def cpu_port_throughput(n_agents: int, seconds: float, threads: int):
         steps += 1
     dt = time.perf_counter() - t0
     return n_agents * steps / dt, steps, dt
+
+
+def training_bench(args, torch, dist, dev, rank, world, barrier):
+    """env-steps/s of (ii) the rollout and (iii) the whole PPO iteration at N agents x H steps per GPU."""
+    import tempfile
+
+    from navbot_ppo_b200 import _capi
+    from navbot_ppo_b200.env import VecEnv
+    from navbot_ppo_b200.nets import NetActor, NetCritic
+    from navbot_ppo_b200.ppo import PPO
+    N, H = args.agents, args.horizon
+    prec = {"fp32": _capi.PREC_FP32, "tf32x3": _capi.PREC_TF32X3, "tf32": _capi.PREC_TF32}[args.precision]
+    env = VecEnv(N, map="stage_1", device=dev.index, seed=0, max_episode_steps=500, agent_id_offset=rank * N)
+    with tempfile.TemporaryDirectory() as tmp:
+        agent = PPO(NetActor, NetCritic, env, 16, 2, timesteps_per_batch=N * H, max_timesteps_per_episode=500,
+                    n_updates_per_iteration=args.epochs, gamma=0.99, lr=3e-4, clip=0.2, seed=0, output_dir=tmp,
+                    method_name=f"bench{rank}", verbose=False, precision=prec)
+        l0 = env.launch_count
+        batch = agent.rollout([0, 0], 0)            # warm-up iteration
+        agent.update(*batch[:4])
+        launches_per_iter = env.launch_count - l0
+        barrier()
+        ro_ms, up_ms = 0.0, 0.0
+        res = None
+        for _ in range(args.train_iters):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record()
+            batch = agent.rollout([0, 0], 0)
+            e[1].record()
+            res = agent.update(*batch[:4])
+            e[2].record()
+            torch.cuda.synchronize()
+            ro_ms += e[0].elapsed_time(e[1]); up_ms += e[1].elapsed_time(e[2])
+        barrier()
+        t = torch.tensor([ro_ms, up_ms, ro_ms + up_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ro_ms, up_ms, tot_ms = (float(x) / args.train_iters for x in t)
+    steps = world * N * H
+    flops = 3.0 * (98432 + 98368) * N * H * args.epochs       # fwd + bwd of both networks, SURVEY 8(d)
+    return {"rollout_env_steps_per_s": steps / (ro_ms * 1e-3), "train_env_steps_per_s": steps / (tot_ms * 1e-3),
+            "rollout_ms": ro_ms, "update_ms": up_ms, "iteration_ms": tot_ms, "epochs": args.epochs, "horizon": H,
+            "samples_per_gpu": N * H, "precision": args.precision,
+            "update_tflops_per_gpu": flops / (up_ms * 1e-3) / 1e12,
+            "final_actor_loss": float(res["actor_losses"][-1]), "final_critic_loss": float(res["critic_losses"][-1]),
+            "sim_launches_per_iteration": int(launches_per_iter)}
 
 
 def run_reference(args, rank, world):
@@ -148,6 +203,10 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=2.0)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the PPO rollout / training-iteration figures")
+    ap.add_argument("--train-iters", type=int, default=2)
+    ap.add_argument("--epochs", type=int, default=50, help="PPO epochs per iteration (main.py:471)")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "tf32"])
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -192,15 +251,17 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.05)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
+    mark0 = sampler.mark()
     for k in range(K):
         flush.fill_(k & 0xFF)          # evict L2 between timed steps (untimed)
         ev[k][0].record()
         one_step()
         ev[k][1].record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(mark0, sampler.mark()) if rank == 0 else None
     ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = env.launch_count - launches0
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -225,6 +286,12 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * N * He * max(1, K // 4) / float(t.item())
+
+    # ---- PPO on top of the simulator: rollout (policy forward + sampling + env step) and the
+    # ---- full training iteration (rollout + reward-to-go + 50-epoch update), SURVEY.md 8(d)
+    training = None
+    if not args.no_train:
+        training = training_bench(args, torch, dist, dev, rank, world, barrier)
 
     if rank != 0:
         if world > 1:
@@ -275,6 +342,7 @@ def main():
         "gpu_launches": int(launches),
         "roofline": roofline,
         "roofline_sweep": sweep,
+        "training": training,
         "cpu_baseline": {"value": cpu_v, "unit": "env-steps/s", "cores": threads, "kind": "port",
                          "single_core_value": cpu1_v,
                          "sample": f"{cpu_dt:.1f} s ({cpu_steps} Env.step batches over {N} agents) of the C port "
