@@ -129,6 +129,19 @@ int navppo_update(navppo_t* h, float* params, float* exp_avg, float* exp_avg_sq,
                   const float* act, const float* logp_old, const float* rtg, int32_t T, double var, int32_t epochs,
                   float* adv_ws, float* v_ws, double* metrics, void* stream);
 
+/* Diagnostic: one CTA computes D[128, N] = A[128, K] * B[N, K]^T on the tcgen05 tensor cores
+ * (kind::tf32) with the operand roles of the fused update kernel (a_mode / b_mode: 0 = rows are
+ * the M/N index, 1 = rows are K, 2 = the buffer is a verbatim shared-memory image) and
+ * caller-supplied descriptor fields {a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep, a_major,
+ * b_major} (host array of 8).  Used by the layout self-test. */
+int navppo_tc_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t a_mode, int32_t b_mode,
+                       const uint32_t* strides6, void* stream);
+
+/* Same with BF16 operands (kind::f16): passes = 1 (bf16 x bf16) or 3 (split x = hi + lo:
+ * hi*hi + lo*hi + hi*lo, ~16 mantissa bits) — the two arithmetic modes of the fused kernel. */
+int navppo_tc_selftest_bf16(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t a_mode, int32_t b_mode,
+                            int32_t passes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

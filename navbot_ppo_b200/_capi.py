@@ -113,6 +113,8 @@ NAVPPO_SYMBOLS = {
     "navppo_adv_normalize": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "navppo_grad": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _f64, _vp, _vp, _vp]),
     "navppo_adam": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "navppo_tc_selftest": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "navppo_tc_selftest_bf16": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "navppo_update": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _f64, _i32, _vp, _vp, _vp, _vp]),
 }
 

@@ -27,6 +27,7 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler",
 UNITS = [
     ("navsim_kernels.cu", ["-fmad=false"]),
     ("navppo_kernels.cu", []),
+    ("navppo_tc.cu", []),
 ]
 
 
