@@ -123,7 +123,7 @@ def training_bench(args, torch, dist, dev, rank, world, barrier):
     from navbot_ppo_b200.nets import NetActor, NetCritic
     from navbot_ppo_b200.ppo import PPO
     N, H = args.agents, args.horizon
-    prec = {"fp32": _capi.PREC_FP32, "tf32x3": _capi.PREC_TF32X3, "tf32": _capi.PREC_TF32}[args.precision]
+    prec = {"fp32": _capi.PREC_FP32, "bf16x3": _capi.PREC_BF16X3, "bf16": _capi.PREC_BF16}[args.precision]
     env = VecEnv(N, map="stage_1", device=dev.index, seed=0, max_episode_steps=500, agent_id_offset=rank * N)
     with tempfile.TemporaryDirectory() as tmp:
         agent = PPO(NetActor, NetCritic, env, 16, 2, timesteps_per_batch=N * H, max_timesteps_per_episode=500,
@@ -206,7 +206,7 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the PPO rollout / training-iteration figures")
     ap.add_argument("--train-iters", type=int, default=2)
     ap.add_argument("--epochs", type=int, default=50, help="PPO epochs per iteration (main.py:471)")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "tf32"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x3", "bf16"])
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

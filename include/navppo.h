@@ -52,8 +52,8 @@ enum navppo_metric {
 /* arithmetic of the MLP GEMMs */
 enum navppo_precision {
   NAVPPO_FP32 = 0,   /* CUDA-core FFMA, the reference's fp32 arithmetic */
-  NAVPPO_TF32X3 = 1, /* tcgen05 tensor cores, 3-pass split TF32 (fp32-level accuracy) */
-  NAVPPO_TF32 = 2    /* tcgen05 tensor cores, single-pass TF32 */
+  NAVPPO_BF16X3 = 1, /* tcgen05 tensor cores, split-BF16 operands (hi + lo), 3 MMAs per step: ~16 mantissa bits */
+  NAVPPO_BF16 = 2    /* tcgen05 tensor cores, plain BF16 operands, fp32 accumulate */
 };
 
 typedef struct navppo navppo_t;
@@ -61,7 +61,7 @@ typedef struct navppo navppo_t;
 typedef struct navppo_cfg {
   int32_t device;
   int32_t max_samples;  /* largest T of any call (sizes the gradient workspace) */
-  int32_t precision;    /* enum navppo_precision */
+  int32_t precision;    /* enum navppo_precision: arithmetic of navppo_grad's matrix products */
   int32_t reserved0;
   double lr;            /* ppo.py:769  3e-4 on the main.py path */
   double beta1, beta2, adam_eps; /* torch.optim.Adam defaults, ppo.py:116-117 */

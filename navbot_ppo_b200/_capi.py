@@ -94,7 +94,7 @@ class NavppoCfg(ctypes.Structure):
 # include/navppo.h constants
 PPO_ACTOR_PARAMS, PPO_CRITIC_PARAMS, PPO_CRITIC_OFFSET, PPO_FLAT, PPO_NUM_METRICS = 50290, 50257, 50304, 100608, 8
 M_ACTOR_LOSS, M_CRITIC_LOSS, M_APPROX_KL, M_CLIP_FRAC, M_ACTOR_GRAD_SQ, M_CRITIC_GRAD_SQ = range(6)
-PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
+PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
 
 _f64 = ctypes.c_double
 _u32 = ctypes.c_uint32

@@ -28,41 +28,16 @@
 #include "../../include/navppo.h"
 #include "nav_common.h"
 #include "navsim_math.h"
+#include "ppo_common.cuh"
+
+// tensor-core gradient pass (navppo_tc.cu): fills gpart / mpart like mlp_grad_kernel
+int navppo_tc_grad_launch(const ppo::GradArgs& a, int rows, int passes, float* wprep, cudaStream_t s);
+size_t navppo_tc_prep_bytes();
+int navppo_tc_init();
 
 namespace {
 
-constexpr int OBS = NAVSIM_OBS_DIM;  // 16
-constexpr int X1 = 2 * OBS;          // 32
-constexpr int HID = NAVPPO_HIDDEN;   // 512
-constexpr float LEAK = 0.2f;         // nn.LeakyReLU(negative_slope=0.2), net_actor.py:37
-
-// canonical offsets inside one network's flat vector (navbot_ppo_b200/layout.py)
-constexpr int O_W1A = 0;                      // [512][16]
-constexpr int O_B1A = O_W1A + HID * OBS;      // 8192
-constexpr int O_W1B = O_B1A + HID;            // 8704   [16][512]
-constexpr int O_B1B = O_W1B + OBS * HID;      // 16896
-constexpr int O_W2A = O_B1B + OBS;            // 16912  [512][32]
-constexpr int O_B2A = O_W2A + HID * X1;       // 33296
-constexpr int O_W2B = O_B2A + HID;            // 33808  [32][512]
-constexpr int O_B2B = O_W2B + X1 * HID;       // 50192
-constexpr int O_HEAD = O_B2B + X1;            // 50224
-constexpr int ACTOR_HEAD = 2 * (X1 + 1);      // out1.weight, out1.bias, out2.weight, out2.bias
-constexpr int CRITIC_HEAD = X1 + 1;
-static_assert(O_HEAD + ACTOR_HEAD == NAVPPO_ACTOR_PARAMS, "actor layout");
-static_assert(O_HEAD + CRITIC_HEAD == NAVPPO_CRITIC_PARAMS, "critic layout");
-
-// "kernel layout" of one network: same regions, but the two fc2 matrices are stored
-// transposed ([hidden][out]) so that everything a hidden unit touches is contiguous.
-// canonical index -> kernel-layout index
-__host__ __device__ inline int klayout(int i) {
-  if (i >= O_W1B && i < O_B1B) { const int r = i - O_W1B; return O_W1B + (r % HID) * OBS + r / HID; }
-  if (i >= O_W2B && i < O_B2B) { const int r = i - O_W2B; return O_W2B + (r % HID) * X1 + r / HID; }
-  return i;
-}
-constexpr int NET_ROW = NAVPPO_CRITIC_OFFSET;  // 50304: padded length of one network's vector
-
-__device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : LEAK * x; }
-__device__ __forceinline__ float dlrelu(float x) { return x > 0.f ? 1.f : LEAK; }
+using namespace ppo;
 
 extern __shared__ __align__(16) unsigned char ppo_smem[];
 
@@ -150,14 +125,6 @@ __device__ __forceinline__ void resblock_fwd(const float* __restrict__ sWa, cons
       u[4 * q + 2] = fmaf(b.z, h1, u[4 * q + 2]); u[4 * q + 3] = fmaf(b.w, h1, u[4 * q + 3]);
     }
   }
-}
-
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
-
-// log N(a; mu, var I), k = 2: -1/2 |a - mu|^2 / var - ln(2 pi) - ln(var)   (ppo.py:704,735)
-__device__ __forceinline__ float gauss_logp(float a0, float a1, float m0, float m1, float var) {
-  const float d0 = a0 - m0, d1 = a1 - m1;
-  return -0.5f * (d0 * d0 + d1 * d1) / var - 1.8378770664093453f - logf(var);
 }
 
 enum { INFER_FORWARD = 0, INFER_ACT = 1, INFER_EVALUATE = 2 };
@@ -301,16 +268,6 @@ __global__ void adv_normalize_kernel(const float* __restrict__ rtg, const float*
 constexpr int GM = 128;          // samples per tile == threads per CTA
 constexpr int JC = 32;           // hidden units per chunk
 constexpr int SROW = GM + 1;     // padded row of the [JC][GM] chunk buffers (bank spread)
-
-struct GradArgs {
-  const float* params;
-  const float* obs; const float* act; const float* logp_old; const float* adv; const float* rtg;
-  int T;
-  float inv_n;        // 1 / n_global
-  float var, clip;
-  float* gpart;       // [2][gridDim.x][NET_ROW]
-  double* mpart;      // [2][gridDim.x][4]
-};
 
 // shared-memory carve-up (floats)
 constexpr int G_SX = 0;                       // [GM][32]  x1 = [x0 | y1]
@@ -645,6 +602,7 @@ struct navppo {
   double* sq_part = nullptr;  // [adam blocks][2]
   double* adv_stats = nullptr;  // [3]
   float* grad_ws = nullptr;   // [NAVPPO_FLAT] used by navppo_update
+  float* wprep = nullptr;     // tensor-core path: pre-split, pre-tiled weights
   int sm_count = 148;
   int64_t launches = 0;
 };
@@ -697,7 +655,8 @@ int navppo_create(navppo_t** out, const navppo_cfg* cfg) {
   if (!out || !cfg) return nav_fail(NAVSIM_EINVAL, "null argument");
   *out = nullptr;
   if (cfg->max_samples <= 0) return nav_fail(NAVSIM_EINVAL, "max_samples must be positive");
-  if (cfg->precision != NAVPPO_FP32) return nav_fail(NAVSIM_EINVAL, "unsupported precision mode");
+  if (cfg->precision != NAVPPO_FP32 && cfg->precision != NAVPPO_BF16X3 && cfg->precision != NAVPPO_BF16)
+    return nav_fail(NAVSIM_EINVAL, "unknown precision mode");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -721,6 +680,13 @@ int navppo_create(navppo_t** out, const navppo_cfg* cfg) {
   if (e == cudaSuccess) e = cudaMalloc(&h->sq_part, (size_t)ADAM_GRID * 2 * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&h->adv_stats, 3 * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&h->grad_ws, (size_t)NAVPPO_FLAT * sizeof(float));
+  if (e == cudaSuccess && cfg->precision != NAVPPO_FP32) {
+    e = cudaMalloc(&h->wprep, navppo_tc_prep_bytes());
+    if (e == cudaSuccess && navppo_tc_init() != NAVSIM_OK) {
+      navppo_destroy(h);
+      return NAVSIM_ECUDA;   // nav_last_error already set
+    }
+  }
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_infer_kernel<INFER_FORWARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INFER_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_infer_kernel<INFER_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INFER_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_infer_kernel<INFER_EVALUATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INFER_SMEM);
@@ -742,6 +708,7 @@ int navppo_destroy(navppo_t* h) {
   if (h->sq_part) cudaFree(h->sq_part);
   if (h->adv_stats) cudaFree(h->adv_stats);
   if (h->grad_ws) cudaFree(h->grad_ws);
+  if (h->wprep) cudaFree(h->wprep);
   delete h;
   return NAVSIM_OK;
 }
@@ -817,12 +784,21 @@ int navppo_grad(navppo_t* h, const float* params, const float* obs, const float*
   if (!(var > 0.0)) return nav_fail(NAVSIM_EINVAL, "var must be positive");
   cudaStream_t s = (cudaStream_t)stream;
   const int tiles = (T + GM - 1) / GM;
-  const int rows = tiles < h->grad_rows ? tiles : h->grad_rows;
+  int rows = tiles < h->grad_rows ? tiles : h->grad_rows;
   GradArgs a{};
   a.params = params; a.obs = obs; a.act = act; a.logp_old = logp_old; a.adv = adv; a.rtg = rtg; a.T = T;
   a.inv_n = (float)(1.0 / (double)n_global); a.var = (float)var; a.clip = (float)h->cfg.clip;
   a.gpart = h->gpart; a.mpart = h->mpart;
-  mlp_grad_kernel<<<dim3(rows, 2), GM, GRAD_SMEM, s>>>(a);
+  if (h->cfg.precision == NAVPPO_FP32) {
+    mlp_grad_kernel<<<dim3(rows, 2), GM, GRAD_SMEM, s>>>(a);
+  } else {
+    // tensor-core kernel: one 256-thread CTA per SM (all of its shared memory and TMEM), the
+    // two networks split the SMs
+    const int per_net = h->sm_count / 2 > 0 ? h->sm_count / 2 : 1;
+    rows = tiles < per_net ? tiles : per_net;
+    if (int rc = navppo_tc_grad_launch(a, rows, h->cfg.precision == NAVPPO_BF16X3 ? 3 : 1, h->wprep, s)) return rc;
+    h->launches++;
+  }
   grad_reduce_kernel<<<(NAVPPO_FLAT + 255) / 256, 256, 0, s>>>(h->gpart, h->mpart, rows, a.inv_n, grad, metrics);
   h->launches += 2;
   NAV_CUDA_TRY(cudaGetLastError());

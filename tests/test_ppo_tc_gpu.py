@@ -1,0 +1,125 @@
+"""GPU parity tests of the tcgen05 tensor-core gradient path (navppo_grad with
+precision = NAVPPO_BF16X3 / NAVPPO_BF16), through the C-ABI, against the reference's own
+gradients (tests/golden/ppo_learn_*.npz) and the float64 oracle.
+
+Tolerances, relative to the largest entry of each network's gradient:
+  BF16X3 (split operands, ~16 mantissa bits): 1e-4 — the same bar as the fp32 CUDA-core path;
+  BF16   (plain bf16 operands, fp32 accumulate): 1e-2 (measured ~1e-3)."""
+import numpy as np
+import pytest
+import torch
+
+from navbot_ppo_b200 import _capi, layout
+from navbot_ppo_b200.env import VecEnv
+from navbot_ppo_b200.nets import NetActor, NetCritic, _Handles
+from navbot_ppo_b200.ppo import PPO
+from oracle import ppo_oracle as po
+from tests.helpers import golden
+from tests.test_ppo_gpu import DEV, _flat_from, _split, _sp, _t
+
+pytestmark = pytest.mark.gpu
+
+MODES = [(_capi.PREC_BF16X3, 1e-4), (_capi.PREC_BF16, 1e-2)]
+
+
+def _grad(h, flat, obs, act, lp, adv, rtg, n_global, var):
+    T = obs.shape[0]
+    grad = torch.empty(_capi.PPO_FLAT, device=DEV)
+    met = torch.zeros(_capi.PPO_NUM_METRICS, dtype=torch.float64, device=DEV)
+    _capi.check(_capi.lib().navppo_grad(h, flat.data_ptr(), obs.data_ptr(), act.data_ptr(), lp.data_ptr(), adv.data_ptr(),
+                                        rtg.data_ptr(), T, n_global, var, grad.data_ptr(), met.data_ptr(), _sp()))
+    torch.cuda.synchronize()
+    return grad, met.cpu().numpy()
+
+
+@pytest.mark.parametrize("prec,rtol", MODES)
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_tc_grad_matches_reference_gradients(tag, prec, rtol):
+    g = golden("ppo_learn_" + tag)
+    var, clip = float(g["var"]), float(g["clip"])
+    h = _Handles.get(torch.device(DEV), 1 << 16, clip, float(g["lr"]), prec)
+    flat = _flat_from(g["actor_before"], g["critic_before"])
+    obs, act, lp, rtg = _t(g["obs"]), _t(g["acts"]), _t(g["logp"]), _t(g["rtgs"])
+    v0, _ = po.evaluate(g["actor_before"], g["critic_before"], g["obs"], g["acts"], var)
+    adv = _t(po.advantage(g["rtgs"], v0).astype(np.float32))
+    grad, m = _grad(h, flat, obs, act, lp, adv, rtg, obs.shape[0], var)
+    ga, gc = _split(grad)
+    for got, want in ((ga, g["actor_grads"][0]), (gc, g["critic_grads"][0])):      # the reference's .grad, epoch 0
+        np.testing.assert_allclose(got, want, atol=rtol * np.abs(want).max(), rtol=0)
+    assert abs(m[_capi.M_ACTOR_LOSS] - g["actor_losses"][0]) <= 1e-5 + 10 * rtol * abs(g["actor_losses"][0])
+    assert abs(m[_capi.M_CRITIC_LOSS] - g["critic_losses"][0]) <= 10 * rtol * abs(g["critic_losses"][0])
+    assert float(grad[layout.ACTOR_PARAMS:_capi.PPO_CRITIC_OFFSET].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("prec,rtol", MODES)
+def test_tc_grad_many_tiles_additive_deterministic(prec, rtol):
+    """Ragged multi-tile batch (persistent loop, partial last tile), clipped ratios: against the
+    float64 oracle on a sub-batch, additivity over shards, bit-reproducibility."""
+    g = golden("ppo_learn_b")
+    rng = np.random.RandomState(4)
+    T = 33333
+    idx = rng.randint(0, len(g["obs"]), T)
+    obs = (g["obs"][idx] + rng.normal(scale=0.01, size=(T, 16))).astype(np.float32)
+    act, lp, rtg = g["acts"][idx], (g["logp"][idx] + rng.normal(scale=0.1, size=T)).astype(np.float32), g["rtgs"][idx]
+    adv = rng.normal(size=T).astype(np.float32)
+    var = float(g["var"])
+    flat = _flat_from(g["actor_after"], g["critic_after"])
+    h = _Handles.get(torch.device(DEV), 1 << 16, 0.2, 3e-4, prec)
+    o, a_, l_, ad, rt = _t(obs), _t(act), _t(lp), _t(adv), _t(rtg)
+    full, mfull = _grad(h, flat, o, a_, l_, ad, rt, T, var)
+    again, _ = _grad(h, flat, o, a_, l_, ad, rt, T, var)
+    assert torch.equal(full, again)
+    cut = 12345
+    ga, ma = _grad(h, flat, o[:cut].contiguous(), a_[:cut].contiguous(), l_[:cut].contiguous(), ad[:cut].contiguous(),
+                   rt[:cut].contiguous(), T, var)
+    gb, mb = _grad(h, flat, o[cut:].contiguous(), a_[cut:].contiguous(), l_[cut:].contiguous(), ad[cut:].contiguous(),
+                   rt[cut:].contiguous(), T, var)
+    fa, fc = _split(full); sa, sc = _split(ga + gb)
+    assert np.abs(sa - fa).max() <= 10 * rtol * np.abs(fa).max() and np.abs(sc - fc).max() <= 10 * rtol * np.abs(fc).max()
+    np.testing.assert_allclose((ma + mb)[:4], mfull[:4], rtol=1e-6, atol=1e-9)
+    n = 3000
+    gs, ms = _grad(h, flat, o[:n].contiguous(), a_[:n].contiguous(), l_[:n].contiguous(), ad[:n].contiguous(), rt[:n].contiguous(),
+                   n, var)
+    m_ref, ga_ref, gc_ref = po.losses_and_grads(g["actor_after"], g["critic_after"], obs[:n], act[:n], lp[:n], adv[:n], rtg[:n],
+                                                var, 0.2)
+    xa, xc = _split(gs)
+    np.testing.assert_allclose(xa, ga_ref, atol=rtol * np.abs(ga_ref).max(), rtol=0)
+    np.testing.assert_allclose(xc, gc_ref, atol=rtol * np.abs(gc_ref).max(), rtol=0)
+    assert abs(ms[_capi.M_CLIP_FRAC] - m_ref["clip_frac"]) <= (2.0 if prec == _capi.PREC_BF16X3 else 12.0) / n
+    assert m_ref["clip_frac"] > 0.05
+
+
+def test_tc_update_tracks_reference_learn_iteration():
+    """Whole update (10 epochs, lr 2e-3) in split-BF16 arithmetic stays on the reference's
+    parameter trajectory."""
+    g = golden("ppo_learn_b")
+    epochs = int(g["epochs"])
+    flat = _flat_from(g["actor_before"], g["critic_before"])
+    m1 = torch.zeros_like(flat); m2 = torch.zeros_like(flat)
+    obs, act, lp, rtg = _t(g["obs"]), _t(g["acts"]), _t(g["logp"]), _t(g["rtgs"])
+    T = obs.shape[0]
+    adv = torch.empty(T, device=DEV); v = torch.empty(T, device=DEV)
+    met = torch.zeros((epochs, _capi.PPO_NUM_METRICS), dtype=torch.float64, device=DEV)
+    h = _Handles.get(torch.device(DEV), 1 << 16, float(g["clip"]), float(g["lr"]), _capi.PREC_BF16X3)
+    _capi.check(_capi.lib().navppo_update(h, flat.data_ptr(), m1.data_ptr(), m2.data_ptr(), 0, obs.data_ptr(), act.data_ptr(),
+                                          lp.data_ptr(), rtg.data_ptr(), T, float(g["var"]), epochs, adv.data_ptr(),
+                                          v.data_ptr(), met.data_ptr(), _sp()))
+    a, c = _split(flat)
+    for got, want in ((a, g["actor_after"]), (c, g["critic_after"])):
+        np.testing.assert_allclose(got, want, atol=float(g["lr"]) / 4, rtol=0)   # a quarter of one Adam step
+        assert (np.abs(got - want) > 1e-4).mean() < 1e-2
+    m = met.cpu().numpy()
+    np.testing.assert_allclose(m[:, _capi.M_ACTOR_LOSS], g["actor_losses"], atol=1e-4, rtol=2e-3)
+    np.testing.assert_allclose(m[:, _capi.M_CRITIC_LOSS], g["critic_losses"], rtol=2e-3)
+
+
+def test_learn_on_vecenv_in_bf16_mode(tmp_path):
+    env = VecEnv(1024, map="stage_1", seed=2, max_episode_steps=60)
+    agent = PPO(NetActor, NetCritic, env, 16, 2, timesteps_per_batch=1024 * 32, max_timesteps_per_episode=60,
+                n_updates_per_iteration=4, output_dir=str(tmp_path), method_name="tc", seed=0, verbose=False,
+                precision=_capi.PREC_BF16)
+    before = agent.flat.clone()
+    agent.learn(total_timesteps=1)
+    assert torch.isfinite(agent.flat).all() and not torch.equal(before, agent.flat)
+    s = agent.logger["summary"]
+    assert np.isfinite(list(s.values())).all()
