@@ -46,7 +46,7 @@ def test_tc_grad_matches_reference_gradients(tag, prec, rtol):
     ga, gc = _split(grad)
     for got, want in ((ga, g["actor_grads"][0]), (gc, g["critic_grads"][0])):      # the reference's .grad, epoch 0
         np.testing.assert_allclose(got, want, atol=rtol * np.abs(want).max(), rtol=0)
-    assert abs(m[_capi.M_ACTOR_LOSS] - g["actor_losses"][0]) <= 1e-5 + 10 * rtol * abs(g["actor_losses"][0])
+    assert abs(m[_capi.M_ACTOR_LOSS] - g["actor_losses"][0]) <= (1e-5 if prec == _capi.PREC_BF16X3 else 1e-4) + 10 * rtol * abs(g["actor_losses"][0])
     assert abs(m[_capi.M_CRITIC_LOSS] - g["critic_losses"][0]) <= 10 * rtol * abs(g["critic_losses"][0])
     assert float(grad[layout.ACTOR_PARAMS:_capi.PPO_CRITIC_OFFSET].abs().max()) == 0.0
 
