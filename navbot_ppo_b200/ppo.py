@@ -385,7 +385,9 @@ class PPO:
                 navdist.all_reduce_sum_(self._grad)                    # the one collective per epoch
                 _capi.check(L.navppo_adam(self._h, self.flat.data_ptr(), self._grad.data_ptr(), self._exp_avg.data_ptr(),
                                           self._exp_avg_sq.data_ptr(), self._adam_step + e + 1, row.data_ptr(), sp))
-            navdist.all_reduce_sum_(metrics[:, :4])
+            shares = metrics[:, :4].contiguous()           # each rank holds its share of the four batch means
+            navdist.all_reduce_sum_(shares)
+            metrics[:, :4] = shares
         self._adam_step += epochs
         self.V = v
         m = metrics.cpu().numpy()[:epochs]
