@@ -6,8 +6,10 @@
 
 One "step" of this benchmark is one pass of the hot path over one batch: H consecutive
 Env.step calls for every one of the 8192 agents of a rank (BASELINE.json configs[1];
-agents shard over ranks with no data-path collective -> weak scaling).  Rank 0 prints ONE
-JSON line.  See DESIGN.md "Measurement" for every figure's definition.
+agents shard over ranks with no data-path collective -> weak scaling), issued as ONE launch
+of the step kernel (navsim_rollout_scripted) that writes every step's observation, reward
+and flags into the [H, N, .] rollout buffers.  Rank 0 prints ONE JSON line.  See DESIGN.md
+"Measurement" for every figure's definition.
 """
 from __future__ import annotations
 
@@ -30,6 +32,9 @@ import numpy as np  # noqa: E402
 #   write: pose 24 + past_dist 8 + prev_action 8 + ep stats 12 + steps 4 + obs 64 + rew 4 + flags 3     = 127
 BYTES_PER_ENV_STEP = 84 + 127
 BYTES_PER_ENV_STEP_SCRIPTED = BYTES_PER_ENV_STEP - 8  # actions drawn in-kernel, not read
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full`
+# capture of the same kernel and shape (profiles/README.md names the file); keyed by (N, H)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {}
 
 
 def load_peaks():
@@ -241,8 +246,10 @@ def main():
     env.reset()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    bufs = env.rollout_scripted(H, action_seed=0)     # allocates the [H, N, .] rollout buffers
+
     def one_step():
-        env.step_scripted(H, action_seed=0)
+        env.rollout_scripted(H, action_seed=0, out=bufs)
 
     for _ in range(W):
         one_step()
@@ -270,6 +277,17 @@ def main():
     ms_total = float(t.item())
     env_steps_total = world * N * H * K
     value = env_steps_total / (ms_total * 1e-3)
+
+    # ---- the same H steps as H single-step launches (what a per-step caller pays) ----------
+    a_ev, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    env.step_scripted(1, 0)
+    barrier()
+    a_ev.record()
+    for _ in range(H):
+        env.step_scripted(1, 0)
+    b_ev.record()
+    torch.cuda.synchronize()
+    single_launch_us = a_ev.elapsed_time(b_ev) * 1e3 / H
 
     # ---- end to end through the host-buffer entry point (navsim_step_host) ----------------
     He = min(H, 32)
@@ -299,29 +317,51 @@ def main():
         return
 
     # ---- roofline of the step kernel: live CUDA-event duration per launch -----------------
-    per_launch_s = (ms_total * 1e-3) / (K * H)
-    achieved = BYTES_PER_ENV_STEP_SCRIPTED * N / per_launch_s / 1e9
+    per_launch_s = (ms_total * 1e-3) / K
+    achieved = BYTES_PER_ENV_STEP_SCRIPTED * N * H / per_launch_s / 1e9
+    fused_bytes = (64 + 4 + 3) + (BYTES_PER_ENV_STEP_SCRIPTED - 71) / H   # outputs every step, state once per launch
     roofline = {"kernel": "navsim_step_kernel", "bound": "hbm", "achieved": achieved, "peak": peak_gbs,
-                "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
-                "bytes_per_env_step": BYTES_PER_ENV_STEP_SCRIPTED, "us_per_launch": per_launch_s * 1e6,
-                "note": "at N=8192 one launch moves 1.7 MB: launch-latency bound; see roofline_sweep"}
+                "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get((N, H)),
+                "peak_source": peak_src, "bytes_per_env_step": BYTES_PER_ENV_STEP_SCRIPTED,
+                "env_steps_per_launch": N * H, "us_per_launch": per_launch_s * 1e6, "us_per_env_step_batch": per_launch_s * 1e6 / H,
+                "lanes_per_agent": env.lanes_per_agent,
+                "fused_launch_bytes_per_env_step": fused_bytes,
+                "note": "one launch = H steps with the agent state in registers: per env-step it really moves "
+                        f"{fused_bytes:.1f} B (outputs + state/H) instead of the per-step-launch figure {BYTES_PER_ENV_STEP_SCRIPTED} B "
+                        "that `achieved` is defined on; N=8192 agents = 55 per SM, so the launch is bound by one "
+                        "agent-step's dependent-instruction latency, not by HBM; see roofline_sweep for the large-batch figure",
+                "single_step_launch_us": single_launch_us,
+                "single_step_launch_env_steps_per_s": N / (single_launch_us * 1e-6)}
     sweep = []
     if not args.no_sweep:
-        for n_big in (65536, 1 << 20, 1 << 22):
+        for n_big, h_big in ((65536, 64), (1 << 20, 16), (1 << 22, 8)):
             e2 = VecEnv(n_big, map="stage_1", device=local, seed=0)
             e2.reset()
-            e2.step_scripted(5, 0)
+            ob = e2.rollout_scripted(h_big, 0)
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = 20
-            a.record(); e2.step_scripted(reps, 0); b.record()
+            reps = 5
+            a.record()
+            for _ in range(reps):
+                e2.rollout_scripted(h_big, 0, out=ob)
+            b.record()
             torch.cuda.synchronize()
-            s = a.elapsed_time(b) * 1e-3 / reps
+            s = a.elapsed_time(b) * 1e-3 / (reps * h_big)
             gbs = BYTES_PER_ENV_STEP_SCRIPTED * n_big / s / 1e9
-            sweep.append({"agents": n_big, "us_per_launch": s * 1e6, "env_steps_per_s": n_big / s, "achieved": gbs,
-                          "frac": gbs / peak_gbs})
+            e2.step_scripted(1, 0)
+            a.record()
+            for _ in range(10):
+                e2.step_scripted(1, 0)
+            b.record()
+            torch.cuda.synchronize()
+            s1 = a.elapsed_time(b) * 1e-3 / 10
+            sweep.append({"agents": n_big, "steps_per_launch": h_big, "lanes_per_agent": e2.lanes_per_agent,
+                          "us_per_env_step_batch": s * 1e6, "env_steps_per_s": n_big / s,
+                          "achieved": gbs, "frac": gbs / peak_gbs,
+                          "single_step_launch": {"us_per_launch": s1 * 1e6, "achieved": BYTES_PER_ENV_STEP_SCRIPTED * n_big / s1 / 1e9,
+                                                 "frac": BYTES_PER_ENV_STEP_SCRIPTED * n_big / s1 / 1e9 / peak_gbs}})
             e2.close()
-            del e2
+            del e2, ob
 
     threads = os.cpu_count() or 1
     cpu_v, cpu_steps, cpu_dt = cpu_port_throughput(N, args.cpu_seconds, threads)
@@ -333,7 +373,8 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"stage_1 map, {N} agents/GPU, 10-beam LiDAR, 16-D obs / 2-D action, "
                                f"{H} env steps per bench step, scripted Philox actions, auto-reset episodes (cap 500)",
-                   "agents_per_gpu": N, "horizon": H, "l2": "flushed between timed steps (256 MiB write, untimed)",
+                   "agents_per_gpu": N, "horizon": H, "launches_per_bench_step": 1,
+                   "l2": "flushed between timed steps (256 MiB write, untimed)",
                    "parallelism": f"agents sharded x{world}, no data-path collective"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N * 8 * H,

@@ -51,7 +51,7 @@ typedef struct navsim_cfg {
   int32_t device;            /* CUDA ordinal */
   int32_t n_reset_rects;     /* goal rejection boxes used by Env.reset  (:340-343) */
   int32_t n_respawn_rects;   /* goal rejection boxes used on arrival    (:248-251) */
-  int32_t reserved0;
+  int32_t lanes_per_agent;   /* 0 = chosen from N; else 1,2,..32 GPU lanes cooperating on one agent's step */
   uint64_t seed;             /* Philox key for goal sampling */
   int64_t agent_id_offset;   /* global id of agent 0 (rank * N when sharded) */
   double dt;                 /* 1 / 5 Hz LiDAR, gazebo.xacro:107 */
@@ -128,10 +128,19 @@ int navsim_reset_host(navsim_t* h, const uint8_t* mask_host, float* obs_host);
 int navsim_step_host(navsim_t* h, const float* act_host, float* obs_host, float* rew_host,
                      uint8_t* done_host, uint8_t* arrive_host, uint8_t* trunc_host);
 
-/* Scripted-action driver used by benchmarks: `num_steps` consecutive steps in one launch
- * sequence with actions a0~U[0,1], a1~U[-1,1] drawn on device (Philox, key action_seed). */
+/* Scripted-action driver used by benchmarks: `num_steps` consecutive steps in ONE launch with
+ * actions a0~U[0,1], a1~U[-1,1] drawn on device (Philox, key action_seed); every step
+ * overwrites the [N,.] output arrays, which end up holding the last step's results. */
 int navsim_step_scripted(navsim_t* h, int32_t num_steps, uint64_t action_seed, float* obs_dev,
                          float* rew_dev, uint8_t* done_dev, uint8_t* arrive_dev, void* stream);
+
+/* Rollout-layout form of the same driver (PPO.rollout's buffers, ppo.py:476-483, time-major):
+ * ONE launch runs `num_steps` steps per agent with the state held in registers and writes
+ * obs_dev[H,N,16], rew_dev[H,N], done/arrive/trunc_dev[H,N] (trunc_dev may be NULL); row t holds
+ * what navsim_step would have returned at step t. */
+int navsim_rollout_scripted(navsim_t* h, int32_t num_steps, uint64_t action_seed, float* obs_dev,
+                            float* rew_dev, uint8_t* done_dev, uint8_t* arrive_dev, uint8_t* trunc_dev,
+                            void* stream);
 
 /* LiDAR ranges of the current pose, ranges_dev[N, num_beams] doubles (+-inf gated),
  * i.e. the LaserScan message of environment_new.py:284 — exposed for parity tests. */
@@ -143,6 +152,8 @@ int navsim_set_state(navsim_t* h, int32_t field, const void* host_in);
 
 int navsim_get_stats(navsim_t* h, navsim_stats* out, int32_t clear);
 int navsim_num_agents(const navsim_t* h);
+/* Lanes per agent the step kernel runs with (cfg.lanes_per_agent, or the library's choice). */
+int navsim_lanes_per_agent(const navsim_t* h);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t navsim_launch_count(const navsim_t* h);
 

@@ -31,7 +31,7 @@ class NavsimCfg(ctypes.Structure):
     _fields_ = [
         ("num_agents", ctypes.c_int32), ("num_beams", ctypes.c_int32), ("max_episode_steps", ctypes.c_int32),
         ("auto_reset", ctypes.c_int32), ("device", ctypes.c_int32), ("n_reset_rects", ctypes.c_int32),
-        ("n_respawn_rects", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("n_respawn_rects", ctypes.c_int32), ("lanes_per_agent", ctypes.c_int32),
         ("seed", ctypes.c_uint64), ("agent_id_offset", ctypes.c_int64),
         ("dt", ctypes.c_double), ("lidar_offset_x", ctypes.c_double),
         ("lidar_min", ctypes.c_double), ("lidar_max", ctypes.c_double),
@@ -74,12 +74,14 @@ NAVSIM_SYMBOLS = {
     "navsim_reset_host": (ctypes.c_int, [_vp, _vp, _vp]),
     "navsim_step_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "navsim_step_scripted": (ctypes.c_int, [_vp, _i32, _u64, _vp, _vp, _vp, _vp, _vp]),
+    "navsim_rollout_scripted": (ctypes.c_int, [_vp, _i32, _u64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "navsim_scan": (ctypes.c_int, [_vp, _vp, _vp]),
     "navsim_get_state": (ctypes.c_int, [_vp, _i32, _vp]),
     "navsim_set_state": (ctypes.c_int, [_vp, _i32, _vp]),
     "navsim_get_stats": (ctypes.c_int, [_vp, ctypes.POINTER(NavsimStats), _i32]),
     "navsim_num_agents": (ctypes.c_int, [_vp]),
     "navsim_launch_count": (_i64, [_vp]),
+    "navsim_lanes_per_agent": (ctypes.c_int, [_vp]),
 }
 
 class NavppoCfg(ctypes.Structure):

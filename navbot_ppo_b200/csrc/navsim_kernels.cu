@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -60,10 +61,13 @@ int fail(int code, const std::string& msg) { return nav_fail(code, msg); }
 // Scalars the kernels need, passed by value (fits the 4 KB kernel-parameter window).
 struct SimConst {
   int32_t N, B, S, max_steps, auto_reset, n_reset_rects, n_respawn_rects, closed_boxes;
+  int32_t rt_R, rt_W;                 // bearing table: offsets -rt_R..rt_R tenths of a metre, row length
+  int32_t pick[NAVSIM_LIDAR_FEATS];   // beam index of lidar feature i = int(i * B / 10), environment_new.py:293
   uint64_t seed;
   int64_t agent_off;
   double dt, off_x, rmin, rmax, collide, arrive_thr, r_scale, r_collide, r_arrive, diag;
   double goal_lo, goal_hi, sx, sy, sth;
+  float inv_diag;
   double reset_rects[NAVSIM_MAX_RECTS * 4];
   double respawn_rects[NAVSIM_MAX_RECTS * 4];
 };
@@ -73,6 +77,17 @@ struct SimState {
   float *pa0, *pa1, *ep_ret, *ep_path, *last_move;
   int32_t* steps;
   uint32_t* draws;
+};
+
+// Where one launch reads actions and writes the per-step outputs.  Fused multi-step launches
+// advance the output pointers by the strides after every step (time-major [H, N, .] rollout
+// layout, ppo.py:476-483) or keep overwriting the same [N, .] arrays (stride 0).
+struct StepIO {
+  const float* act;   // [N,2], single-step launches with caller-provided actions
+  float* obs;         // [N,16]
+  float* rew;         // [N]
+  uint8_t *done, *arrive, *trunc;  // [N] each, trunc may be null
+  long long obs_stride, vec_stride;
 };
 
 // Device-side episode statistics (ppo.py:558-580).
@@ -88,12 +103,29 @@ struct Agent {
   uint32_t draws;
 };
 
+constexpr int kBlock = 128;                  // threads per CTA of every simulator kernel
 constexpr int kObsPad = NAVSIM_OBS_DIM + 1;  // +1 float: conflict-free column access
+constexpr int kPadBeams = 36;                // register-resident beam count of the padded variant
+constexpr float kInvRmax = 1.0f / 3.5f;      // environment_new.py:289 (lidar / 3.5)
 
-// Obstacle set as staged into shared memory: S packed wall records (8 floats each), then the
-// beam table (B cosines, B sines), fp32, padded to the 16-byte granule of cp.async.bulk.
+// Obstacle set as staged into shared memory: S packed wall records (8 floats each), the beam
+// table (B cosines, B sines) and the B sanitised ranges seen from the spawn pose, fp32, padded
+// to the 16-byte granule of cp.async.bulk.
 __host__ __device__ inline uint32_t map_bytes_of(int B, int S) {
-  return (uint32_t)(((size_t)(NV_SEG_FLOATS * S + 2 * B) * sizeof(float) + 15) & ~(size_t)15);
+  return (uint32_t)(((size_t)(NV_SEG_FLOATS * S + 3 * B) * sizeof(float) + 15) & ~(size_t)15);
+}
+
+struct MapView {
+  const float *seg, *bc, *bs, *start_r;
+};
+
+__device__ __forceinline__ MapView map_view(const float* s_map, int B, int S) {
+  MapView m;
+  m.seg = s_map;
+  m.bc = s_map + NV_SEG_FLOATS * S;
+  m.bs = m.bc + B;
+  m.start_r = m.bs + B;
+  return m;
 }
 
 // ----------------------------------------------------------------------------------------
@@ -118,7 +150,10 @@ __device__ __forceinline__ void stage_map(float* s_map, const float* g_map, uint
         "l"(g_map), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
   }
-  // every thread waits for phase 0 of the barrier
+}
+
+// every thread waits for phase 0 of the barrier (called after the state loads are in flight)
+__device__ __forceinline__ void wait_map(uint64_t* bar) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -132,112 +167,42 @@ __device__ __forceinline__ void stage_map(float* s_map, const float* g_map, uint
 }
 
 // ----------------------------------------------------------------------------------------
-// Env.getOdometry (environment_new.py:138-181) from the pose directly.
+// Env.getOdometry (environment_new.py:138-181) in integers: yaw in whole degrees, rel_theta
+// and diff_angle in hundredths of a degree (navsim_math.h explains why this is exact).  The
+// bearing comes from the per-map table rt_tab (built by navsim_set_map with the host build of
+// nv_rel_theta_centideg) whenever both goal offsets are within +-rt_R tenths of a metre.
 // ----------------------------------------------------------------------------------------
-__device__ __forceinline__ void odom_features(double x, double y, double th, double gx, double gy, double* yaw_o,
-                                              double* rel_theta_o, double* diff_o) {
+__device__ __forceinline__ void odom_features(const SimConst& c, const uint16_t* __restrict__ rt_tab, double x, double y,
+                                              double th, double gx, double gy, int* yaw_o, int* rel_o, int* diff_o) {
   // :142 — the quaternion round trip atan2(sin th, cos th) returns th itself for th in (-pi, pi]
-  double yaw = nv_pyround0(th * NV_RAD2DEG) + 0.0;
-  if (!(yaw >= 0.0)) yaw = yaw + 360.0;            // :144-147
-  double rx = nv_pyround1(gx - x);                 // :149
-  double ry = nv_pyround1(gy - y);                 // :150
-  double theta;
-  if (rx > 0.0 && ry > 0.0) theta = nv_atan(ry / rx);                       // :153
-  else if (rx > 0.0 && ry < 0.0) theta = 2.0 * NV_PI + nv_atan(ry / rx);    // :155
-  else if (rx < 0.0 && ry < 0.0) theta = NV_PI + nv_atan(ry / rx);          // :157
-  else if (rx < 0.0 && ry > 0.0) theta = NV_PI + nv_atan(ry / rx);          // :159
-  else if (rx == 0.0 && ry > 0.0) theta = 0.5 * NV_PI;                      // :161
-  else if (rx == 0.0 && ry < 0.0) theta = 1.5 * NV_PI;                      // :163
-  else if (ry == 0.0 && rx > 0.0) theta = 0.0;                              // :165
-  else theta = NV_PI;                                                       // :167
-  double rel_theta = nv_pyround2(theta * NV_RAD2DEG);                       // :169
-  double diff = yaw - rel_theta;                                            // :170
-  if ((0.0 <= diff && diff <= 180.0) || (-180.0 <= diff && diff < 0.0)) diff = nv_pyround2(diff);
-  else if (diff < -180.0) diff = nv_pyround2(360.0 + diff);
-  else diff = nv_pyround2(-360.0 + diff);
+  int yaw = (int)nv_pyround0(th * NV_RAD2DEG);
+  if (yaw < 0) yaw += 360;                                  // :144-147
+  const double nxd = nv_round_scaled(gx - x, 10.0);         // :149  rel_dis_x = nx / 10
+  const double nyd = nv_round_scaled(gy - y, 10.0);         // :150
+  int m;
+  const double R = (double)c.rt_R;
+  if (fabs(nxd) <= R && fabs(nyd) <= R) {
+    m = (int)__ldg(rt_tab + ((int)nyd + c.rt_R) * c.rt_W + ((int)nxd + c.rt_R));
+  } else {
+    const double lim = 2.0e9;
+    const double cx = fmin(fmax(nxd, -lim), lim), cy = fmin(fmax(nyd, -lim), lim);
+    m = nv_rel_theta_centideg((int)cx, (int)cy);            // :153-169
+  }
   *yaw_o = yaw;
-  *rel_theta_o = rel_theta;
-  *diff_o = diff;
+  *rel_o = m;
+  *diff_o = nv_diff_angle_centideg(yaw, m);                 // :170-176
 }
 
-// LaserScan of the pose + getState + observation assembly (:183-207, :289-301).
-// s_seg: S packed wall records (navsim_math.h), s_bc/s_bs: beam direction table, fp32, all in
-// shared memory.
-// KB > 0: beam count known at compile time -> segment-major loop with the per-beam best
-// inverse hit distances in registers (the per-wall setup and culling run once per wall);
-// KB == 0: any beam count, beam-major.  Both orders visit a beam's segments 0..S-1 in the
-// same order with the same arithmetic, so they agree bit for bit with the host build.
-template <int KB>
-__device__ __forceinline__ void observe(const SimConst& c, const float* s_seg, const float* s_bc, const float* s_bs,
-                                        const Agent& a, float pa0, float pa1,
-                                        float* obs /* kObsPad row in smem */, bool* done, bool* arrive,
-                                        double* dist) {
-  double s, co;
-  nv_sincos(a.th, &s, &co);
-  const float ox = (float)(a.x + c.off_x * co), oy = (float)(a.y + c.off_x * s);
-  const float ch = (float)co, sh = (float)s;
-  const float rmin = (float)c.rmin, rmax = (float)c.rmax;
-  float mn = NV_INF_F;
-  if (KB > 0) {
-    float dx[KB > 0 ? KB : 1], dy[KB > 0 ? KB : 1], q[KB > 0 ? KB : 1];
-#pragma unroll
-    for (int b = 0; b < KB; ++b) {
-      nv_beam_dir(ch, sh, s_bc[b], s_bs[b], &dx[b], &dy[b]);
-      q[b] = 0.0f;
-    }
-    for (int k = 0; k < c.S; ++k) {
-      nv_seg_view v;
-      if (!nv_seg_setup(s_seg + NV_SEG_FLOATS * k, ox, oy, c.closed_boxes, &v)) continue;
-#pragma unroll
-      for (int b = 0; b < KB; ++b) q[b] = nv_ray_q(&v, dx[b], dy[b], q[b]);
-    }
-#pragma unroll
-    for (int b = 0; b < KB; ++b) {
-      float r = nv_range_from_q(q[b], rmin, rmax);
-      if (r == NV_INF_F) r = 3.5f;                  // :193-194
-      mn = (r < mn) ? r : mn;
-      if (KB == NAVSIM_LIDAR_FEATS) obs[b] = r / 3.5f;  // :289, idx_i == i when L == 10
-      else q[b] = r;
-    }
-    if (KB != NAVSIM_LIDAR_FEATS) {
-#pragma unroll
-      for (int i = 0; i < NAVSIM_LIDAR_FEATS; ++i) {
-        const int idx = (int)((double)(i * KB) / 10.0);  // :293
-        float r = 0.f;
-#pragma unroll
-        for (int b = 0; b < KB; ++b) r = (b == idx) ? q[b] : r;
-        obs[i] = r / 3.5f;
-      }
-    }
-  } else {
-    int pick = 0;                                   // next lidar feature to emit
-    int next_idx = 0;                               // int(pick * L / 10), :293
-    for (int b = 0; b < c.B; ++b) {
-      float dxb, dyb;
-      nv_beam_dir(ch, sh, s_bc[b], s_bs[b], &dxb, &dyb);
-      float r = nv_range_from_q(nv_beam_q(ox, oy, dxb, dyb, s_seg, c.S, c.closed_boxes), rmin, rmax);
-      if (r == NV_INF_F) r = 3.5f;                  // :193-194
-      mn = (r < mn) ? r : mn;
-      while (pick < NAVSIM_LIDAR_FEATS && next_idx == b) {
-        obs[pick] = r / 3.5f;                       // :289
-        ++pick;
-        next_idx = (int)((double)(pick * c.B) / 10.0);
-      }
-    }
-  }
-  *done = (c.collide > (double)mn) && (mn > 0.0f);  // :200
-  const double ddx = a.gx - a.x, ddy = a.gy - a.y;
-  const double d = sqrt(ddx * ddx + ddy * ddy);     // :203
-  *arrive = (d <= c.arrive_thr);                    // :204
-  *dist = d;
-  double yaw, rel_theta, diff;
-  odom_features(a.x, a.y, a.th, a.gx, a.gy, &yaw, &rel_theta, &diff);
-  obs[10] = pa0;                                    // :299-300
+// obs[10..15] (:299-301) from the integer features; every lane of an agent's group holds the
+// same values, lane 0 writes the row.
+__device__ __forceinline__ void write_goal_feats(const SimConst& c, float* obs, float pa0, float pa1, double dist, int yaw,
+                                                 int rel, int diff) {
+  obs[10] = pa0;
   obs[11] = pa1;
-  obs[12] = (float)d / (float)c.diag;               // :301
-  obs[13] = (float)yaw / 360.0f;
-  obs[14] = (float)rel_theta / 360.0f;
-  obs[15] = (float)diff / 180.0f;
+  obs[12] = (float)dist * c.inv_diag;
+  obs[13] = (float)yaw * (1.0f / 360.0f);
+  obs[14] = (float)rel * (1.0f / 36000.0f);
+  obs[15] = (float)diff * (1.0f / 18000.0f);
 }
 
 __device__ __forceinline__ bool in_rects(const double* r, int n, double gx, double gy) {
@@ -260,18 +225,26 @@ __device__ __forceinline__ void sample_goal(const SimConst& c, const double* rec
   }
 }
 
-// Env.reset (:312-382) for one agent; obs row filled with the first observation.
-template <int KB>
-__device__ __forceinline__ void reset_agent(const SimConst& c, const float* s_seg, const float* s_bc,
-                                            const float* s_bs, uint64_t agent, Agent* a, float* obs) {
+// Env.reset (:312-382) for one agent.  The robot always respawns at the same pose
+// (turtlebot3_stage_1.launch:3-5), so its first LaserScan is a per-map constant: the B
+// sanitised ranges were cast once by navsim_set_map (host build of the same physics) and sit
+// behind the beam table in shared memory.  Row ownership follows the step kernel: the lane
+// with (i mod lidar_mod) == lidar_lane writes lidar feature i, `feats` lanes write obs[10..15].
+__device__ __forceinline__ void reset_agent(const SimConst& c, const MapView& mv, const uint16_t* __restrict__ rt_tab,
+                                            uint64_t agent, Agent* a, float* obs, bool feats, int lidar_mod,
+                                            int lidar_lane) {
   a->x = c.sx; a->y = c.sy; a->th = c.sth;                       // reset_world, :325
   sample_goal(c, c.reset_rects, c.n_reset_rects, agent, a);
   const double dx = a->gx - a->x, dy = a->gy - a->y;
   a->past = sqrt(dx * dx + dy * dy);                             // :359 via :116-120
   a->pa0 = 0.f; a->pa1 = 0.f; a->steps = 0;
   a->ep_ret = 0.f; a->ep_path = 0.f; a->last_move = 0.f;
-  bool done, arrive; double d;
-  observe<KB>(c, s_seg, s_bc, s_bs, *a, 0.f, 0.f, obs, &done, &arrive, &d);
+  int yaw, rel, diff;
+  odom_features(c, rt_tab, a->x, a->y, a->th, a->gx, a->gy, &yaw, &rel, &diff);
+#pragma unroll
+  for (int i = 0; i < NAVSIM_LIDAR_FEATS; ++i)
+    if ((i & (lidar_mod - 1)) == lidar_lane) obs[i] = mv.start_r[c.pick[i]] * kInvRmax;      // :361-369
+  if (feats) write_goal_feats(c, obs, 0.f, 0.f, a->past, yaw, rel, diff);                    // :372-376
 }
 
 __device__ __forceinline__ void load_agent(const SimState& st, int i, Agent* a) {
@@ -293,67 +266,203 @@ __device__ __forceinline__ void store_agent(const SimState& st, int i, const Age
   }
 }
 
-// Coalesced write-out of a CTA's observation tile: rows [row0, row0+rows) of obs[N,16].
-__device__ __forceinline__ void flush_obs_tile(const float* s_obs, float* obs, int row0, int rows) {
-  const int vec_total = rows * (NAVSIM_OBS_DIM / 4);
-  float4* dst = reinterpret_cast<float4*>(obs + (size_t)row0 * NAVSIM_OBS_DIM);
-  for (int v = threadIdx.x; v < vec_total; v += blockDim.x) {
-    const int r = v >> 2, q = (v & 3) * 4;
-    const float* src = s_obs + r * kObsPad + q;
-    dst[v] = make_float4(src[0], src[1], src[2], src[3]);
+// ----------------------------------------------------------------------------------------
+// LaserScan (row R) of one agent by the G lanes of its group.  Wall k is handled by lane
+// k mod G: that lane culls / orients the wall once and tests all beams against it, keeping
+// the best inverse hit distance per beam in registers; the group then combines the per-beam
+// maxima with one warp reduction (redux.sync over the group's lane mask) per beam.  q >= +0
+// always, so the unsigned-integer maximum of the bit patterns is the float maximum, and a
+// maximum does not depend on the order the walls were visited in: the result is bit-identical
+// to the serial sweep of the host build (nv_beam_q).
+// KB = beams held in registers: exactly B when KB == 10 (the reference's sensor), else B <= KB.
+// Output: r[b] = range with the Gazebo gates applied, +inf already mapped to 3.5 (:193-194).
+// ----------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) {
+    const float w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = (w > v) ? w : v;
   }
+  return v;
+}
+
+template <int G>
+__device__ __forceinline__ float group_min(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) {
+    const float w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = (w < v) ? w : v;
+  }
+  return v;
+}
+
+// Sweeps the walls and leaves in q[b] the largest inverse hit distance of beam b over ALL
+// walls (every lane of the group holds all of them).
+template <int G, int KB>
+__device__ __forceinline__ void group_sweep(const SimConst& c, const MapView& mv, float ox, float oy, float ch, float sh,
+                                            int g, float* q) {
+  const int B = (KB == NAVSIM_LIDAR_FEATS) ? KB : c.B;
+  float dx[KB], dy[KB];
+#pragma unroll
+  for (int b = 0; b < KB; ++b) {
+    if (b < B) nv_beam_dir(ch, sh, mv.bc[b], mv.bs[b], &dx[b], &dy[b]);
+    else { dx[b] = 0.f; dy[b] = 0.f; }
+    q[b] = 0.0f;
+  }
+  for (int k = g; k < c.S; k += G) {
+    nv_seg_view v;
+    if (!nv_seg_setup(mv.seg + NV_SEG_FLOATS * k, ox, oy, c.closed_boxes, &v)) continue;
+#pragma unroll
+    for (int b = 0; b < KB; ++b)
+      if (b < B) q[b] = nv_ray_q(&v, dx[b], dy[b], q[b]);
+  }
+  if (G > 1) {
+#pragma unroll
+    for (int b = 0; b < KB; ++b)
+      if (b < B) q[b] = group_max<G>(q[b]);
+  }
+}
+
+// Range of one beam with the Gazebo gates and getState's sanitising (+inf -> 3.5, :193-194).
+__device__ __forceinline__ float sanitised_range(float q, float rmin, float rmax) {
+  const float t = nv_range_from_q(q, rmin, rmax);
+  return (t == NV_INF_F) ? 3.5f : t;
 }
 
 extern __shared__ __align__(16) unsigned char dyn_smem[];
 
 // ----------------------------------------------------------------------------------------
-// Env.step for all agents.  SCRIPTED: actions drawn on device (benchmark driver).
+// Env.step for all agents, `nsteps` consecutive steps per launch.
+//   G        lanes per agent (1, 2, 4, .. 32): the host picks it from N so that small batches
+//            (BASELINE's 8192 agents = 55 per SM) still fill the machine and each agent's
+//            step has a short critical path; G = 1 is the plain thread-per-agent form for
+//            batches that fill the machine on their own.  Every lane of a group carries the
+//            agent's scalar state redundantly (identical arithmetic, identical bits); the wall
+//            sweep is the part that is split.
+//   KB       10: the reference's 10-beam sensor; kPadBeams: any B <= 36 (beam sweep).
+//   SCRIPTED actions drawn on device (benchmark / rollout driver), else read from io.act.
 // ----------------------------------------------------------------------------------------
-template <bool SCRIPTED, int KB>
-__global__ void __launch_bounds__(128) navsim_step_kernel(SimConst c, SimState st, const float* __restrict__ g_map,
-                                                          const float* __restrict__ act, float* __restrict__ obs,
-                                                          float* __restrict__ rew, uint8_t* __restrict__ done_o,
-                                                          uint8_t* __restrict__ arrive_o,
-                                                          uint8_t* __restrict__ trunc_o, DevStats* stats,
-                                                          uint64_t action_seed, uint32_t script_step) {
-  // shared: [mbarrier 16 B][map: 8S + 2B floats, padded to 16 B][obs tile: blockDim x kObsPad floats]
+template <int G, int KB, bool SCRIPTED>
+__global__ void __launch_bounds__(kBlock) navsim_step_kernel(SimConst c, SimState st, const float* __restrict__ g_map,
+                                                             const uint16_t* __restrict__ rt_tab, StepIO io,
+                                                             DevStats* stats, uint64_t action_seed,
+                                                             uint32_t script_step0, int nsteps) {
+  constexpr int APB = kBlock / G;  // agents per CTA
+  constexpr int APW = 32 / G;      // agents per warp
+  // shared: [mbarrier 16 B][map blob, padded to 16 B][obs tile: APB x kObsPad floats]
   uint64_t* bar = reinterpret_cast<uint64_t*>(dyn_smem);
   float* s_map = reinterpret_cast<float*>(dyn_smem + 16);
   const uint32_t map_bytes = map_bytes_of(c.B, c.S);
   float* s_obs = reinterpret_cast<float*>(dyn_smem + 16 + map_bytes);
   stage_map(s_map, g_map, map_bytes, bar);
-  const float* s_seg = s_map;
-  const float* s_bc = s_map + NV_SEG_FLOATS * c.S;
-  const float* s_bs = s_bc + c.B;
+  const MapView mv = map_view(s_map, c.B, c.S);
 
-  const int row0 = blockIdx.x * blockDim.x;
-  const int i = row0 + threadIdx.x;
-  float* my_obs = s_obs + threadIdx.x * kObsPad;
-  if (i < c.N) {
-    Agent a;
-    load_agent(st, i, &a);
-    const uint64_t agent = (uint64_t)(c.agent_off + i);
+  const int lane = threadIdx.x & 31;
+  const int g = threadIdx.x & (G - 1);
+  const int slot = threadIdx.x / G;
+  const int i_raw = blockIdx.x * APB + slot;
+  const bool valid = i_raw < c.N;
+  const int i = valid ? i_raw : c.N - 1;   // surplus lanes shadow the last agent and store nothing
+  const bool writer = valid && g == 0;
+  const uint64_t agent = (uint64_t)(c.agent_off + i);
+  float* my_obs = s_obs + slot * kObsPad;
+  Agent a;
+  load_agent(st, i, &a);
+  bool goal_dirty = false;
+
+  for (int t = 0; t < nsteps; ++t) {
     float a0, a1;
     if (SCRIPTED) {
       uint32_t o[4];
-      nv_philox4x32_10(script_step, 1u, (uint32_t)agent, (uint32_t)(agent >> 32), (uint32_t)action_seed,
+      nv_philox4x32_10(script_step0 + (uint32_t)t, 1u, (uint32_t)agent, (uint32_t)(agent >> 32), (uint32_t)action_seed,
                        (uint32_t)(action_seed >> 32), o);
       a0 = (float)(o[0] >> 8) * (1.0f / 16777216.0f);
       a1 = (float)(o[1] >> 8) * (2.0f / 16777216.0f) - 1.0f;
     } else {
-      const float2 av = reinterpret_cast<const float2*>(act)[i];
+      const float2 av = reinterpret_cast<const float2*>(io.act)[i];
       a0 = av.x; a1 = av.y;
     }
     // ppo.py:535-538 — path length trails the motion by one step
     if (a.steps > 0) a.ep_path += a.last_move;
+
+    // cmd_vel -> pose after one LiDAR period (:276-286).  The step needs sin/cos of the
+    // midpoint heading (motion) and of the new heading (sensor); with G > 1 even lanes
+    // evaluate one, odd lanes the other, and they swap results.
+    double ds, th_mid, th_new, s_mid, c_mid, s_new, c_new;
+    nv_drive_plan(a.th, (double)a0 / 4.0, (double)a1, c.dt, &ds, &th_mid, &th_new);
+    if (G == 1) {
+      nv_sincos(th_mid, &s_mid, &c_mid);
+      nv_sincos(th_new, &s_new, &c_new);
+    } else {
+      const bool odd = (g & 1) != 0;
+      double sv, cv;
+      nv_sincos(odd ? th_new : th_mid, &sv, &cv);
+      const double ps = __shfl_xor_sync(0xffffffffu, sv, 1), pc = __shfl_xor_sync(0xffffffffu, cv, 1);
+      s_mid = odd ? ps : sv; c_mid = odd ? pc : cv;
+      s_new = odd ? sv : ps; c_new = odd ? cv : pc;
+    }
     const double px = a.x, py = a.y;
-    nv_drive(&a.x, &a.y, &a.th, (double)a0 / 4.0, (double)a1, c.dt);  // :276-286
+    nv_drive_apply(&a.x, &a.y, ds, s_mid, c_mid);
+    a.th = th_new;
     {
       const double mx = a.x - px, my = a.y - py;
       a.last_move = sqrtf((float)(mx * mx + my * my));
     }
-    bool done, arrive; double d;
-    observe<KB>(c, s_seg, s_bc, s_bs, a, a.pa0, a.pa1, my_obs, &done, &arrive, &d);  // :288-301
+
+    // LaserScan + getState (:183-207).  The map is first needed here: its TMA copy has been
+    // in flight behind the state loads and the drive arithmetic.
+    if (t == 0) wait_map(bar);
+    float q[KB];
+    group_sweep<G, KB>(c, mv, (float)(a.x + c.off_x * c_new), (float)(a.y + c.off_x * s_new), (float)c_new, (float)s_new, g,
+                       q);
+    const int B = (KB == NAVSIM_LIDAR_FEATS) ? KB : c.B;
+    const float rmin = (float)c.rmin, rmax = (float)c.rmax;
+    float mn = NV_INF_F;
+    if (G == 1 || KB != NAVSIM_LIDAR_FEATS) {
+      // every lane turns all beams into ranges; lane 0 of the group fills the row (:289-294)
+      int pickn = 0;
+#pragma unroll
+      for (int b = 0; b < KB; ++b) {
+        if (b < B) {
+          const float rb = sanitised_range(q[b], rmin, rmax);
+          mn = (rb < mn) ? rb : mn;
+          if (KB == NAVSIM_LIDAR_FEATS) {
+            if (writer) my_obs[b] = rb * kInvRmax;                   // idx_i == i when L == 10
+          } else {
+            while (pickn < NAVSIM_LIDAR_FEATS && c.pick[pickn] == b) {
+              if (writer) my_obs[pickn] = rb * kInvRmax;
+              ++pickn;
+            }
+          }
+        }
+      }
+    } else {
+      // 10 beams over G lanes: lane g owns beams g, g + G, ..; it divides only those, writes
+      // their features, and the group combines the minimum.
+      constexpr int PER = (KB + G - 1) / G;
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        const int mine = g + j * G;
+        float qm = 0.0f;
+#pragma unroll
+        for (int b = j * G; b < KB && b < (j + 1) * G; ++b) qm = (b == mine) ? q[b] : qm;
+        if (mine < KB) {
+          const float rb = sanitised_range(qm, rmin, rmax);
+          mn = (rb < mn) ? rb : mn;
+          if (valid) my_obs[mine] = rb * kInvRmax;
+        }
+      }
+      mn = group_min<G>(mn);
+    }
+    const bool done = (c.collide > (double)mn) && (mn > 0.0f);       // :200
+    const double ddx = a.gx - a.x, ddy = a.gy - a.y;
+    const double d = sqrt(ddx * ddx + ddy * ddy);                    // :203
+    const bool arrive = (d <= c.arrive_thr);                         // :204
+    int yaw, rel, diff;
+    odom_features(c, rt_tab, a.x, a.y, a.th, a.gx, a.gy, &yaw, &rel, &diff);
+    if (writer) write_goal_feats(c, my_obs, a.pa0, a.pa1, d, yaw, rel, diff);   // :299-301
+
     double reward = c.r_scale * (a.past - d);                        // :211-213
     a.past = d;                                                      // :214
     if (done) reward = c.r_collide;                                  // :216-217
@@ -362,57 +471,198 @@ __global__ void __launch_bounds__(128) navsim_step_kernel(SimConst c, SimState s
     a.steps += 1;                                                    // ppo.py:549
     a.ep_ret += (float)reward;                                       // ppo.py:544
     const bool timeout = a.steps >= c.max_steps;                     // ppo.py:552
-    rew[i] = (float)reward;
-    done_o[i] = done ? 1 : 0;
-    arrive_o[i] = arrive ? 1 : 0;
-    if (trunc_o) trunc_o[i] = (timeout && !done && !arrive) ? 1 : 0;
-    bool goal_changed = false;
+    if (writer) {
+      const long long vo = (long long)t * io.vec_stride + i;
+      io.rew[vo] = (float)reward;
+      io.done[vo] = done ? 1 : 0;
+      io.arrive[vo] = arrive ? 1 : 0;
+      if (io.trunc) io.trunc[vo] = (timeout && !done && !arrive) ? 1 : 0;
+    }
     if (c.auto_reset) {
       if (done || arrive || timeout) {                               // ppo.py:553-593
         // setReward has already respawned a goal on arrival (:245-253); rollout throws it
         // away by resetting, but the draws it consumed stay consumed
         if (arrive) sample_goal(c, c.respawn_rects, c.n_respawn_rects, agent, &a);
-        atomicAdd(&stats->episodes, 1ull);
-        if (arrive) atomicAdd(&stats->successes, 1ull);              // ppo.py:558-560
-        else if (done) atomicAdd(&stats->collisions, 1ull);
-        else atomicAdd(&stats->timeouts, 1ull);
-        atomicAdd(&stats->return_sum, (double)a.ep_ret);
-        atomicAdd(&stats->length_sum, (double)a.steps);
-        atomicAdd(&stats->path_sum, (double)a.ep_path);
-        reset_agent<KB>(c, s_seg, s_bc, s_bs, agent, &a, my_obs);
-        goal_changed = true;
+        if (writer) {
+          atomicAdd(&stats->episodes, 1ull);
+          if (arrive) atomicAdd(&stats->successes, 1ull);            // ppo.py:558-560
+          else if (done) atomicAdd(&stats->collisions, 1ull);
+          else atomicAdd(&stats->timeouts, 1ull);
+          atomicAdd(&stats->return_sum, (double)a.ep_ret);
+          atomicAdd(&stats->length_sum, (double)a.steps);
+          atomicAdd(&stats->path_sum, (double)a.ep_path);
+        }
+        if (G == 1 || KB != NAVSIM_LIDAR_FEATS) reset_agent(c, mv, rt_tab, agent, &a, my_obs, writer, 1, writer ? 0 : -1);
+        else reset_agent(c, mv, rt_tab, agent, &a, my_obs, writer, G, valid ? g : -1);
+        goal_dirty = true;
       }
     } else if (arrive) {                                             // :245-267
       sample_goal(c, c.respawn_rects, c.n_respawn_rects, agent, &a);
       const double gx = a.gx - a.x, gy = a.gy - a.y;
       a.past = sqrt(gx * gx + gy * gy);
-      goal_changed = true;
+      goal_dirty = true;
     }
-    store_agent(st, i, a, goal_changed);
+
+    // each warp writes out the rows of its own agents as 128-bit stores
+    __syncwarp();
+    {
+      const int wslot = (threadIdx.x >> 5) * APW;
+      const int row0 = blockIdx.x * APB + wslot;
+      float* dst_base = io.obs + (long long)t * io.obs_stride;
+#pragma unroll
+      for (int v = lane; v < APW * (NAVSIM_OBS_DIM / 4); v += 32) {
+        const int rr = v >> 2, qq = (v & 3) * 4;
+        if (row0 + rr < c.N) {
+          const float* src = s_obs + (wslot + rr) * kObsPad + qq;
+          reinterpret_cast<float4*>(dst_base + (size_t)(row0 + rr) * NAVSIM_OBS_DIM)[v & 3] =
+              make_float4(src[0], src[1], src[2], src[3]);
+        }
+      }
+    }
+    __syncwarp();
   }
-  __syncthreads();
-  const int rows = min((int)blockDim.x, c.N - row0);
-  if (rows > 0) flush_obs_tile(s_obs, obs, row0, rows);
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats->steps, (unsigned long long)c.N);
+  if (writer) store_agent(st, i, a, goal_dirty);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats->steps, (unsigned long long)c.N * (unsigned long long)nsteps);
 }
 
-// Env.reset for the masked agents.
-__global__ void __launch_bounds__(128) navsim_reset_kernel(SimConst c, SimState st, const float* __restrict__ g_map,
-                                                           const uint8_t* __restrict__ mask,
-                                                           float* __restrict__ obs) {
+// Generic beam count (B > kPadBeams, up to NAVSIM_MAX_BEAMS): a warp per agent, one beam at a
+// time; every lane sweeps its walls for that beam and the warp combines the maxima.
+__global__ void __launch_bounds__(kBlock) navsim_step_anybeam_kernel(SimConst c, SimState st,
+                                                                     const float* __restrict__ g_map,
+                                                                     const uint16_t* __restrict__ rt_tab, StepIO io,
+                                                                     DevStats* stats, uint64_t action_seed,
+                                                                     uint32_t script_step0, int nsteps, int scripted) {
+  constexpr int APB = kBlock / 32;
   uint64_t* bar = reinterpret_cast<uint64_t*>(dyn_smem);
   float* s_map = reinterpret_cast<float*>(dyn_smem + 16);
   const uint32_t map_bytes = map_bytes_of(c.B, c.S);
   float* s_obs = reinterpret_cast<float*>(dyn_smem + 16 + map_bytes);
   stage_map(s_map, g_map, map_bytes, bar);
+  const MapView mv = map_view(s_map, c.B, c.S);
+  const int g = threadIdx.x & 31, slot = threadIdx.x >> 5;
+  const int i_raw = blockIdx.x * APB + slot;
+  const bool valid = i_raw < c.N;
+  const int i = valid ? i_raw : c.N - 1;
+  const bool writer = valid && g == 0;
+  const uint64_t agent = (uint64_t)(c.agent_off + i);
+  float* my_obs = s_obs + slot * kObsPad;
+  Agent a;
+  load_agent(st, i, &a);
+  wait_map(bar);
+  bool goal_dirty = false;
+  for (int t = 0; t < nsteps; ++t) {
+    __syncwarp();
+    float a0, a1;
+    if (scripted) {
+      uint32_t o[4];
+      nv_philox4x32_10(script_step0 + (uint32_t)t, 1u, (uint32_t)agent, (uint32_t)(agent >> 32), (uint32_t)action_seed,
+                       (uint32_t)(action_seed >> 32), o);
+      a0 = (float)(o[0] >> 8) * (1.0f / 16777216.0f);
+      a1 = (float)(o[1] >> 8) * (2.0f / 16777216.0f) - 1.0f;
+    } else {
+      const float2 av = reinterpret_cast<const float2*>(io.act)[i];
+      a0 = av.x; a1 = av.y;
+    }
+    if (a.steps > 0) a.ep_path += a.last_move;
+    const double px = a.x, py = a.y;
+    nv_drive(&a.x, &a.y, &a.th, (double)a0 / 4.0, (double)a1, c.dt);
+    {
+      const double mx = a.x - px, my = a.y - py;
+      a.last_move = sqrtf((float)(mx * mx + my * my));
+    }
+    double s_new, c_new;
+    nv_sincos(a.th, &s_new, &c_new);
+    const float ox = (float)(a.x + c.off_x * c_new), oy = (float)(a.y + c.off_x * s_new);
+    const float ch = (float)c_new, sh = (float)s_new, rmin = (float)c.rmin, rmax = (float)c.rmax;
+    float mn = NV_INF_F;
+    int pickn = 0;
+    for (int b = 0; b < c.B; ++b) {
+      float dxb, dyb, q = 0.0f;
+      nv_beam_dir(ch, sh, mv.bc[b], mv.bs[b], &dxb, &dyb);
+      for (int k = g; k < c.S; k += 32) {
+        nv_seg_view v;
+        if (nv_seg_setup(mv.seg + NV_SEG_FLOATS * k, ox, oy, c.closed_boxes, &v)) q = nv_ray_q(&v, dxb, dyb, q);
+      }
+      __syncwarp();
+      q = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(q)));
+      float rb = nv_range_from_q(q, rmin, rmax);
+      if (rb == NV_INF_F) rb = 3.5f;
+      mn = (rb < mn) ? rb : mn;
+      while (pickn < NAVSIM_LIDAR_FEATS && c.pick[pickn] == b) {
+        if (writer) my_obs[pickn] = rb * kInvRmax;
+        ++pickn;
+      }
+    }
+    const bool done = (c.collide > (double)mn) && (mn > 0.0f);
+    const double ddx = a.gx - a.x, ddy = a.gy - a.y;
+    const double d = sqrt(ddx * ddx + ddy * ddy);
+    const bool arrive = (d <= c.arrive_thr);
+    int yaw, rel, diff;
+    odom_features(c, rt_tab, a.x, a.y, a.th, a.gx, a.gy, &yaw, &rel, &diff);
+    if (writer) write_goal_feats(c, my_obs, a.pa0, a.pa1, d, yaw, rel, diff);
+    double reward = c.r_scale * (a.past - d);
+    a.past = d;
+    if (done) reward = c.r_collide;
+    if (arrive) reward = c.r_arrive;
+    a.pa0 = a0; a.pa1 = a1;
+    a.steps += 1;
+    a.ep_ret += (float)reward;
+    const bool timeout = a.steps >= c.max_steps;
+    if (writer) {
+      const long long vo = (long long)t * io.vec_stride + i;
+      io.rew[vo] = (float)reward;
+      io.done[vo] = done ? 1 : 0;
+      io.arrive[vo] = arrive ? 1 : 0;
+      if (io.trunc) io.trunc[vo] = (timeout && !done && !arrive) ? 1 : 0;
+    }
+    if (c.auto_reset) {
+      if (done || arrive || timeout) {
+        if (arrive) sample_goal(c, c.respawn_rects, c.n_respawn_rects, agent, &a);
+        if (writer) {
+          atomicAdd(&stats->episodes, 1ull);
+          if (arrive) atomicAdd(&stats->successes, 1ull);
+          else if (done) atomicAdd(&stats->collisions, 1ull);
+          else atomicAdd(&stats->timeouts, 1ull);
+          atomicAdd(&stats->return_sum, (double)a.ep_ret);
+          atomicAdd(&stats->length_sum, (double)a.steps);
+          atomicAdd(&stats->path_sum, (double)a.ep_path);
+        }
+        reset_agent(c, mv, rt_tab, agent, &a, my_obs, writer, 1, writer ? 0 : -1);
+        goal_dirty = true;
+      }
+    } else if (arrive) {
+      sample_goal(c, c.respawn_rects, c.n_respawn_rects, agent, &a);
+      const double gx = a.gx - a.x, gy = a.gy - a.y;
+      a.past = sqrt(gx * gx + gy * gy);
+      goal_dirty = true;
+    }
+    __syncwarp();
+    if (valid && g < NAVSIM_OBS_DIM / 4)
+      reinterpret_cast<float4*>(io.obs + (long long)t * io.obs_stride + (size_t)i * NAVSIM_OBS_DIM)[g] =
+          make_float4(my_obs[4 * g], my_obs[4 * g + 1], my_obs[4 * g + 2], my_obs[4 * g + 3]);
+    __syncwarp();
+  }
+  if (writer) store_agent(st, i, a, goal_dirty);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats->steps, (unsigned long long)c.N * (unsigned long long)nsteps);
+}
+
+// Env.reset for the masked agents (thread per agent).
+__global__ void __launch_bounds__(kBlock) navsim_reset_kernel(SimConst c, SimState st, const float* __restrict__ g_map,
+                                                              const uint16_t* __restrict__ rt_tab,
+                                                              const uint8_t* __restrict__ mask, float* __restrict__ obs) {
+  uint64_t* bar = reinterpret_cast<uint64_t*>(dyn_smem);
+  float* s_map = reinterpret_cast<float*>(dyn_smem + 16);
+  const uint32_t map_bytes = map_bytes_of(c.B, c.S);
+  float* s_obs = reinterpret_cast<float*>(dyn_smem + 16 + map_bytes);
+  stage_map(s_map, g_map, map_bytes, bar);
+  wait_map(bar);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.N) return;
   if (mask && !mask[i]) return;
   float* my_obs = s_obs + threadIdx.x * kObsPad;
   Agent a;
   load_agent(st, i, &a);
-  reset_agent<0>(c, s_map, s_map + NV_SEG_FLOATS * c.S, s_map + NV_SEG_FLOATS * c.S + c.B,
-                 (uint64_t)(c.agent_off + i), &a, my_obs);
+  reset_agent(c, map_view(s_map, c.B, c.S), rt_tab, (uint64_t)(c.agent_off + i), &a, my_obs, true, 1, 0);
   store_agent(st, i, a, true);
   if (obs) {
     float4* dst = reinterpret_cast<float4*>(obs + (size_t)i * NAVSIM_OBS_DIM);
@@ -421,12 +671,13 @@ __global__ void __launch_bounds__(128) navsim_reset_kernel(SimConst c, SimState 
 }
 
 // LaserScan only (parity tests of row R): ranges[N, B] doubles with the +-inf gates.
-__global__ void __launch_bounds__(128) navsim_scan_kernel(SimConst c, SimState st, const float* __restrict__ g_map,
-                                                          double* __restrict__ ranges) {
+__global__ void __launch_bounds__(kBlock) navsim_scan_kernel(SimConst c, SimState st, const float* __restrict__ g_map,
+                                                             double* __restrict__ ranges) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(dyn_smem);
   float* s_map = reinterpret_cast<float*>(dyn_smem + 16);
   stage_map(s_map, g_map, map_bytes_of(c.B, c.S), bar);
-  const float* s_seg = s_map; const float* s_bc = s_map + NV_SEG_FLOATS * c.S; const float* s_bs = s_bc + c.B;
+  wait_map(bar);
+  const MapView mv = map_view(s_map, c.B, c.S);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.N) return;
   double s, co;
@@ -435,8 +686,8 @@ __global__ void __launch_bounds__(128) navsim_scan_kernel(SimConst c, SimState s
   const float ch = (float)co, sh = (float)s;
   for (int b = 0; b < c.B; ++b) {
     float dx, dy;
-    nv_beam_dir(ch, sh, s_bc[b], s_bs[b], &dx, &dy);
-    ranges[(size_t)i * c.B + b] = (double)nv_range_from_q(nv_beam_q(ox, oy, dx, dy, s_seg, c.S, c.closed_boxes),
+    nv_beam_dir(ch, sh, mv.bc[b], mv.bs[b], &dx, &dy);
+    ranges[(size_t)i * c.B + b] = (double)nv_range_from_q(nv_beam_q(ox, oy, dx, dy, mv.seg, c.S, c.closed_boxes),
                                                           (float)c.rmin, (float)c.rmax);
   }
 }
@@ -450,7 +701,8 @@ struct navsim {
   navsim_cfg cfg;
   SimConst c;
   SimState st;
-  float* d_map = nullptr;        // [8S + 2B] floats: packed wall records, beam cos, beam sin
+  float* d_map = nullptr;        // [8S + 3B] floats: packed wall records, beam cos, beam sin, spawn-pose ranges
+  uint16_t* d_rt = nullptr;      // bearing table, (2 rt_R + 1)^2 entries (hundredths of a degree)
   int32_t S = 0;
   DevStats* d_stats = nullptr;
   cudaStream_t own_stream = nullptr;
@@ -461,16 +713,42 @@ struct navsim {
   uint8_t* d_flags = nullptr;
   int64_t launches = 0;
   uint32_t script_step = 0;
-  int block = 128;
+  int lanes = 1;                 // lanes per agent of the step kernel (G)
 };
 
 namespace {
 
-size_t smem_bytes(const navsim* h) {
-  return 16 + (size_t)map_bytes_of(h->c.B, h->c.S) + (size_t)h->block * kObsPad * sizeof(float);
+// variant: 0 = 10-beam register path, 1 = padded (B <= kPadBeams), 2 = any beam count (warp per agent)
+int variant_of(const navsim* h) { return h->c.B == NAVSIM_LIDAR_FEATS ? 0 : (h->c.B <= kPadBeams ? 1 : 2); }
+
+int lanes_of(const navsim* h) { return variant_of(h) == 2 ? 32 : h->lanes; }
+
+size_t step_smem_bytes(const navsim* h) {
+  return 16 + (size_t)map_bytes_of(h->c.B, h->c.S) + (size_t)(kBlock / lanes_of(h)) * kObsPad * sizeof(float);
 }
 
-int grid_of(const navsim* h) { return (h->c.N + h->block - 1) / h->block; }
+// reset / scan kernels: thread per agent
+size_t aux_smem_bytes(const navsim* h) {
+  return 16 + (size_t)map_bytes_of(h->c.B, h->c.S) + (size_t)kBlock * kObsPad * sizeof(float);
+}
+
+int aux_grid_of(const navsim* h) { return (h->c.N + kBlock - 1) / kBlock; }
+
+// Lanes per agent when the caller does not say.
+int pick_lanes(int n_agents, int requested) {
+  if (requested > 0) {
+    int g = 1;
+    while (g * 2 <= requested && g < 32) g *= 2;
+    return g;
+  }
+  const char* env = getenv("NAVSIM_LANES");
+  if (env && atoi(env) > 0) return pick_lanes(n_agents, atoi(env));
+  // measured on B200 (tools/lane_sweep.py, stage maps): the fused step is fastest with about
+  // 220 lanes per SM in flight -- N = 8192 -> 4 lanes, 16384 -> 2, >= 32768 -> 1
+  int g = 32;
+  while (g > 1 && (long long)n_agents * g > 32768LL) g /= 2;
+  return g;
+}
 
 int check_ready(const navsim* h) {
   if (!h) return fail(NAVSIM_EINVAL, "null handle");
@@ -478,21 +756,55 @@ int check_ready(const navsim* h) {
   return NAVSIM_OK;
 }
 
-int launch_step(navsim* h, const float* act, float* obs, float* rew, uint8_t* done, uint8_t* arrive, uint8_t* trunc,
-                cudaStream_t s, bool scripted, uint64_t action_seed) {
-  const size_t smem = smem_bytes(h);
-  const dim3 grid(grid_of(h)), block(h->block);
-#define NAVSIM_LAUNCH(SCR, KB)                                                                               \
-  navsim_step_kernel<SCR, KB><<<grid, block, smem, s>>>(h->c, h->st, h->d_map, act, obs, rew, done, arrive, trunc, \
-                                                        h->d_stats, action_seed, script_step)
-  const uint32_t script_step = scripted ? h->script_step++ : 0u;
-  const bool ten = (h->c.B == 10);  // the reference's sensor (gazebo.xacro:111) gets the unrolled path
-  if (scripted) { if (ten) NAVSIM_LAUNCH(true, 10); else NAVSIM_LAUNCH(true, 0); }
-  else          { if (ten) NAVSIM_LAUNCH(false, 10); else NAVSIM_LAUNCH(false, 0); }
-#undef NAVSIM_LAUNCH
+typedef void (*step_kernel_t)(SimConst, SimState, const float*, const uint16_t*, StepIO, DevStats*, uint64_t, uint32_t,
+                              int);
+
+template <int KB, bool SCR>
+step_kernel_t step_kernel_for_lanes(int g) {
+  switch (g) {
+    case 1: return navsim_step_kernel<1, KB, SCR>;
+    case 2: return navsim_step_kernel<2, KB, SCR>;
+    case 4: return navsim_step_kernel<4, KB, SCR>;
+    case 8: return navsim_step_kernel<8, KB, SCR>;
+    case 16: return navsim_step_kernel<16, KB, SCR>;
+    default: return navsim_step_kernel<32, KB, SCR>;
+  }
+}
+
+step_kernel_t step_kernel_of(const navsim* h, bool scripted) {
+  const int g = lanes_of(h);
+  if (variant_of(h) == 0)
+    return scripted ? step_kernel_for_lanes<NAVSIM_LIDAR_FEATS, true>(g) : step_kernel_for_lanes<NAVSIM_LIDAR_FEATS, false>(g);
+  return scripted ? step_kernel_for_lanes<kPadBeams, true>(g) : step_kernel_for_lanes<kPadBeams, false>(g);
+}
+
+// One launch = `nsteps` consecutive Env.step calls for every agent.
+int launch_step(navsim* h, const StepIO& io, cudaStream_t s, bool scripted, uint64_t action_seed, int nsteps) {
+  if (nsteps < 1) return NAVSIM_OK;
+  const size_t smem = step_smem_bytes(h);
+  const int g = lanes_of(h);
+  const int apb = kBlock / g;
+  const dim3 grid((h->c.N + apb - 1) / apb), block(kBlock);
+  const uint32_t script_step = scripted ? h->script_step : 0u;
+  if (scripted) h->script_step += (uint32_t)nsteps;
+  if (variant_of(h) == 2) {
+    navsim_step_anybeam_kernel<<<grid, block, smem, s>>>(h->c, h->st, h->d_map, h->d_rt, io, h->d_stats, action_seed,
+                                                         script_step, nsteps, scripted ? 1 : 0);
+  } else {
+    step_kernel_of(h, scripted)<<<grid, block, smem, s>>>(h->c, h->st, h->d_map, h->d_rt, io, h->d_stats, action_seed,
+                                                          script_step, nsteps);
+  }
   h->launches++;
   CUDA_TRY(cudaGetLastError());
   return NAVSIM_OK;
+}
+
+StepIO make_io(const float* act, float* obs, float* rew, uint8_t* done, uint8_t* arrive, uint8_t* trunc,
+               long long obs_stride, long long vec_stride) {
+  StepIO io;
+  io.act = act; io.obs = obs; io.rew = rew; io.done = done; io.arrive = arrive; io.trunc = trunc;
+  io.obs_stride = obs_stride; io.vec_stride = vec_stride;
+  return io;
 }
 
 }  // namespace
@@ -569,8 +881,10 @@ int navsim_create(navsim_t** out, const navsim_cfg* cfg) {
   c.sx = cfg->start_x; c.sy = cfg->start_y; c.sth = cfg->start_theta;
   memcpy(c.reset_rects, cfg->reset_rects, sizeof c.reset_rects);
   memcpy(c.respawn_rects, cfg->respawn_rects, sizeof c.respawn_rects);
-  // a CTA of 64 keeps >= 128 CTAs in flight at N = 8192 (148 SMs); big batches use 128
-  h->block = (c.N >= 148 * 128 * 2) ? 128 : 64;
+  c.inv_diag = (float)(1.0 / cfg->diag_norm);
+  for (int i = 0; i < NAVSIM_LIDAR_FEATS; ++i) c.pick[i] = (int)((double)(i * cfg->num_beams) / 10.0);  // :293
+  c.rt_R = 0; c.rt_W = 1;
+  h->lanes = pick_lanes(c.N, cfg->lanes_per_agent);
   const size_t N = (size_t)c.N;
   // one slab for the SoA state: 6 doubles, 5 floats, 1 int32, 1 uint32 per agent
   double* dslab = nullptr;
@@ -617,6 +931,7 @@ int navsim_destroy(navsim_t* h) {
   if (h->st.x) cudaFree(h->st.x);
   if (h->st.pa0) cudaFree(h->st.pa0);
   if (h->d_map) cudaFree(h->d_map);
+  if (h->d_rt) cudaFree(h->d_rt);
   if (h->d_stats) cudaFree(h->d_stats);
   if (h->h_act) cudaFreeHost(h->h_act);
   if (h->h_obs) cudaFreeHost(h->h_obs);
@@ -636,43 +951,85 @@ int navsim_set_map(navsim_t* h, const double* seg_host, int32_t num_segments, in
   if (num_segments < 1) return fail(NAVSIM_EINVAL, "a map needs at least one segment");
   const int B = h->c.B;
   const size_t bytes = map_bytes_of(B, num_segments);
-  if (16 + bytes + (size_t)h->block * kObsPad * sizeof(float) > 200 * 1024)
+  if (16 + bytes + (size_t)kBlock * kObsPad * sizeof(float) > 200 * 1024)
     return fail(NAVSIM_EINVAL, "map does not fit in shared memory");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const int closed = (flags & NAVSIM_MAP_CLOSED_BOXES) ? 1 : 0;
   float* host = new (std::nothrow) float[bytes / sizeof(float)]();
   if (!host) return fail(NAVSIM_ENOMEM, "host allocation failed");
-  for (int k = 0; k < num_segments; ++k) nv_pack_segment(seg_host + 4 * k, h->cfg.lidar_max, host + NV_SEG_FLOATS * k);
+  float* h_bc = host + NV_SEG_FLOATS * num_segments;
+  float* h_bs = h_bc + B;
+  float* h_start = h_bs + B;
+  double xmax = 0.0;  // map half-extent, for the bearing table
+  for (int k = 0; k < num_segments; ++k) {
+    nv_pack_segment(seg_host + 4 * k, h->cfg.lidar_max, host + NV_SEG_FLOATS * k);
+    for (int j = 0; j < 4; ++j) xmax = fmax(xmax, fabs(seg_host[4 * k + j]));
+  }
   // beam direction table, gazebo.xacro:111-114: B samples over [fov_min, fov_max] inclusive
   for (int i = 0; i < B; ++i) {
     const double a = (B > 1) ? h->cfg.fov_min + (double)i * ((h->cfg.fov_max - h->cfg.fov_min) / (double)(B - 1))
                              : 0.5 * (h->cfg.fov_min + h->cfg.fov_max);
     double sn, cs;
     nv_sincos(a, &sn, &cs);
-    host[NV_SEG_FLOATS * num_segments + i] = (float)cs;
-    host[NV_SEG_FLOATS * num_segments + B + i] = (float)sn;
+    h_bc[i] = (float)cs;
+    h_bs[i] = (float)sn;
+  }
+  // LaserScan of the spawn pose (Env.reset always puts the robot there): the host build of the
+  // physics header rounds exactly like the device build, so these are the ranges the kernel
+  // would cast, sanitised as getState does (:193-194).
+  {
+    double sn, cs;
+    nv_sincos(h->cfg.start_theta, &sn, &cs);
+    const float ox = (float)(h->cfg.start_x + h->cfg.lidar_offset_x * cs), oy = (float)(h->cfg.start_y + h->cfg.lidar_offset_x * sn);
+    for (int i = 0; i < B; ++i) {
+      float dx, dy;
+      nv_beam_dir((float)cs, (float)sn, h_bc[i], h_bs[i], &dx, &dy);
+      const float r = nv_range_from_q(nv_beam_q(ox, oy, dx, dy, host, num_segments, closed), (float)h->cfg.lidar_min,
+                                      (float)h->cfg.lidar_max);
+      h_start[i] = (r == NV_INF_F) ? 3.5f : r;
+    }
   }
   if (h->d_map) { cudaFree(h->d_map); h->d_map = nullptr; }
   cudaError_t e = cudaMalloc(&h->d_map, bytes);
   if (e == cudaSuccess) e = cudaMemcpy(h->d_map, host, bytes, cudaMemcpyHostToDevice);
   delete[] host;
   if (e != cudaSuccess) return fail(NAVSIM_ECUDA, std::string("set_map: ") + cudaGetErrorString(e));
+  // bearing table over every goal offset the map allows (capped; larger offsets are computed)
+  {
+    const double reach = fmax(fabs(h->cfg.goal_lo), fabs(h->cfg.goal_hi)) + fmax(xmax, fmax(fabs(h->cfg.start_x), fabs(h->cfg.start_y)));
+    int R = (int)ceil(reach * 10.0) + 2;
+    if (R > 256) R = 256;
+    if (R < 8) R = 8;
+    const int W = 2 * R + 1;
+    uint16_t* tab = new (std::nothrow) uint16_t[(size_t)W * W];
+    if (!tab) return fail(NAVSIM_ENOMEM, "host allocation failed");
+    for (int ny = -R; ny <= R; ++ny)
+      for (int nx = -R; nx <= R; ++nx) tab[(size_t)(ny + R) * W + (nx + R)] = (uint16_t)nv_rel_theta_centideg(nx, ny);
+    if (h->d_rt) { cudaFree(h->d_rt); h->d_rt = nullptr; }
+    e = cudaMalloc(&h->d_rt, (size_t)W * W * sizeof(uint16_t));
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_rt, tab, (size_t)W * W * sizeof(uint16_t), cudaMemcpyHostToDevice);
+    delete[] tab;
+    if (e != cudaSuccess) return fail(NAVSIM_ECUDA, std::string("set_map: ") + cudaGetErrorString(e));
+    h->c.rt_R = R;
+    h->c.rt_W = W;
+  }
   h->S = num_segments;
   h->c.S = num_segments;
-  h->c.closed_boxes = (flags & NAVSIM_MAP_CLOSED_BOXES) ? 1 : 0;
-  const size_t smem = smem_bytes(h);
-  CUDA_TRY(cudaFuncSetAttribute(navsim_step_kernel<false, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CUDA_TRY(cudaFuncSetAttribute(navsim_step_kernel<true, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CUDA_TRY(cudaFuncSetAttribute(navsim_step_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CUDA_TRY(cudaFuncSetAttribute(navsim_step_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CUDA_TRY(cudaFuncSetAttribute(navsim_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CUDA_TRY(cudaFuncSetAttribute(navsim_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  h->c.closed_boxes = closed;
+  const int smem = (int)step_smem_bytes(h);
+  CUDA_TRY(cudaFuncSetAttribute(step_kernel_of(h, false), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CUDA_TRY(cudaFuncSetAttribute(step_kernel_of(h, true), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CUDA_TRY(cudaFuncSetAttribute(navsim_step_anybeam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int aux = (int)aux_smem_bytes(h);
+  CUDA_TRY(cudaFuncSetAttribute(navsim_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, aux));
+  CUDA_TRY(cudaFuncSetAttribute(navsim_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, aux));
   return NAVSIM_OK;
 }
 
 int navsim_reset(navsim_t* h, const uint8_t* mask_dev, float* obs_dev, void* stream) {
   if (int rc = check_ready(h)) return rc;
-  navsim_reset_kernel<<<grid_of(h), h->block, smem_bytes(h), (cudaStream_t)stream>>>(h->c, h->st, h->d_map, mask_dev,
-                                                                                    obs_dev);
+  navsim_reset_kernel<<<aux_grid_of(h), kBlock, aux_smem_bytes(h), (cudaStream_t)stream>>>(h->c, h->st, h->d_map, h->d_rt,
+                                                                                         mask_dev, obs_dev);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
   return NAVSIM_OK;
@@ -682,18 +1039,25 @@ int navsim_step(navsim_t* h, const float* act_dev, float* obs_dev, float* rew_de
                 uint8_t* arrive_dev, uint8_t* trunc_dev, void* stream) {
   if (int rc = check_ready(h)) return rc;
   if (!act_dev || !obs_dev || !rew_dev || !done_dev || !arrive_dev) return fail(NAVSIM_EINVAL, "null buffer");
-  return launch_step(h, act_dev, obs_dev, rew_dev, done_dev, arrive_dev, trunc_dev, (cudaStream_t)stream, false, 0);
+  return launch_step(h, make_io(act_dev, obs_dev, rew_dev, done_dev, arrive_dev, trunc_dev, 0, 0), (cudaStream_t)stream,
+                     false, 0, 1);
 }
 
 int navsim_step_scripted(navsim_t* h, int32_t num_steps, uint64_t action_seed, float* obs_dev, float* rew_dev,
                          uint8_t* done_dev, uint8_t* arrive_dev, void* stream) {
   if (int rc = check_ready(h)) return rc;
   if (!obs_dev || !rew_dev || !done_dev || !arrive_dev) return fail(NAVSIM_EINVAL, "null buffer");
-  for (int t = 0; t < num_steps; ++t)
-    if (int rc = launch_step(h, nullptr, obs_dev, rew_dev, done_dev, arrive_dev, nullptr, (cudaStream_t)stream, true,
-                             action_seed))
-      return rc;
-  return NAVSIM_OK;
+  return launch_step(h, make_io(nullptr, obs_dev, rew_dev, done_dev, arrive_dev, nullptr, 0, 0), (cudaStream_t)stream, true,
+                     action_seed, num_steps);
+}
+
+int navsim_rollout_scripted(navsim_t* h, int32_t num_steps, uint64_t action_seed, float* obs_dev, float* rew_dev,
+                            uint8_t* done_dev, uint8_t* arrive_dev, uint8_t* trunc_dev, void* stream) {
+  if (int rc = check_ready(h)) return rc;
+  if (!obs_dev || !rew_dev || !done_dev || !arrive_dev) return fail(NAVSIM_EINVAL, "null buffer");
+  const long long N = h->c.N;
+  return launch_step(h, make_io(nullptr, obs_dev, rew_dev, done_dev, arrive_dev, trunc_dev, N * NAVSIM_OBS_DIM, N),
+                     (cudaStream_t)stream, true, action_seed, num_steps);
 }
 
 int navsim_reset_host(navsim_t* h, const uint8_t* mask_host, float* obs_host) {
@@ -727,7 +1091,8 @@ int navsim_step_host(navsim_t* h, const float* act_host, float* obs_host, float*
   cudaStream_t s = h->own_stream;
   memcpy(h->h_act, act_host, N * 2 * sizeof(float));
   CUDA_TRY(cudaMemcpyAsync(h->d_act, h->h_act, N * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
-  if (int rc = launch_step(h, h->d_act, h->d_obs, h->d_rew, h->d_flags, h->d_flags + N, h->d_flags + 2 * N, s, false, 0))
+  if (int rc = launch_step(h, make_io(h->d_act, h->d_obs, h->d_rew, h->d_flags, h->d_flags + N, h->d_flags + 2 * N, 0, 0), s,
+                           false, 0, 1))
     return rc;
   CUDA_TRY(cudaMemcpyAsync(h->h_obs, h->d_obs, N * NAVSIM_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(h->h_rew, h->d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -744,7 +1109,7 @@ int navsim_step_host(navsim_t* h, const float* act_host, float* obs_host, float*
 int navsim_scan(navsim_t* h, double* ranges_dev, void* stream) {
   if (int rc = check_ready(h)) return rc;
   if (!ranges_dev) return fail(NAVSIM_EINVAL, "null buffer");
-  navsim_scan_kernel<<<grid_of(h), h->block, smem_bytes(h), (cudaStream_t)stream>>>(h->c, h->st, h->d_map, ranges_dev);
+  navsim_scan_kernel<<<aux_grid_of(h), kBlock, aux_smem_bytes(h), (cudaStream_t)stream>>>(h->c, h->st, h->d_map, ranges_dev);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
   return NAVSIM_OK;
@@ -804,6 +1169,8 @@ int navsim_get_stats(navsim_t* h, navsim_stats* out, int32_t clear) {
 }
 
 int navsim_num_agents(const navsim_t* h) { return h ? h->c.N : 0; }
+
+int navsim_lanes_per_agent(const navsim_t* h) { return h ? lanes_of(h) : 0; }
 
 int64_t navsim_launch_count(const navsim_t* h) { return h ? h->launches : 0; }
 

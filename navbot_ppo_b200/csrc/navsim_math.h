@@ -124,9 +124,53 @@ NV_HD double nv_round_scaled(double x, double scale) {
   else if (d == -0.5 && lo < 0.0) n -= 1.0;  // true value just below the tie
   return n;
 }
+// n / scale for an integer-valued n and scale in {10, 100}.  For |n| < 2^26 one Markstein
+// correction step on n * RN(1/scale) yields the correctly rounded quotient (checked against
+// the division for EVERY such n by tests/test_math_host.py); anything larger divides.  Costs
+// three fp64 instructions instead of a division subroutine.
+NV_HD double nv_div_scale(double n, double scale, double inv_scale) {
+  if (!(fabs(n) < 67108864.0)) return n / scale;
+  double q = n * inv_scale;
+  double r = fma(-q, scale, n);
+  double q1 = fma(r, inv_scale, q);
+  return (n == 0.0) ? n : q1;  // keep the sign of a zero
+}
 NV_HD double nv_pyround0(double x) { return rint(x); }
-NV_HD double nv_pyround1(double x) { return nv_round_scaled(x, 10.0) / 10.0; }
-NV_HD double nv_pyround2(double x) { return nv_round_scaled(x, 100.0) / 100.0; }
+NV_HD double nv_pyround1(double x) { return nv_div_scale(nv_round_scaled(x, 10.0), 10.0, 0.1); }
+NV_HD double nv_pyround2(double x) { return nv_div_scale(nv_round_scaled(x, 100.0), 100.0, 0.01); }
+
+// ---------------------------------------------------------------------------------------
+// Env.getOdometry's goal bearing (environment_new.py:149-169) as a function of the two goal
+// offsets in tenths of a metre: rel_dis_x = round(goal.x - x, 1) = RN(nx / 10) and likewise
+// ny, so rel_theta = round(degrees(theta), 2) depends on the integers (nx, ny) alone.
+// Returns rel_theta in hundredths of a degree (0 .. 36000).  The simulator tabulates this
+// function once per map (host build of this header) and the step kernel looks it up.
+// ---------------------------------------------------------------------------------------
+NV_HD int nv_rel_theta_centideg(int nx, int ny) {
+  const double rx = nv_div_scale((double)nx, 10.0, 0.1), ry = nv_div_scale((double)ny, 10.0, 0.1);
+  double theta;
+  if (nx > 0 && ny > 0) theta = nv_atan(ry / rx);                        // :153
+  else if (nx > 0 && ny < 0) theta = 2.0 * NV_PI + nv_atan(ry / rx);     // :155
+  else if (nx < 0 && ny < 0) theta = NV_PI + nv_atan(ry / rx);           // :157
+  else if (nx < 0 && ny > 0) theta = NV_PI + nv_atan(ry / rx);           // :159
+  else if (nx == 0 && ny > 0) theta = 0.5 * NV_PI;                       // :161
+  else if (nx == 0 && ny < 0) theta = 1.5 * NV_PI;                       // :163
+  else if (ny == 0 && nx > 0) theta = 0.0;                               // :165
+  else theta = NV_PI;                                                    // :167
+  return (int)nv_round_scaled(theta * NV_RAD2DEG, 100.0);                // :169
+}
+
+// diff_angle = yaw - rel_theta wrapped to [-180, 180] and rounded to 0.01 (:170-176), in
+// hundredths of a degree.  yaw is a whole number of degrees and rel_theta = RN(m / 100), so
+// the floating-point difference lies within 1e-13 of the exact hundredth (100 yaw - m) / 100,
+// every round(., 2) in :172-176 lands on that hundredth, and the comparisons against 0 and
+// +-180 can only tie when the hundredth is the bound itself, where the difference is exact.
+NV_HD int nv_diff_angle_centideg(int yaw_deg, int rel_theta_centideg) {
+  int k = 100 * yaw_deg - rel_theta_centideg;
+  if (k < -18000) k += 36000;       // :174
+  else if (k > 18000) k -= 36000;   // :176
+  return k;
+}
 
 // ---------------------------------------------------------------------------------------
 // Philox4x32-10 counter RNG.  Goal sampling draws are keyed (seed, global agent id) and
@@ -172,17 +216,28 @@ NV_HD void nv_goal_uniforms(uint64_t seed, uint64_t agent, uint32_t draw, double
 // algebraically ds = v dt, dth = w dt, which is what is integrated here in midpoint form
 // (:157-163).  Heading is kept wrapped to (-pi, pi] so the trig argument stays small.
 // ---------------------------------------------------------------------------------------
-NV_HD void nv_drive(double* x, double* y, double* th, double v, double w, double dt) {
-  double ds = v * dt;
+// Split in two so a caller can evaluate the two sines/cosines a step needs (midpoint heading
+// for the motion, new heading for the sensor) side by side: nv_drive_plan gives the
+// arguments, nv_drive_apply moves the pose.
+NV_HD void nv_drive_plan(double th, double v, double w, double dt, double* ds, double* th_mid, double* th_new) {
+  *ds = v * dt;
   double dth = w * dt;
-  double s, c;
-  nv_sincos(*th + dth / 2.0, &s, &c);
-  *x = *x + ds * c;
-  *y = *y + ds * s;
-  double t = *th + dth;
+  *th_mid = th + dth / 2.0;
+  double t = th + dth;
   if (t > NV_PI) t = t - NV_TWO_PI;
   else if (t <= -NV_PI) t = t + NV_TWO_PI;
-  *th = t;
+  *th_new = t;
+}
+NV_HD void nv_drive_apply(double* x, double* y, double ds, double s_mid, double c_mid) {
+  *x = *x + ds * c_mid;
+  *y = *y + ds * s_mid;
+}
+NV_HD void nv_drive(double* x, double* y, double* th, double v, double w, double dt) {
+  double ds, th_mid, th_new, s, c;
+  nv_drive_plan(*th, v, w, dt, &ds, &th_mid, &th_new);
+  nv_sincos(th_mid, &s, &c);
+  nv_drive_apply(x, y, ds, s, c);
+  *th = th_new;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -230,15 +285,17 @@ NV_HD void nv_pack_segment(const double* xyxy, double rmax, float* out) {
 
 typedef struct nv_seg_view { float wx, wy, ex, ey, inv_tn; } nv_seg_view;
 
-// Per-segment setup for a sensor origin.  Returns 0 when no beam can see the wall.
+// Per-segment setup for a sensor origin.  Returns 0 when no beam can see the wall.  The three
+// culls are independent predicates of (wall, origin), so their order is free: the cheapest and
+// most selective come first (half of a box's edges face away; most others are out of range).
 NV_HD int nv_seg_setup(const float* sg, float ox, float oy, int closed_boxes, nv_seg_view* v) {
-  float cx = sg[4] - ox, cy = sg[5] - oy;
-  if (fmaf(cx, cx, cy * cy) > sg[6]) return 0;
   float wx = sg[0] - ox, wy = sg[1] - oy, ex = sg[2], ey = sg[3];
   float tn = fmaf(wx, ey, -(wy * ex));
   if (closed_boxes && tn >= 0.0f) return 0;
   if (tn < 0.0f) { tn = -tn; wx = -wx; wy = -wy; ex = -ex; ey = -ey; }
   if (tn > sg[7] || tn == 0.0f) return 0;
+  float cx = sg[4] - ox, cy = sg[5] - oy;
+  if (fmaf(cx, cx, cy * cy) > sg[6]) return 0;
   v->wx = wx; v->wy = wy; v->ex = ex; v->ey = ey;
   v->inv_tn = 1.0f / tn;
   return 1;

@@ -32,7 +32,7 @@ class VecEnv:
     def __init__(self, num_envs: int, map: str | np.ndarray = "stage_1", device: int | str | torch.device = 0,
                  seed: int = 0, max_episode_steps: int = 500, auto_reset: bool = True, is_training: bool = True,
                  num_beams: int = 10, agent_id_offset: int = 0, cfg: _capi.NavsimCfg | None = None,
-                 closed_boxes: bool = True):
+                 closed_boxes: bool = True, lanes_per_agent: int = 0):
         self._h = ctypes.c_void_p()
         L = _capi.lib()
         dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
@@ -46,6 +46,7 @@ class VecEnv:
             cfg.auto_reset = 1 if auto_reset else 0
             cfg.num_beams = num_beams
             cfg.agent_id_offset = agent_id_offset
+            cfg.lanes_per_agent = lanes_per_agent   # 0: chosen from N by the library
             # environment_new.py:44-47
             cfg.arrive_threshold = 0.2 if is_training else 0.4
         cfg.device = dev.index if dev.index is not None else torch.cuda.current_device()
@@ -111,6 +112,23 @@ class VecEnv:
                                                      _stream_ptr(self.device)))
         return self.obs, self.rew, self.done, self.arrive
 
+    def rollout_scripted(self, num_steps: int, action_seed: int = 0, out: dict | None = None):
+        """`num_steps` scripted steps in ONE launch, outputs in the rollout layout [H, N, .]
+        (navsim_rollout_scripted).  Returns dict(obs, rew, done, arrive, trunc)."""
+        n, d = self.num_envs, self.device
+        if out is None:
+            out = dict(obs=torch.empty((num_steps, n, self.obs_dim), dtype=torch.float32, device=d),
+                       rew=torch.empty((num_steps, n), dtype=torch.float32, device=d),
+                       done=torch.empty((num_steps, n), dtype=torch.uint8, device=d),
+                       arrive=torch.empty((num_steps, n), dtype=torch.uint8, device=d),
+                       trunc=torch.empty((num_steps, n), dtype=torch.uint8, device=d))
+        assert out["obs"].shape[0] >= num_steps
+        _capi.check(_capi.lib().navsim_rollout_scripted(self._h, num_steps, action_seed, out["obs"].data_ptr(),
+                                                        out["rew"].data_ptr(), out["done"].data_ptr(),
+                                                        out["arrive"].data_ptr(), out["trunc"].data_ptr(),
+                                                        _stream_ptr(self.device)))
+        return out
+
     def scan(self) -> torch.Tensor:
         out = torch.empty((self.num_envs, int(self.cfg.num_beams)), dtype=torch.float64, device=self.device)
         _capi.check(_capi.lib().navsim_scan(self._h, out.data_ptr(), _stream_ptr(self.device)))
@@ -149,6 +167,11 @@ class VecEnv:
         s = _capi.NavsimStats()
         _capi.check(_capi.lib().navsim_get_stats(self._h, ctypes.byref(s), 1 if clear else 0))
         return s
+
+    @property
+    def lanes_per_agent(self) -> int:
+        """GPU lanes cooperating on one agent's step (chosen by the library from N unless requested)."""
+        return int(_capi.lib().navsim_lanes_per_agent(self._h))
 
     @property
     def launch_count(self) -> int:

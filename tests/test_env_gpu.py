@@ -274,3 +274,105 @@ def test_error_paths():
                                  env.arrive.data_ptr(), None, None)
     assert rc == -22 and b"set_map" in _capi.lib().nav_last_error()
     _capi.lib().navsim_destroy(h)
+
+
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16, 32])
+def test_every_lane_split_is_bit_identical_and_matches_oracle(lanes):
+    """The step kernel spreads one agent's wall sweep over G lanes (G picked from N); every G
+    must give the oracle's flags/poses and the same observation bits as G = 1."""
+    n = 777  # not a multiple of any agents-per-CTA count: exercises the shadow lanes
+    cfg = _capi.default_cfg(n)
+    cfg.seed = 21
+    cfg.max_episode_steps = 30
+    cfg.lanes_per_agent = lanes
+    seg = maps.get_map("stage_2")
+    env = _vec_from_cfg(cfg, seg)
+    cfg1 = _capi.default_cfg(n)
+    cfg1.seed, cfg1.max_episode_steps, cfg1.lanes_per_agent = 21, 30, 1
+    base = _vec_from_cfg(cfg1, seg)
+    sim = binding.OracleSim(cfg, seg, nthreads=8)
+    o0 = env.reset().cpu().numpy()
+    np.testing.assert_allclose(o0, sim.reset(), atol=OBS_ATOL, rtol=0)
+    np.testing.assert_array_equal(o0, base.reset().cpu().numpy())
+    for t in range(80):
+        act = binding.scripted_actions(13, 0, t, n)
+        if t % 3 == 0:
+            act[::2, 0] = 1.0
+        o_ref, r_ref, d_ref, a_ref, tr_ref = sim.step(act)
+        ad = torch.from_numpy(act).cuda()
+        obs, rew, done, arrive = env.step(ad)
+        ob, rb, db, ab = base.step(ad)
+        assert torch.equal(obs, ob) and torch.equal(rew, rb) and torch.equal(done, db) and torch.equal(arrive, ab)
+        np.testing.assert_array_equal(done.cpu().numpy(), d_ref, err_msg=f"done t={t}")
+        np.testing.assert_array_equal(arrive.cpu().numpy(), a_ref, err_msg=f"arrive t={t}")
+        np.testing.assert_array_equal(env.trunc.cpu().numpy(), tr_ref, err_msg=f"trunc t={t}")
+        np.testing.assert_allclose(obs.cpu().numpy(), o_ref, atol=OBS_ATOL, rtol=0, err_msg=f"obs t={t}")
+        np.testing.assert_allclose(rew.cpu().numpy(), r_ref, atol=REW_ATOL, rtol=0, err_msg=f"rew t={t}")
+    for k, f in (("x", _capi.F_X), ("y", _capi.F_Y), ("th", _capi.F_THETA), ("gx", _capi.F_GOAL_X), ("gy", _capi.F_GOAL_Y)):
+        np.testing.assert_array_equal(env.get_state(f), sim.arr[k], err_msg=k)
+    s = env.stats()
+    assert s.episodes == s.successes + s.collisions + s.timeouts > 0 and s.steps == 80 * n
+
+
+@pytest.mark.parametrize("n,lanes", [(8192, 0), (1500, 4), (300, 1)])
+def test_fused_rollout_launch_equals_step_by_step(n, lanes):
+    """navsim_rollout_scripted: H steps in ONE launch, state in registers, outputs in the
+    [H, N, .] rollout layout == H single-step launches == the oracle."""
+    H = 48
+    cfg = _capi.default_cfg(n)
+    cfg.seed, cfg.max_episode_steps, cfg.lanes_per_agent = 4, 20, lanes
+    seg = maps.get_map("stage_1")
+    fused, single = _vec_from_cfg(cfg, seg), _vec_from_cfg(cfg, seg)
+    sim = binding.OracleSim(cfg, seg, nthreads=8)
+    fused.reset(); single.reset(); sim.reset()
+    out = fused.rollout_scripted(H, action_seed=77)
+    torch.cuda.synchronize()
+    for t in range(H):
+        o_ref, r_ref, d_ref, a_ref, tr_ref = sim.step(binding.scripted_actions(77, 0, t, n))
+        obs, rew, done, arrive = single.step_scripted(1, action_seed=77)
+        assert torch.equal(out["obs"][t], obs) and torch.equal(out["rew"][t], rew), t
+        assert torch.equal(out["done"][t], done) and torch.equal(out["arrive"][t], arrive), t
+        np.testing.assert_array_equal(out["done"][t].cpu().numpy(), d_ref)
+        np.testing.assert_array_equal(out["arrive"][t].cpu().numpy(), a_ref)
+        np.testing.assert_array_equal(out["trunc"][t].cpu().numpy(), tr_ref)
+        np.testing.assert_allclose(out["obs"][t].cpu().numpy(), o_ref, atol=OBS_ATOL, rtol=0)
+        np.testing.assert_allclose(out["rew"][t].cpu().numpy(), r_ref, atol=REW_ATOL, rtol=0)
+    for f in (_capi.F_X, _capi.F_Y, _capi.F_THETA, _capi.F_GOAL_X, _capi.F_DRAWS, _capi.F_STEPS, _capi.F_EP_RETURN,
+              _capi.F_EP_PATH):
+        np.testing.assert_array_equal(fused.get_state(f), single.get_state(f))
+    np.testing.assert_array_equal(fused.get_state(_capi.F_X), sim.arr["x"])
+    assert fused.stats().episodes == single.stats().episodes > 0
+    # a second fused call continues the same action stream
+    out2 = fused.rollout_scripted(3, action_seed=77)
+    for t in range(3):
+        obs, *_ = single.step_scripted(1, action_seed=77)
+        assert torch.equal(out2["obs"][t], obs)
+
+
+@pytest.mark.parametrize("beams,lanes", [(12, 0), (18, 8), (24, 1), (36, 32), (48, 0), (360, 0)])
+def test_beam_sweep_multi_step_matches_oracle(beams, lanes):
+    """BASELINE configs[4] beam sweep on a house-like map (52 boxes = 208 walls): the padded
+    register variant (B <= 36) and the warp-per-agent variant (B > 36) over many steps,
+    including the lidar subsampling idx_i = int(i * L / 10) (environment_new.py:292-294)."""
+    n = 600
+    cfg = _capi.default_cfg(n)
+    cfg.num_beams, cfg.seed, cfg.max_episode_steps, cfg.lanes_per_agent = beams, 8, 25, lanes
+    cfg.goal_lo, cfg.goal_hi = -6.0, 6.0
+    seg = maps.synthetic_map(52, seed=5)
+    env = _vec_from_cfg(cfg, seg)
+    sim = binding.OracleSim(cfg, seg, nthreads=8)
+    np.testing.assert_allclose(env.reset().cpu().numpy(), sim.reset(), atol=OBS_ATOL, rtol=0)
+    nd = 0
+    for t in range(60):
+        act = binding.scripted_actions(6, 0, t, n)
+        act[:, 0] = np.maximum(act[:, 0], 0.7)
+        o_ref, r_ref, d_ref, a_ref, tr_ref = sim.step(act)
+        obs, rew, done, arrive = env.step(torch.from_numpy(act).cuda())
+        np.testing.assert_array_equal(done.cpu().numpy(), d_ref, err_msg=f"done t={t}")
+        np.testing.assert_array_equal(arrive.cpu().numpy(), a_ref, err_msg=f"arrive t={t}")
+        np.testing.assert_allclose(obs.cpu().numpy(), o_ref, atol=OBS_ATOL, rtol=0, err_msg=f"obs t={t}")
+        np.testing.assert_allclose(rew.cpu().numpy(), r_ref, atol=REW_ATOL, rtol=0, err_msg=f"rew t={t}")
+        nd += int(d_ref.sum())
+    assert nd > 0
+    np.testing.assert_array_equal(env.get_state(_capi.F_X), sim.arr["x"])
+    np.testing.assert_array_equal(env.scan().cpu().numpy(), sim.scan())

@@ -236,3 +236,27 @@ def test_shared_header_raycast_against_bruteforce():
                     assert g_ == float(np.float32(g_))  # travels as float32
             checked += 1
         assert checked > 800
+
+def test_markstein_division_equals_division_for_every_small_integer():
+    """nv_div_scale (three fp64 ops instead of a division) is what nv_pyround1/2 finish with."""
+    L = binding.lib()
+    L.oracle_nv_div_scale_mismatches.argtypes = [ctypes.c_long]
+    L.oracle_nv_div_scale_mismatches.restype = ctypes.c_long
+    assert L.oracle_nv_div_scale_mismatches(1 << 26) == 0
+
+
+def test_tabulated_bearing_features_equal_reference_formula():
+    """nv_rel_theta_centideg / nv_diff_angle_centideg (the integer form the step kernel looks up)
+    against the restated Env.getOdometry on the whole +-20 m offset grid and every whole-degree yaw."""
+    L = binding.lib()
+    L.oracle_nv_bearing_mismatches.argtypes = [ctypes.c_int]
+    L.oracle_nv_bearing_mismatches.restype = ctypes.c_long
+    assert L.oracle_nv_bearing_mismatches(200) == 0
+    L.oracle_nv_rel_theta_centideg.argtypes = [ctypes.c_int, ctypes.c_int]
+    L.oracle_nv_rel_theta_centideg.restype = ctypes.c_int
+    for nx, ny, want in ((10, 10, 4500), (0, 5, 9000), (-3, 0, 18000), (0, 0, 18000), (4, 0, 0), (0, -1, 27000),
+                         (10, -10, 31500), (-10, -10, 22500), (-10, 10, 13500)):
+        assert L.oracle_nv_rel_theta_centideg(nx, ny) == want
+        rx, ry = round(nx / 10, 1), round(ny / 10, 1)
+        if rx > 0 and ry > 0:
+            assert want == round(round(math.degrees(math.atan(ry / rx)), 2) * 100)

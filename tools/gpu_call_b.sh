@@ -1,0 +1,8 @@
+#!/bin/bash
+# GPU call: parity tests of the lane-cooperative step kernel + lane sweep timings
+set -x
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_env_gpu.py -m gpu -x -q > gpurun_out/b_pytest_env.log 2>&1; echo "pytest rc=$?" >> gpurun_out/b_pytest_env.log
+timeout 600 python tools/lane_sweep.py > gpurun_out/b_lane_sweep.log 2>&1
+tail -5 gpurun_out/b_pytest_env.log
+cat gpurun_out/b_lane_sweep.log
