@@ -200,7 +200,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--agents", type=int, default=8192, help="agents per GPU (BASELINE configs[1])")
@@ -290,20 +290,30 @@ def main():
     single_launch_us = a_ev.elapsed_time(b_ev) * 1e3 / H
 
     # ---- end to end through the host-buffer entry point (navsim_step_host) ----------------
-    He = min(H, 32)
-    acts = np.random.RandomState(rank).uniform(0, 1, size=(N, 2)).astype(np.float32)
+    He = H
+    hb = env.alloc_host_buffers()                       # page-locked numpy arrays owned by the caller
+    hb["act"][:] = np.random.RandomState(rank).uniform(0, 1, size=(N, 2)).astype(np.float32)
     for _ in range(3):
-        env.step_host(acts)
+        env.step_host(hb["act"], out=hb)
     barrier()
+    e2e_steps = He * max(1, min(K, 8))
     t0 = time.perf_counter()
-    for _ in range(He * max(1, K // 4)):
-        env.step_host(acts)
+    for _ in range(e2e_steps):
+        env.step_host(hb["act"], out=hb)                # blocks until obs/reward/flags are in host memory
     torch.cuda.synchronize()
     e2e_dt = time.perf_counter() - t0
     t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * N * He * max(1, K // 4) / float(t.item())
+    e2e_value = world * N * e2e_steps / float(t.item())
+    # the same call with ordinary (pageable) numpy arrays, as a drop-in caller would pass them
+    acts_pageable = np.array(hb["act"])
+    for _ in range(3):
+        env.step_host(acts_pageable)
+    t0 = time.perf_counter()
+    for _ in range(He):
+        env.step_host(acts_pageable)
+    e2e_pageable = N * He / (time.perf_counter() - t0)
 
     # ---- PPO on top of the simulator: rollout (policy forward + sampling + env step) and the
     # ---- full training iteration (rollout + reward-to-go + 50-epoch update), SURVEY.md 8(d)
@@ -379,7 +389,9 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N * 8 * H,
                 "d2h_bytes_per_step": N * (64 + 4 + 3) * H,
-                "api": "navsim_step_host via VecEnv.step_host: host actions in, host obs/reward/flags out, every env step"},
+                "api": "navsim_step_host via VecEnv.step_host: host actions in, host obs/reward/flags out, every env step; "
+                       "caller buffers page-locked (VecEnv.alloc_host_buffers)",
+                "pageable_buffers_value": e2e_pageable},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "roofline_sweep": sweep,

@@ -99,6 +99,16 @@ int navppo_act(navppo_t* h, const float* params, const float* obs, int32_t N, do
 int navppo_evaluate(navppo_t* h, const float* params, const float* obs, const float* act, int32_t T, double var,
                     float* v, float* logp, void* stream);
 
+/* The step loop of PPO.rollout (ppo.py:505-549) for all N agents of `sim`, H steps, enqueued
+ * back to back with no host round trip: for t < H  { act[t], logp[t] = get_action(obs[t]);
+ * obs[t+1], rew[t], flags[t] = sim.step(act[t]) }.  obs[H,N,16] must hold the first
+ * observation (Env.reset) in row 0; the observation after the last step goes to next_obs[N,16].
+ * act[H,N,2], logp[H,N], rew[H,N], done/arrive/trunc[H,N] are the time-major rollout buffers.
+ * Action noise: Philox counter draw0 + t (see navppo_act). */
+int navppo_rollout(navppo_t* h, navsim_t* sim, const float* params, int32_t H, double var, uint64_t seed,
+                   int64_t agent_id_offset, uint32_t draw0, float* obs, float* next_obs, float* act, float* logp, float* rew,
+                   uint8_t* done, uint8_t* arrive, uint8_t* trunc, void* stream);
+
 /* Advantage, ppo.py:277,284, in two halves so a multi-GPU run can all-reduce the three
  * doubles in between: stats[0..2] += (sum, sum of squares, count) of A = rtg - v over T rows;
  * then adv = (A - mean) / (unbiased std + 1e-10). */

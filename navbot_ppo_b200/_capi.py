@@ -111,6 +111,7 @@ NAVPPO_SYMBOLS = {
     "navppo_forward": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "navppo_act": (ctypes.c_int, [_vp, _vp, _vp, _i32, _f64, _u64, _i64, _u32, _vp, _vp, _vp, _vp, _vp]),
     "navppo_evaluate": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _f64, _vp, _vp, _vp]),
+    "navppo_rollout": (ctypes.c_int, [_vp, _vp, _vp, _i32, _f64, _u64, _i64, _u32] + [_vp] * 9),
     "navppo_adv_stats": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp]),
     "navppo_adv_normalize": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "navppo_grad": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _f64, _vp, _vp, _vp]),

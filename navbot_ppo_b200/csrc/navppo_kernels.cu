@@ -68,32 +68,6 @@ __global__ void rtg_scan_kernel(const float* __restrict__ rew, const uint8_t* __
   }
 }
 
-// ----------------------------------------------------------------------------------------
-// Inference: thread per sample, the whole network (kernel layout) resident in shared memory
-// and read as warp-wide broadcasts.
-// ----------------------------------------------------------------------------------------
-constexpr int S_W1A = 0, S_W1BT = S_W1A + HID * OBS, S_W2A = S_W1BT + HID * OBS, S_W2BT = S_W2A + HID * X1,
-              S_B1A = S_W2BT + HID * X1, S_B2A = S_B1A + HID, S_B1B = S_B2A + HID, S_B2B = S_B1B + OBS,
-              S_HEAD = S_B2B + X1, S_TOTAL = S_HEAD + ACTOR_HEAD;  // 50290 floats = 201,160 B
-
-__device__ __forceinline__ void stage_network(float* s, const float* __restrict__ p, int head) {
-  for (int i = threadIdx.x; i < HID * OBS; i += blockDim.x) {
-    s[S_W1A + i] = p[O_W1A + i];
-    s[S_W1BT + (i % HID) * OBS + i / HID] = p[O_W1B + i];
-  }
-  for (int i = threadIdx.x; i < HID * X1; i += blockDim.x) {
-    s[S_W2A + i] = p[O_W2A + i];
-    s[S_W2BT + (i % HID) * X1 + i / HID] = p[O_W2B + i];
-  }
-  for (int i = threadIdx.x; i < HID; i += blockDim.x) {
-    s[S_B1A + i] = p[O_B1A + i];
-    s[S_B2A + i] = p[O_B2A + i];
-  }
-  if (threadIdx.x < OBS) s[S_B1B + threadIdx.x] = p[O_B1B + threadIdx.x];
-  if (threadIdx.x < X1) s[S_B2B + threadIdx.x] = p[O_B2B + threadIdx.x];
-  for (int i = threadIdx.x; i < head; i += blockDim.x) s[S_HEAD + i] = p[O_HEAD + i];
-}
-
 // One residual block for one sample: u = x + Wb lrelu(Wa x + ba) + bb, two hidden units per
 // trip for instruction-level parallelism.  Wa rows and WbT rows are IN contiguous floats.
 template <int IN>
@@ -148,42 +122,212 @@ struct InferArgs {
   const float* act_in;   // [T,2]
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(256) mlp_infer_kernel(InferArgs a) {
-  const int net = blockIdx.y;  // 0 actor, 1 critic
-  if (MODE == INFER_FORWARD && ((net == 0 && !a.mu) || (net == 1 && !a.v))) return;
-  float* s = reinterpret_cast<float*>(ppo_smem);
-  stage_network(s, a.params + (net ? NAVPPO_CRITIC_OFFSET : 0), net ? CRITIC_HEAD : ACTOR_HEAD);
-  __syncthreads();
-  for (int base = blockIdx.x * blockDim.x; base < a.T; base += gridDim.x * blockDim.x) {
-    const int i = base + threadIdx.x;
-    if (i >= a.T) continue;
-    float x1[X1], u1[OBS], u2[X1];
-    {
-      const float4* o = reinterpret_cast<const float4*>(a.obs + (size_t)i * OBS);
+// ----------------------------------------------------------------------------------------
+// Inference (NetActor / NetCritic forward + the get_action / evaluate epilogues).
+//
+// One CTA = 64 samples x 8 warps.  Lane l of every warp carries samples l and l + 32 of the
+// tile; warp w owns hidden units 32 c + 4 w + {0..3} of each 32-unit chunk c of a residual
+// block.  The weights of a chunk - 32 fc1 rows, their biases and the 32 matching fc2 columns
+// (taken straight from the canonical [out][hidden] layout) - are streamed into shared memory
+// with cp.async, double buffered, and every weight read is a warp-wide broadcast (one
+// wavefront) used for 8 FMAs.  Per-warp partial residual sums meet in shared memory; the
+// activated block output goes back to all warps through shared memory as well.
+// At rollout sizes (8192 samples = 128 CTAs) this is bound by the FP32 pipe, not by weight
+// latency.
+// ----------------------------------------------------------------------------------------
+constexpr int CF_THREADS = 256;                       // 8 warps
+constexpr int CF_WARPS = CF_THREADS / 32;
+constexpr int CF_SPT = 2;                             // samples per thread
+constexpr int CF_TILE = 32 * CF_SPT;                  // samples per CTA
+constexpr int CF_CHUNK = 4 * CF_WARPS;                // hidden units per staged chunk (32)
+constexpr int CF_NCHUNK = HID / CF_CHUNK;             // 16
+// shared memory (floats): [2 chunk buffers][partials: warps x X1 x tile][block output: X1 x tile]
+constexpr int CF_CHUNK_FLOATS = CF_CHUNK * X1 + CF_CHUNK + X1 * CF_CHUNK;   // sized for the 32-input block
+constexpr int CF_PART = 2 * CF_CHUNK_FLOATS;
+constexpr int CF_YBUF = CF_PART + CF_WARPS * X1 * CF_TILE;
+constexpr int CF_SMEM_FLOATS = CF_YBUF + X1 * CF_TILE;
+constexpr size_t CF_SMEM = (size_t)CF_SMEM_FLOATS * sizeof(float);
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// chunk image: [CF_CHUNK rows of IN][CF_CHUNK biases][IN rows of CF_CHUNK]
+template <int IN>
+__device__ __forceinline__ void stage_chunk(float* dst, const float* __restrict__ Wa, const float* __restrict__ ba,
+                                            const float* __restrict__ Wb, int c) {
+  const int tid = threadIdx.x;
+  for (int v = tid; v < CF_CHUNK * IN / 4; v += CF_THREADS) cp_async16(dst + 4 * v, Wa + (size_t)(CF_CHUNK * c) * IN + 4 * v);
+  if (tid < CF_CHUNK / 4) cp_async16(dst + CF_CHUNK * IN + 4 * tid, ba + CF_CHUNK * c + 4 * tid);
+  float* dB = dst + CF_CHUNK * IN + CF_CHUNK;
+  for (int v = tid; v < IN * (CF_CHUNK / 4); v += CF_THREADS) {
+    const int k = v / (CF_CHUNK / 4), q = v % (CF_CHUNK / 4);
+    cp_async16(dB + k * CF_CHUNK + 4 * q, Wb + (size_t)k * HID + CF_CHUNK * c + 4 * q);
+  }
+}
+
+// u[s][k] <- this warp's share of  Wb lrelu(Wa x + ba)  for its lanes' samples
+template <int IN>
+__device__ __forceinline__ void coop_resblock(float* smem, const float* __restrict__ Wa, const float* __restrict__ ba,
+                                              const float* __restrict__ Wb, int warp, const float (&x)[CF_SPT][IN],
+                                              float (&u)[CF_SPT][IN]) {
 #pragma unroll
-      for (int q = 0; q < OBS / 4; ++q) {
-        const float4 t = o[q];
-        x1[4 * q] = t.x; x1[4 * q + 1] = t.y; x1[4 * q + 2] = t.z; x1[4 * q + 3] = t.w;
+  for (int s = 0; s < CF_SPT; ++s)
+#pragma unroll
+    for (int k = 0; k < IN; ++k) u[s][k] = 0.f;
+  stage_chunk<IN>(smem, Wa, ba, Wb, 0);
+  cp_async_commit();
+#pragma unroll 1
+  for (int c = 0; c < CF_NCHUNK; ++c) {
+    if (c + 1 < CF_NCHUNK) {
+      stage_chunk<IN>(smem + ((c + 1) & 1) * CF_CHUNK_FLOATS, Wa, ba, Wb, c + 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* buf = smem + (c & 1) * CF_CHUNK_FLOATS;
+    const float* A = buf + (4 * warp) * IN;
+    const float* Bm = buf + CF_CHUNK * IN + CF_CHUNK + 4 * warp;
+    float h[CF_SPT][4];
+    {
+      const float4 b4 = *reinterpret_cast<const float4*>(buf + CF_CHUNK * IN + 4 * warp);
+#pragma unroll
+      for (int s = 0; s < CF_SPT; ++s) { h[s][0] = b4.x; h[s][1] = b4.y; h[s][2] = b4.z; h[s][3] = b4.w; }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int q = 0; q < IN / 4; ++q) {
+        const float4 w = *reinterpret_cast<const float4*>(A + r * IN + 4 * q);
+#pragma unroll
+        for (int s = 0; s < CF_SPT; ++s) {
+          h[s][r] = fmaf(w.x, x[s][4 * q], h[s][r]);
+          h[s][r] = fmaf(w.y, x[s][4 * q + 1], h[s][r]);
+          h[s][r] = fmaf(w.z, x[s][4 * q + 2], h[s][r]);
+          h[s][r] = fmaf(w.w, x[s][4 * q + 3], h[s][r]);
+        }
       }
     }
-    {
-      float x0[OBS];
 #pragma unroll
-      for (int k = 0; k < OBS; ++k) { x0[k] = x1[k]; u1[k] = x0[k] + s[S_B1B + k]; }
-      resblock_fwd<OBS>(s + S_W1A, s + S_B1A, s + S_W1BT, s + S_B1B, x0, u1, 0, HID);
+    for (int s = 0; s < CF_SPT; ++s)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) h[s][r] = lrelu(h[s][r]);
+#pragma unroll
+    for (int k = 0; k < IN; ++k) {
+      const float4 w = *reinterpret_cast<const float4*>(Bm + k * CF_CHUNK);
+#pragma unroll
+      for (int s = 0; s < CF_SPT; ++s)
+        u[s][k] = fmaf(w.x, h[s][0], fmaf(w.y, h[s][1], fmaf(w.z, h[s][2], fmaf(w.w, h[s][3], u[s][k]))));
     }
+    __syncthreads();   // the buffer is refilled two iterations later
+  }
+}
+
+// Sum the 8 warps' partials, add skip + bias, activate: every thread finishes IN / 8 outputs
+// of its two samples and publishes them in ybuf[k][sample]; returns after a CTA barrier.
+template <int IN>
+__device__ __forceinline__ void coop_block_output(float* smem, const float* __restrict__ bb, int warp, int lane,
+                                                  const float (&x)[CF_SPT][IN], const float (&u)[CF_SPT][IN],
+                                                  float (&ymine)[CF_SPT][IN / CF_WARPS]) {
+  float* part = smem + CF_PART;
+  float* ybuf = smem + CF_YBUF;
 #pragma unroll
-    for (int k = 0; k < OBS; ++k) x1[OBS + k] = lrelu(u1[k]);
+  for (int s = 0; s < CF_SPT; ++s)
 #pragma unroll
-    for (int k = 0; k < X1; ++k) u2[k] = x1[k] + s[S_B2B + k];
-    resblock_fwd<X1>(s + S_W2A, s + S_B2A, s + S_W2BT, s + S_B2B, x1, u2, 0, HID);
-    float o1 = s[S_HEAD + X1], o2 = (net == 0) ? s[S_HEAD + 2 * X1 + 1] : 0.f;
+    for (int k = 0; k < IN; ++k) part[(warp * IN + k) * CF_TILE + s * 32 + lane] = u[s][k];
+  __syncthreads();
+  constexpr int PER = IN / CF_WARPS;
 #pragma unroll
-    for (int k = 0; k < X1; ++k) {
-      const float y = lrelu(u2[k]);
-      o1 = fmaf(s[S_HEAD + k], y, o1);
-      if (net == 0) o2 = fmaf(s[S_HEAD + X1 + 1 + k], y, o2);
+  for (int s = 0; s < CF_SPT; ++s)
+#pragma unroll
+    for (int kk = 0; kk < PER; ++kk) {
+      const int k = warp * PER + kk;
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < CF_WARPS; ++w) acc += part[(w * IN + k) * CF_TILE + s * 32 + lane];
+      // select x[s][k] without dynamic register indexing
+      float xs = 0.f;
+#pragma unroll
+      for (int k2 = 0; k2 < IN; ++k2) xs = (k2 == k) ? x[s][k2] : xs;
+      const float y = lrelu(acc + (xs + __ldg(bb + k)));
+      ymine[s][kk] = y;
+      ybuf[k * CF_TILE + s * 32 + lane] = y;
+    }
+  __syncthreads();
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(CF_THREADS) mlp_infer_kernel(InferArgs a) {
+  const int net = blockIdx.y;  // 0 actor, 1 critic
+  if (MODE == INFER_FORWARD && ((net == 0 && !a.mu) || (net == 1 && !a.v))) return;
+  float* smem = reinterpret_cast<float*>(ppo_smem);
+  const float* __restrict__ p = a.params + (net ? NAVPPO_CRITIC_OFFSET : 0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int base = blockIdx.x * CF_TILE;
+  float x1[CF_SPT][X1];
+#pragma unroll
+  for (int s = 0; s < CF_SPT; ++s) {
+    const int i0 = base + s * 32 + lane;
+    const int ii = i0 < a.T ? i0 : a.T - 1;              // surplus lanes shadow the last sample
+    const float4* o = reinterpret_cast<const float4*>(a.obs + (size_t)ii * OBS);
+#pragma unroll
+    for (int q = 0; q < OBS / 4; ++q) {
+      const float4 v = __ldg(o + q);
+      x1[s][4 * q] = v.x; x1[s][4 * q + 1] = v.y; x1[s][4 * q + 2] = v.z; x1[s][4 * q + 3] = v.w;
+    }
+  }
+  {
+    float x0[CF_SPT][OBS], u1[CF_SPT][OBS], y1[CF_SPT][OBS / CF_WARPS];
+#pragma unroll
+    for (int s = 0; s < CF_SPT; ++s)
+#pragma unroll
+      for (int k = 0; k < OBS; ++k) x0[s][k] = x1[s][k];
+    coop_resblock<OBS>(smem, p + O_W1A, p + O_B1A, p + O_W1B, warp, x0, u1);
+    coop_block_output<OBS>(smem, p + O_B1B, warp, lane, x0, u1, y1);
+    const float* ybuf = smem + CF_YBUF;
+#pragma unroll
+    for (int s = 0; s < CF_SPT; ++s)
+#pragma unroll
+      for (int k = 0; k < OBS; ++k) x1[s][OBS + k] = ybuf[k * CF_TILE + s * 32 + lane];
+  }
+  float y2[CF_SPT][X1 / CF_WARPS];
+  {
+    float u2[CF_SPT][X1];
+    coop_resblock<X1>(smem, p + O_W2A, p + O_B2A, p + O_W2B, warp, x1, u2);
+    coop_block_output<X1>(smem, p + O_B2B, warp, lane, x1, u2, y2);
+  }
+  // heads: each warp contributes the 4 outputs it finished; warp 0 adds the 8 partial sums
+  float* part = smem + CF_PART;
+  constexpr int PER = X1 / CF_WARPS;
+#pragma unroll
+  for (int s = 0; s < CF_SPT; ++s) {
+    float o1 = 0.f, o2 = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < PER; ++kk) {
+      const int k = warp * PER + kk;
+      o1 = fmaf(__ldg(p + O_HEAD + k), y2[s][kk], o1);
+      if (net == 0) o2 = fmaf(__ldg(p + O_HEAD + X1 + 1 + k), y2[s][kk], o2);
+    }
+    part[(warp * 2 + 0) * CF_TILE + s * 32 + lane] = o1;
+    part[(warp * 2 + 1) * CF_TILE + s * 32 + lane] = o2;
+  }
+  __syncthreads();
+  if (warp != 0) return;
+#pragma unroll
+  for (int s = 0; s < CF_SPT; ++s) {
+    const int i = base + s * 32 + lane;
+    if (i >= a.T) continue;
+    float o1 = __ldg(p + O_HEAD + X1), o2 = (net == 0) ? __ldg(p + O_HEAD + 2 * X1 + 1) : 0.f;
+#pragma unroll
+    for (int w = 0; w < CF_WARPS; ++w) {
+      o1 += part[(w * 2 + 0) * CF_TILE + s * 32 + lane];
+      o2 += part[(w * 2 + 1) * CF_TILE + s * 32 + lane];
     }
     if (net == 1) {                      // critic: V = out(X), net_critic.py:129
       a.v[i] = o1;
@@ -611,7 +755,6 @@ namespace {
 
 constexpr int ADAM_BLOCK = 256;
 constexpr int ADAM_GRID = (NAVPPO_FLAT + ADAM_BLOCK - 1) / ADAM_BLOCK;
-constexpr size_t INFER_SMEM = (size_t)S_TOTAL * sizeof(float);
 
 int check_handle(const navppo* h) {
   if (!h) return nav_fail(NAVSIM_EINVAL, "null navppo handle");
@@ -621,13 +764,8 @@ int check_handle(const navppo* h) {
 template <int MODE>
 int launch_infer(navppo* h, const InferArgs& a, bool both_nets, cudaStream_t s) {
   if (a.T <= 0) return nav_fail(NAVSIM_EINVAL, "T must be positive");
-  // small batches (rollout): narrow CTAs so that every SM gets one; large batches: one
-  // 256-thread CTA per SM looping over its tiles
-  int block = 256;
-  if (a.T < h->sm_count * 256) block = (a.T >= h->sm_count * 128) ? 128 : 64;
-  int grid = (a.T + block - 1) / block;
-  if (grid > h->sm_count) grid = h->sm_count;
-  mlp_infer_kernel<MODE><<<dim3(grid, both_nets ? 2 : 1), block, INFER_SMEM, s>>>(a);
+  const int grid = (a.T + CF_TILE - 1) / CF_TILE;
+  mlp_infer_kernel<MODE><<<dim3(grid, both_nets ? 2 : 1), CF_THREADS, CF_SMEM, s>>>(a);
   h->launches++;
   NAV_CUDA_TRY(cudaGetLastError());
   return NAVSIM_OK;
@@ -687,9 +825,9 @@ int navppo_create(navppo_t** out, const navppo_cfg* cfg) {
       return NAVSIM_ECUDA;   // nav_last_error already set
     }
   }
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_infer_kernel<INFER_FORWARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INFER_SMEM);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_infer_kernel<INFER_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INFER_SMEM);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_infer_kernel<INFER_EVALUATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INFER_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_infer_kernel<INFER_FORWARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_infer_kernel<INFER_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_infer_kernel<INFER_EVALUATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAD_SMEM);
   if (e != cudaSuccess) {
     navppo_destroy(h);
@@ -822,6 +960,27 @@ int navppo_adam(navppo_t* h, float* params, const float* grad, float* exp_avg, f
     h->launches++;
   }
   NAV_CUDA_TRY(cudaGetLastError());
+  return NAVSIM_OK;
+}
+
+int navppo_rollout(navppo_t* h, navsim_t* sim, const float* params, int32_t H, double var, uint64_t seed,
+                   int64_t agent_id_offset, uint32_t draw0, float* obs, float* next_obs, float* act, float* logp, float* rew,
+                   uint8_t* done, uint8_t* arrive, uint8_t* trunc, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (!sim || !params || !obs || !next_obs || !act || !logp || !rew || !done || !arrive || !trunc)
+    return nav_fail(NAVSIM_EINVAL, "null buffer");
+  if (H < 1) return nav_fail(NAVSIM_EINVAL, "H must be positive");
+  const size_t N = (size_t)navsim_num_agents(sim);
+  for (int t = 0; t < H; ++t) {
+    float* o_t = obs + (size_t)t * N * OBS;
+    float* o_next = (t + 1 < H) ? obs + (size_t)(t + 1) * N * OBS : next_obs;
+    if (int rc = navppo_act(h, params, o_t, (int32_t)N, var, seed, agent_id_offset, draw0 + (uint32_t)t, nullptr,
+                            act + (size_t)t * N * 2, logp + (size_t)t * N, nullptr, stream))
+      return rc;
+    if (int rc = navsim_step(sim, act + (size_t)t * N * 2, o_next, rew + (size_t)t * N, done + (size_t)t * N,
+                             arrive + (size_t)t * N, trunc + (size_t)t * N, stream))
+      return rc;
+  }
   return NAVSIM_OK;
 }
 

@@ -714,6 +714,8 @@ struct navsim {
   int64_t launches = 0;
   uint32_t script_step = 0;
   int lanes = 1;                 // lanes per agent of the step kernel (G)
+  const void* pin_seen[2] = {nullptr, nullptr};  // last caller buffers of navsim_step_host (actions, obs)
+  bool pin_is[2] = {false, false};
 };
 
 namespace {
@@ -748,6 +750,19 @@ int pick_lanes(int n_agents, int requested) {
   int g = 32;
   while (g > 1 && (long long)n_agents * g > 32768LL) g /= 2;
   return g;
+}
+
+// Is this caller buffer page-locked?  (One driver query per new pointer; a training loop
+// passes the same buffers every step.)
+bool host_is_pinned(navsim* h, int slot, const void* p) {
+  if (h->pin_seen[slot] == p) return h->pin_is[slot];
+  cudaPointerAttributes at;
+  bool pinned = false;
+  if (cudaPointerGetAttributes(&at, p) == cudaSuccess) pinned = (at.type == cudaMemoryTypeHost);
+  else cudaGetLastError();
+  h->pin_seen[slot] = p;
+  h->pin_is[slot] = pinned;
+  return pinned;
 }
 
 int check_ready(const navsim* h) {
@@ -914,12 +929,13 @@ int navsim_create(navsim_t** out, const navsim_cfg* cfg) {
   TRY_OR_CLEAN(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   TRY_OR_CLEAN(cudaMallocHost(&h->h_act, N * 2 * sizeof(float)));
   TRY_OR_CLEAN(cudaMallocHost(&h->h_obs, N * NAVSIM_OBS_DIM * sizeof(float)));
-  TRY_OR_CLEAN(cudaMallocHost(&h->h_rew, N * sizeof(float)));
-  TRY_OR_CLEAN(cudaMallocHost(&h->h_flags, N * 3));
+  // reward + the three flag arrays share one block (one D2H copy): [N floats][3N bytes]
+  TRY_OR_CLEAN(cudaMallocHost(&h->h_rew, N * sizeof(float) + N * 3));
+  h->h_flags = reinterpret_cast<uint8_t*>(h->h_rew + N);
   TRY_OR_CLEAN(cudaMalloc(&h->d_act, N * 2 * sizeof(float)));
   TRY_OR_CLEAN(cudaMalloc(&h->d_obs, N * NAVSIM_OBS_DIM * sizeof(float)));
-  TRY_OR_CLEAN(cudaMalloc(&h->d_rew, N * sizeof(float)));
-  TRY_OR_CLEAN(cudaMalloc(&h->d_flags, N * 3));
+  TRY_OR_CLEAN(cudaMalloc(&h->d_rew, N * sizeof(float) + N * 3));
+  h->d_flags = reinterpret_cast<uint8_t*>(h->d_rew + N);
 #undef TRY_OR_CLEAN
   *out = h;
   return NAVSIM_OK;
@@ -936,11 +952,9 @@ int navsim_destroy(navsim_t* h) {
   if (h->h_act) cudaFreeHost(h->h_act);
   if (h->h_obs) cudaFreeHost(h->h_obs);
   if (h->h_rew) cudaFreeHost(h->h_rew);
-  if (h->h_flags) cudaFreeHost(h->h_flags);
   if (h->d_act) cudaFree(h->d_act);
   if (h->d_obs) cudaFree(h->d_obs);
   if (h->d_rew) cudaFree(h->d_rew);
-  if (h->d_flags) cudaFree(h->d_flags);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return NAVSIM_OK;
@@ -1089,16 +1103,23 @@ int navsim_step_host(navsim_t* h, const float* act_host, float* obs_host, float*
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   const size_t N = (size_t)h->c.N;
   cudaStream_t s = h->own_stream;
-  memcpy(h->h_act, act_host, N * 2 * sizeof(float));
-  CUDA_TRY(cudaMemcpyAsync(h->d_act, h->h_act, N * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+  // Page-locked caller buffers (cudaHostRegister / cudaMallocHost / torch pin_memory) are the
+  // DMA endpoints themselves; pageable ones go through the handle's pinned staging.
+  const bool act_pinned = host_is_pinned(h, 0, act_host), obs_pinned = host_is_pinned(h, 1, obs_host);
+  const float* act_src = act_host;
+  if (!act_pinned) {
+    memcpy(h->h_act, act_host, N * 2 * sizeof(float));
+    act_src = h->h_act;
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->d_act, act_src, N * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
   if (int rc = launch_step(h, make_io(h->d_act, h->d_obs, h->d_rew, h->d_flags, h->d_flags + N, h->d_flags + 2 * N, 0, 0), s,
                            false, 0, 1))
     return rc;
-  CUDA_TRY(cudaMemcpyAsync(h->h_obs, h->d_obs, N * NAVSIM_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(h->h_rew, h->d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(h->h_flags, h->d_flags, N * 3, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(obs_pinned ? obs_host : h->h_obs, h->d_obs, N * NAVSIM_OBS_DIM * sizeof(float),
+                           cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h->h_rew, h->d_rew, N * sizeof(float) + N * 3, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
-  memcpy(obs_host, h->h_obs, N * NAVSIM_OBS_DIM * sizeof(float));
+  if (!obs_pinned) memcpy(obs_host, h->h_obs, N * NAVSIM_OBS_DIM * sizeof(float));
   memcpy(rew_host, h->h_rew, N * sizeof(float));
   memcpy(done_host, h->h_flags, N);
   memcpy(arrive_host, h->h_flags + N, N);

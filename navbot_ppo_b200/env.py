@@ -141,14 +141,24 @@ class VecEnv:
         _capi.check(_capi.lib().navsim_reset_host(self._h, None if m is None else m.ctypes.data, obs.ctypes.data))
         return obs
 
-    def step_host(self, actions: np.ndarray):
-        a = np.ascontiguousarray(actions, np.float32).reshape(self.num_envs, 2)
+    def alloc_host_buffers(self):
+        """Page-locked host arrays for step_host(): dict(act, obs, rew, done, arrive, trunc).  With
+        these the library DMAs straight from / into the caller's memory (no staging copy)."""
         n = self.num_envs
-        obs = np.empty((n, self.obs_dim), np.float32)
-        rew = np.empty(n, np.float32)
-        done = np.empty(n, np.uint8)
-        arrive = np.empty(n, np.uint8)
-        trunc = np.empty(n, np.uint8)
+        mk = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()  # noqa: E731
+        return dict(act=mk((n, 2), torch.float32), obs=mk((n, self.obs_dim), torch.float32), rew=mk((n,), torch.float32),
+                    done=mk((n,), torch.uint8), arrive=mk((n,), torch.uint8), trunc=mk((n,), torch.uint8))
+
+    def step_host(self, actions: np.ndarray, out: dict | None = None):
+        """Env.step with HOST buffers: actions[N,2] float32 in, (obs, rew, done, arrive, trunc) numpy
+        arrays out (written into `out` when given, e.g. the arrays of alloc_host_buffers())."""
+        n = self.num_envs
+        a = actions if (isinstance(actions, np.ndarray) and actions.dtype == np.float32 and actions.flags.c_contiguous
+                        and actions.size == 2 * n) else np.ascontiguousarray(actions, np.float32).reshape(n, 2)
+        if out is None:
+            out = dict(obs=np.empty((n, self.obs_dim), np.float32), rew=np.empty(n, np.float32), done=np.empty(n, np.uint8),
+                       arrive=np.empty(n, np.uint8), trunc=np.empty(n, np.uint8))
+        obs, rew, done, arrive, trunc = out["obs"], out["rew"], out["done"], out["arrive"], out["trunc"]
         _capi.check(_capi.lib().navsim_step_host(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data,
                                                  done.ctypes.data, arrive.ctypes.data, trunc.ctypes.data))
         return obs, rew, done, arrive, trunc

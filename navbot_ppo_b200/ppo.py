@@ -316,15 +316,12 @@ class PPO:
         env.stats(clear=True)
         obs = env.reset(out=self._b_obs[0])                                      # ppo.py:486
         seed = 0 if self.seed is None else int(self.seed)
-        for t in range(H):
-            _capi.check(L.navppo_act(self._h, self.flat.data_ptr(), obs.data_ptr(), N, self.var, seed,
-                                     int(env.cfg.agent_id_offset), self._draw, None, self._b_act[t].data_ptr(),
-                                     self._b_logp[t].data_ptr(), None, sp))
-            self._draw += 1
-            nxt = self._b_obs[t + 1] if t + 1 < H else self._next_obs
-            env.step(self._b_act[t], out_obs=nxt, out_rew=self._b_rew[t], out_done=self._b_flags[0, t],
-                     out_arrive=self._b_flags[1, t], out_trunc=self._b_flags[2, t])
-            obs = nxt
+        # the step loop of ppo.py:505-549 is enqueued by the library: 2 H launches, no Python in between
+        _capi.check(L.navppo_rollout(self._h, env._h, self.flat.data_ptr(), H, self.var, seed, int(env.cfg.agent_id_offset),
+                                     self._draw, self._b_obs.data_ptr(), self._next_obs.data_ptr(), self._b_act.data_ptr(),
+                                     self._b_logp.data_ptr(), self._b_rew.data_ptr(), self._b_flags[0].data_ptr(),
+                                     self._b_flags[1].data_ptr(), self._b_flags[2].data_ptr(), sp))
+        self._draw += H
         torch.amax(self._b_flags, dim=0, out=self._b_term)                       # done | arrive | timeout, ppo.py:553
         _capi.check(L.navppo_rtg_scan(self._b_rew.data_ptr(), self._b_term.data_ptr(), None, None, float(self.gamma), 1.0,
                                       self._b_rtg.data_ptr(), H, N, sp))
