@@ -373,6 +373,30 @@ def main():
             e2.close()
             del e2, ob
 
+    # ---- the other BASELINE.json configurations, per GPU (parity-tested in tests/; shown for scale)
+    other = []
+    if not args.no_sweep:
+        for label, mp, n_c, beams in (("configs[2] stage_2 16384 agents", "stage_2", 16384, 10),
+                                      ("configs[4] house 4096 agents/GPU 10 beams", "house", 4096, 10),
+                                      ("configs[4] house 4096 agents/GPU 36 beams", "house", 4096, 36)):
+            e3 = VecEnv(n_c, map=mp, device=local, seed=0, num_beams=beams)
+            e3.reset()
+            ob = e3.rollout_scripted(H, 0)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                e3.rollout_scripted(H, 0, out=ob)
+            b.record()
+            torch.cuda.synchronize()
+            s3 = a.elapsed_time(b) * 1e-3 / (3 * H)
+            nseg = int(e3.segments.shape[0])
+            other.append({"config": label, "agents": n_c, "beams": beams, "walls": nseg, "lanes_per_agent": e3.lanes_per_agent,
+                          "us_per_env_step_batch": s3 * 1e6, "env_steps_per_s": n_c / s3,
+                          "nominal_ray_wall_tests_per_s": n_c * beams * nseg / s3})
+            e3.close()
+            del e3, ob
+
     threads = os.cpu_count() or 1
     cpu_v, cpu_steps, cpu_dt = cpu_port_throughput(N, args.cpu_seconds, threads)
     cpu1_v, _, _ = cpu_port_throughput(N, min(3.0, args.cpu_seconds), 1)
@@ -395,6 +419,7 @@ def main():
         "gpu_launches": int(launches),
         "roofline": roofline,
         "roofline_sweep": sweep,
+        "other_configs": other,
         "training": training,
         "cpu_baseline": {"value": cpu_v, "unit": "env-steps/s", "cores": threads, "kind": "port",
                          "single_core_value": cpu1_v,

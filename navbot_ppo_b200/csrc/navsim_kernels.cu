@@ -299,9 +299,16 @@ __device__ __forceinline__ float group_min(float v) {
 
 // Sweeps the walls and leaves in q[b] the largest inverse hit distance of beam b over ALL
 // walls (every lane of the group holds all of them).
+// Maps with more than kCompactWalls walls (house: 208) are swept in two phases: the lanes first
+// cull their share of the walls and append the survivors to the agent's list in shared memory
+// (a robot sees a handful of the walls of a house), then share out the survivors and cast the
+// beams.  Without the list a warp would run the beam loop for a wall whenever ANY of its lanes
+// sees it.  The list order is arbitrary (shared-memory atomics); the per-beam maximum is not.
+constexpr int kCompactWalls = 32;
+
 template <int G, int KB>
 __device__ __forceinline__ void group_sweep(const SimConst& c, const MapView& mv, float ox, float oy, float ch, float sh,
-                                            int g, float* q) {
+                                            int g, uint16_t* vis_list, int* vis_count, float* q) {
   const int B = (KB == NAVSIM_LIDAR_FEATS) ? KB : c.B;
   float dx[KB], dy[KB];
 #pragma unroll
@@ -310,12 +317,39 @@ __device__ __forceinline__ void group_sweep(const SimConst& c, const MapView& mv
     else { dx[b] = 0.f; dy[b] = 0.f; }
     q[b] = 0.0f;
   }
-  for (int k = g; k < c.S; k += G) {
-    nv_seg_view v;
-    if (!nv_seg_setup(mv.seg + NV_SEG_FLOATS * k, ox, oy, c.closed_boxes, &v)) continue;
+  if (c.S <= kCompactWalls) {
+    for (int k = g; k < c.S; k += G) {
+      nv_seg_view v;
+      if (!nv_seg_setup(mv.seg + NV_SEG_FLOATS * k, ox, oy, c.closed_boxes, &v)) continue;
 #pragma unroll
-    for (int b = 0; b < KB; ++b)
-      if (b < B) q[b] = nv_ray_q(&v, dx[b], dy[b], q[b]);
+      for (int b = 0; b < KB; ++b)
+        if (b < B) q[b] = nv_ray_q(&v, dx[b], dy[b], q[b]);
+    }
+  } else {
+    int n = 0;
+    if (G > 1) {
+      if (g == 0) *vis_count = 0;
+      __syncwarp();
+    }
+    for (int k = g; k < c.S; k += G) {
+      float wx, wy, ex, ey, tn;
+      if (nv_seg_cull(mv.seg + NV_SEG_FLOATS * k, ox, oy, c.closed_boxes, &wx, &wy, &ex, &ey, &tn)) {
+        const int pos = (G == 1) ? n++ : atomicAdd(vis_count, 1);
+        vis_list[pos] = (uint16_t)k;
+      }
+    }
+    if (G > 1) {
+      __syncwarp();
+      n = *vis_count;
+    }
+    for (int idx = g; idx < n; idx += G) {
+      nv_seg_view v;
+      nv_seg_setup(mv.seg + NV_SEG_FLOATS * (int)vis_list[idx], ox, oy, c.closed_boxes, &v);
+#pragma unroll
+      for (int b = 0; b < KB; ++b)
+        if (b < B) q[b] = nv_ray_q(&v, dx[b], dy[b], q[b]);
+    }
+    if (G > 1) __syncwarp();   // the list is rewritten next step
   }
   if (G > 1) {
 #pragma unroll
@@ -351,10 +385,13 @@ __global__ void __launch_bounds__(kBlock) navsim_step_kernel(SimConst c, SimStat
   constexpr int APB = kBlock / G;  // agents per CTA
   constexpr int APW = 32 / G;      // agents per warp
   // shared: [mbarrier 16 B][map blob, padded to 16 B][obs tile: APB x kObsPad floats]
+  //         [visible-wall counters: APB ints][visible-wall lists: APB x S uint16]   (S > kCompactWalls only)
   uint64_t* bar = reinterpret_cast<uint64_t*>(dyn_smem);
   float* s_map = reinterpret_cast<float*>(dyn_smem + 16);
   const uint32_t map_bytes = map_bytes_of(c.B, c.S);
   float* s_obs = reinterpret_cast<float*>(dyn_smem + 16 + map_bytes);
+  int* s_cnt = reinterpret_cast<int*>(s_obs + APB * kObsPad);
+  uint16_t* s_list = reinterpret_cast<uint16_t*>(s_cnt + APB);
   stage_map(s_map, g_map, map_bytes, bar);
   const MapView mv = map_view(s_map, c.B, c.S);
 
@@ -415,7 +452,7 @@ __global__ void __launch_bounds__(kBlock) navsim_step_kernel(SimConst c, SimStat
     if (t == 0) wait_map(bar);
     float q[KB];
     group_sweep<G, KB>(c, mv, (float)(a.x + c.off_x * c_new), (float)(a.y + c.off_x * s_new), (float)c_new, (float)s_new, g,
-                       q);
+                       s_list + (size_t)slot * c.S, s_cnt + slot, q);
     const int B = (KB == NAVSIM_LIDAR_FEATS) ? KB : c.B;
     const float rmin = (float)c.rmin, rmax = (float)c.rmax;
     float mn = NV_INF_F;
@@ -539,7 +576,9 @@ __global__ void __launch_bounds__(kBlock) navsim_step_anybeam_kernel(SimConst c,
   float* s_obs = reinterpret_cast<float*>(dyn_smem + 16 + map_bytes);
   stage_map(s_map, g_map, map_bytes, bar);
   const MapView mv = map_view(s_map, c.B, c.S);
+  int* s_cnt = reinterpret_cast<int*>(s_obs + APB * kObsPad);
   const int g = threadIdx.x & 31, slot = threadIdx.x >> 5;
+  uint16_t* my_list = reinterpret_cast<uint16_t*>(s_cnt + APB) + (size_t)slot * c.S;
   const int i_raw = blockIdx.x * APB + slot;
   const bool valid = i_raw < c.N;
   const int i = valid ? i_raw : c.N - 1;
@@ -576,10 +615,25 @@ __global__ void __launch_bounds__(kBlock) navsim_step_anybeam_kernel(SimConst c,
     const float ch = (float)c_new, sh = (float)s_new, rmin = (float)c.rmin, rmax = (float)c.rmax;
     float mn = NV_INF_F;
     int pickn = 0;
+    // walls this agent can see at all (same two-phase sweep as group_sweep)
+    int nvis = c.S;
+    const bool compact = c.S > kCompactWalls;
+    if (compact) {
+      if (g == 0) s_cnt[slot] = 0;
+      __syncwarp();
+      for (int k = g; k < c.S; k += 32) {
+        float wx, wy, ex, ey, tn;
+        if (nv_seg_cull(mv.seg + NV_SEG_FLOATS * k, ox, oy, c.closed_boxes, &wx, &wy, &ex, &ey, &tn))
+          my_list[atomicAdd(s_cnt + slot, 1)] = (uint16_t)k;
+      }
+      __syncwarp();
+      nvis = s_cnt[slot];
+    }
     for (int b = 0; b < c.B; ++b) {
       float dxb, dyb, q = 0.0f;
       nv_beam_dir(ch, sh, mv.bc[b], mv.bs[b], &dxb, &dyb);
-      for (int k = g; k < c.S; k += 32) {
+      for (int idx = g; idx < nvis; idx += 32) {
+        const int k = compact ? (int)my_list[idx] : idx;
         nv_seg_view v;
         if (nv_seg_setup(mv.seg + NV_SEG_FLOATS * k, ox, oy, c.closed_boxes, &v)) q = nv_ray_q(&v, dxb, dyb, q);
       }
@@ -723,10 +777,23 @@ namespace {
 // variant: 0 = 10-beam register path, 1 = padded (B <= kPadBeams), 2 = any beam count (warp per agent)
 int variant_of(const navsim* h) { return h->c.B == NAVSIM_LIDAR_FEATS ? 0 : (h->c.B <= kPadBeams ? 1 : 2); }
 
-int lanes_of(const navsim* h) { return variant_of(h) == 2 ? 32 : h->lanes; }
+// Lanes per agent in force: the request / heuristic, raised for big maps so that the per-agent
+// visible-wall lists of a CTA (agents x S x 2 bytes) stay within ~64 KB of shared memory.
+int lanes_of(const navsim* h) {
+  if (variant_of(h) == 2) return 32;
+  int g = h->lanes;
+  // measured (tools/lane_sweep.py house 10 beams, 4096 agents): with hundreds of walls and few
+  // beams the cull phase dominates and one more doubling pays
+  if (h->cfg.lanes_per_agent <= 0 && h->c.S > 64 && h->c.B <= 12 && g < 32 && (long long)h->c.N * g <= 32768) g *= 2;
+  while (g < 32 && (size_t)(kBlock / g) * (size_t)h->c.S * 2 > 65536) g *= 2;
+  return g;
+}
 
 size_t step_smem_bytes(const navsim* h) {
-  return 16 + (size_t)map_bytes_of(h->c.B, h->c.S) + (size_t)(kBlock / lanes_of(h)) * kObsPad * sizeof(float);
+  const size_t apb = (size_t)(kBlock / lanes_of(h));
+  size_t b = 16 + (size_t)map_bytes_of(h->c.B, h->c.S) + apb * kObsPad * sizeof(float);
+  if (h->c.S > kCompactWalls) b += apb * sizeof(int) + apb * (size_t)h->c.S * sizeof(uint16_t);
+  return b;
 }
 
 // reset / scan kernels: thread per agent
@@ -1030,6 +1097,11 @@ int navsim_set_map(navsim_t* h, const double* seg_host, int32_t num_segments, in
   h->S = num_segments;
   h->c.S = num_segments;
   h->c.closed_boxes = closed;
+  if (step_smem_bytes(h) > 200 * 1024 || aux_smem_bytes(h) > 200 * 1024) {
+    cudaFree(h->d_map);
+    h->d_map = nullptr;
+    return fail(NAVSIM_EINVAL, "map does not fit in shared memory");
+  }
   const int smem = (int)step_smem_bytes(h);
   CUDA_TRY(cudaFuncSetAttribute(step_kernel_of(h, false), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CUDA_TRY(cudaFuncSetAttribute(step_kernel_of(h, true), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

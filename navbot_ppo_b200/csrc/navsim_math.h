@@ -288,7 +288,10 @@ typedef struct nv_seg_view { float wx, wy, ex, ey, inv_tn; } nv_seg_view;
 // Per-segment setup for a sensor origin.  Returns 0 when no beam can see the wall.  The three
 // culls are independent predicates of (wall, origin), so their order is free: the cheapest and
 // most selective come first (half of a box's edges face away; most others are out of range).
-NV_HD int nv_seg_setup(const float* sg, float ox, float oy, int closed_boxes, nv_seg_view* v) {
+// nv_seg_cull is the visibility test alone (the step kernel uses it to compact the walls an
+// agent can see before it casts any beam); nv_seg_setup adds the reciprocal a beam test needs.
+NV_HD int nv_seg_cull(const float* sg, float ox, float oy, int closed_boxes, float* wx_o, float* wy_o, float* ex_o,
+                      float* ey_o, float* tn_o) {
   float wx = sg[0] - ox, wy = sg[1] - oy, ex = sg[2], ey = sg[3];
   float tn = fmaf(wx, ey, -(wy * ex));
   if (closed_boxes && tn >= 0.0f) return 0;
@@ -296,7 +299,13 @@ NV_HD int nv_seg_setup(const float* sg, float ox, float oy, int closed_boxes, nv
   if (tn > sg[7] || tn == 0.0f) return 0;
   float cx = sg[4] - ox, cy = sg[5] - oy;
   if (fmaf(cx, cx, cy * cy) > sg[6]) return 0;
-  v->wx = wx; v->wy = wy; v->ex = ex; v->ey = ey;
+  *wx_o = wx; *wy_o = wy; *ex_o = ex; *ey_o = ey; *tn_o = tn;
+  return 1;
+}
+
+NV_HD int nv_seg_setup(const float* sg, float ox, float oy, int closed_boxes, nv_seg_view* v) {
+  float tn;
+  if (!nv_seg_cull(sg, ox, oy, closed_boxes, &v->wx, &v->wy, &v->ex, &v->ey, &tn)) return 0;
   v->inv_tn = 1.0f / tn;
   return 1;
 }

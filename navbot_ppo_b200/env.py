@@ -49,6 +49,11 @@ class VecEnv:
             cfg.lanes_per_agent = lanes_per_agent   # 0: chosen from N by the library
             # environment_new.py:44-47
             cfg.arrive_threshold = 0.2 if is_training else 0.4
+            if isinstance(map, str) and map in maps.SPAWN:
+                cfg.start_x, cfg.start_y, cfg.start_theta = maps.SPAWN[map]
+                cfg.goal_lo, cfg.goal_hi, rects = maps.GOAL_RANGE[map]
+                if not rects:
+                    cfg.n_reset_rects = cfg.n_respawn_rects = 0
         cfg.device = dev.index if dev.index is not None else torch.cuda.current_device()
         self.cfg = cfg
         self.num_envs = int(cfg.num_agents)

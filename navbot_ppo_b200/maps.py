@@ -12,7 +12,14 @@ becomes four wall segments {x0, y0, x1, y1}.  The named maps below were compiled
            (turtlebot3_stage_2.launch:8 names a world file that is absent from the
            reference; train_world_new.world is the in-repo "added boxes" map that the goal
            rejection rectangles of environment_new.py:340-343 were written for)
+  house    models/turtlebot3_house/model.sdf     52 boxes = 208 wall segments, 15 x 10.5 m: the
+           vendored stand-in for the un-vendored aws_robomaker_small_house_world that
+           project_ppo/launch/navbot_small_house.launch:11 names (BASELINE configs[4]).
+           Robot spawn (-3, 1): the launch file's (0, 0) (navbot_small_house.launch:5-6) lies
+           0.1 m from a wall of THIS model; (-3, 1) is in the open-space family of
+           spawn_goal_sampler.py:5 and has 1.1 m clearance
 """
+
 from __future__ import annotations
 
 import math
@@ -22,6 +29,12 @@ import xml.etree.ElementTree as ET
 import numpy as np
 
 LIDAR_Z = 0.182
+
+# robot spawn pose per map (x, y, yaw): turtlebot3_stage_1.launch:3-5; house: see the docstring
+SPAWN = {"stage_1": (0.0, 0.0, 0.0), "stage_2": (0.0, 0.0, 0.0), "house": (-3.0, 1.0, 0.0)}
+# goal sampling square (environment_new.py:337) and whether the stage rejection rectangles
+# (:340-343) apply; the house has no such rectangles (goals are only used for the features)
+GOAL_RANGE = {"stage_1": (-3.6, 3.6, True), "stage_2": (-3.6, 3.6, True), "house": (-4.5, 4.5, False)}
 
 # (cx, cy, sx, sy, yaw) per collision box, yaw exactly as printed in the world file.
 _BOXES = {
@@ -40,6 +53,61 @@ _BOXES = {
         (0.0, -2.0, 2.0, 0.2, 3.14159),
         (-2.0, 0.0, 2.0, 0.2, 1.5708),
         (0.0, 2.0, 2.0, 0.2, 0.0),
+    ],
+    # models/turtlebot3_house/model.sdf: the 52 box collisions (of 100) that cross the LiDAR plane
+    "house": [
+        (-0.05, 3.1, 4.5, 0.15, -1.5708),
+        (2.299992, 5.21625, 0.267504, 0.15, 1.5708),
+        (2.300002, 2.516248, 3.3325, 0.15, 1.5708),
+        (7.122235, -0.175, 0.905529, 0.15, 0.0),
+        (5.297235, -0.175, 0.944471, 0.15, 0.0),
+        (1.96856, -0.17488, 0.812647, 0.15, 0.0),
+        (-2.231444, -0.17488, 5.78735, 0.15, 0.0),
+        (5.07752, 5.2688, 5.0, 0.15, 3.14159),
+        (1.25, 5.26876, 2.75, 0.15, 3.14159),
+        (-0.05599, 5.274994, 0.161986, 0.15, 3.14159),
+        (-2.555993, 5.275, 4.83801, 0.15, 3.14159),
+        (-6.2, 5.275, 2.75, 0.15, 3.14159),
+        (-7.500004, 1.99694, 2.29388, 0.15, -1.5708),
+        (-7.499996, 4.24694, 2.20612, 0.15, -1.5708),
+        (-7.500001, -1.78462, 4.43076, 0.15, -1.5708),
+        (-7.499992, 0.71538, 0.569241, 0.15, -1.5708),
+        (-6.325, -3.925, 2.5, 0.15, 0.0),
+        (-5.15151, -1.49625, 5.0, 0.15, 1.5708),
+        (1.125, 0.925, 2.5, 0.15, 0.0),
+        (2.300003, 0.926561, 0.146998, 0.15, -1.57091),
+        (2.29988, -0.148439, 0.203002, 0.15, -1.57091),
+        (3.59994, -0.17494, 2.75, 0.15, -4.6e-05),
+        (4.9, -2.725, 5.25, 0.15, -1.5708),
+        (6.2, -5.275, 2.75, 0.15, 0.0),
+        (7.500009, -5.05429, 0.591431, 0.15, 1.5708),
+        (7.499999, -2.429285, 4.65857, 0.15, 1.5708),
+        (7.500007, 0.50174, 1.50348, 0.15, 1.5708),
+        (7.499997, 3.25174, 3.99652, 0.15, 1.5708),
+        (-7.167111, 0.925, 0.815777, 0.15, 0.0),
+        (-5.467111, 0.925, 0.784223, 0.15, 0.0),
+        (-5.149994, 1.47884, 1.25768, 0.15, 1.5708),
+        (-5.150007, 4.93695, 0.826108, 0.15, 1.5708),
+        (-6.54397, 5.19986, 0.9, 0.01, 0.0),
+        (-6.09397, 4.99986, 0.02, 0.4, 0.0),
+        (-6.99397, 4.99986, 0.02, 0.4, 0.0),
+        (4.72359, 5.18421, 0.9, 0.01, 0.0),
+        (5.17359, 4.98421, 0.02, 0.4, 0.0),
+        (4.27359, 4.98421, 0.02, 0.4, 0.0),
+        (5.64449, 5.18412, 0.9, 0.01, 0.0),
+        (6.09449, 4.98412, 0.02, 0.4, 0.0),
+        (5.19449, 4.98412, 0.02, 0.4, 0.0),
+        (-5.237, -1.57624, 0.02, 0.45, 0.0),
+        (-5.472, -1.34124, 0.45, 0.02, 0.0),
+        (-5.472, -1.81124, 0.45, 0.02, 0.0),
+        (-5.23789, -2.06545, 0.02, 0.45, 0.0),
+        (-5.47289, -1.83045, 0.45, 0.02, 0.0),
+        (-5.47289, -2.30045, 0.45, 0.02, 0.0),
+        (-7.183631, 1.01299, 0.02, 0.45, -1.5708),
+        (-6.94863, 1.247989, 0.45, 0.02, -1.5708),
+        (-7.41863, 1.247991, 0.45, 0.02, -1.5708),
+        (6.35919, -3.19202, 0.042, 0.042, 0.0),
+        (6.35903, -2.27759, 0.042, 0.042, 0.0),
     ],
 }
 

@@ -376,3 +376,29 @@ def test_beam_sweep_multi_step_matches_oracle(beams, lanes):
     assert nd > 0
     np.testing.assert_array_equal(env.get_state(_capi.F_X), sim.arr["x"])
     np.testing.assert_array_equal(env.scan().cpu().numpy(), sim.scan())
+
+
+@pytest.mark.parametrize("beams,n", [(10, 4096), (36, 1024)])
+def test_house_map_matches_oracle(beams, n):
+    """BASELINE configs[4]: the vendored turtlebot3_house geometry (52 boxes = 208 walls), spawn
+    (-3, 1), 10 and 36 beams, against the C oracle."""
+    env = VecEnv(n, map="house", seed=3, max_episode_steps=40, num_beams=beams)
+    assert env.segments.shape == (208, 4) and (env.cfg.start_x, env.cfg.start_y) == (-3.0, 1.0)
+    sim = binding.OracleSim(env.cfg, env.segments, nthreads=8)
+    np.testing.assert_allclose(env.reset().cpu().numpy(), sim.reset(), atol=OBS_ATOL, rtol=0)
+    nd = 0
+    for t in range(70):
+        act = binding.scripted_actions(2, 0, t, n)
+        act[:, 0] = np.maximum(act[:, 0], 0.6)
+        o_ref, r_ref, d_ref, a_ref, tr_ref = sim.step(act)
+        obs, rew, done, arrive = env.step(torch.from_numpy(act).cuda())
+        np.testing.assert_array_equal(done.cpu().numpy(), d_ref, err_msg=f"done t={t}")
+        np.testing.assert_array_equal(arrive.cpu().numpy(), a_ref, err_msg=f"arrive t={t}")
+        np.testing.assert_array_equal(env.trunc.cpu().numpy(), tr_ref, err_msg=f"trunc t={t}")
+        np.testing.assert_allclose(obs.cpu().numpy(), o_ref, atol=OBS_ATOL, rtol=0, err_msg=f"obs t={t}")
+        np.testing.assert_allclose(rew.cpu().numpy(), r_ref, atol=REW_ATOL, rtol=0, err_msg=f"rew t={t}")
+        nd += int(d_ref.sum())
+    assert nd > 0
+    for k, f in (("x", _capi.F_X), ("y", _capi.F_Y), ("th", _capi.F_THETA), ("gx", _capi.F_GOAL_X)):
+        np.testing.assert_array_equal(env.get_state(f), sim.arr[k], err_msg=k)
+    np.testing.assert_array_equal(env.scan().cpu().numpy(), sim.scan())
