@@ -414,7 +414,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N * 8 * H,
                 "d2h_bytes_per_step": N * (64 + 4 + 3) * H,
                 "api": "navsim_step_host via VecEnv.step_host: host actions in, host obs/reward/flags out, every env step; "
-                       "caller buffers page-locked (VecEnv.alloc_host_buffers)",
+                       "caller buffers page-locked (VecEnv.alloc_host_buffers): the kernel reads the actions and writes the "
+                       "observations in host memory over PCIe (zero-copy), reward/flags via a mapped block",
                 "pageable_buffers_value": e2e_pageable},
         "gpu_launches": int(launches),
         "roofline": roofline,

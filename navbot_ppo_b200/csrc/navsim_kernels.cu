@@ -306,7 +306,7 @@ __device__ __forceinline__ float group_min(float v) {
 // sees it.  The list order is arbitrary (shared-memory atomics); the per-beam maximum is not.
 constexpr int kCompactWalls = 32;
 
-template <int G, int KB>
+template <int G, int KB, bool CW>
 __device__ __forceinline__ void group_sweep(const SimConst& c, const MapView& mv, float ox, float oy, float ch, float sh,
                                             int g, uint16_t* vis_list, int* vis_count, float* q) {
   const int B = (KB == NAVSIM_LIDAR_FEATS) ? KB : c.B;
@@ -317,7 +317,7 @@ __device__ __forceinline__ void group_sweep(const SimConst& c, const MapView& mv
     else { dx[b] = 0.f; dy[b] = 0.f; }
     q[b] = 0.0f;
   }
-  if (c.S <= kCompactWalls) {
+  if (!CW) {
     for (int k = g; k < c.S; k += G) {
       nv_seg_view v;
       if (!nv_seg_setup(mv.seg + NV_SEG_FLOATS * k, ox, oy, c.closed_boxes, &v)) continue;
@@ -376,8 +376,9 @@ extern __shared__ __align__(16) unsigned char dyn_smem[];
 //            sweep is the part that is split.
 //   KB       10: the reference's 10-beam sensor; kPadBeams: any B <= 36 (beam sweep).
 //   SCRIPTED actions drawn on device (benchmark / rollout driver), else read from io.act.
+//   CW       two-phase wall sweep with a compacted visible-wall list (maps with > kCompactWalls walls).
 // ----------------------------------------------------------------------------------------
-template <int G, int KB, bool SCRIPTED>
+template <int G, int KB, bool SCRIPTED, bool CW>
 __global__ void __launch_bounds__(kBlock) navsim_step_kernel(SimConst c, SimState st, const float* __restrict__ g_map,
                                                              const uint16_t* __restrict__ rt_tab, StepIO io,
                                                              DevStats* stats, uint64_t action_seed,
@@ -451,8 +452,8 @@ __global__ void __launch_bounds__(kBlock) navsim_step_kernel(SimConst c, SimStat
     // in flight behind the state loads and the drive arithmetic.
     if (t == 0) wait_map(bar);
     float q[KB];
-    group_sweep<G, KB>(c, mv, (float)(a.x + c.off_x * c_new), (float)(a.y + c.off_x * s_new), (float)c_new, (float)s_new, g,
-                       s_list + (size_t)slot * c.S, s_cnt + slot, q);
+    group_sweep<G, KB, CW>(c, mv, (float)(a.x + c.off_x * c_new), (float)(a.y + c.off_x * s_new), (float)c_new, (float)s_new,
+                           g, CW ? s_list + (size_t)slot * c.S : nullptr, CW ? s_cnt + slot : nullptr, q);
     const int B = (KB == NAVSIM_LIDAR_FEATS) ? KB : c.B;
     const float rmin = (float)c.rmin, rmax = (float)c.rmax;
     float mn = NV_INF_F;
@@ -769,7 +770,8 @@ struct navsim {
   uint32_t script_step = 0;
   int lanes = 1;                 // lanes per agent of the step kernel (G)
   const void* pin_seen[2] = {nullptr, nullptr};  // last caller buffers of navsim_step_host (actions, obs)
-  bool pin_is[2] = {false, false};
+  const float* pin_alias[2] = {nullptr, nullptr};
+  float* h_rew_dev = nullptr;    // device alias of the pinned h_rew block (reward + flags)
 };
 
 namespace {
@@ -819,17 +821,20 @@ int pick_lanes(int n_agents, int requested) {
   return g;
 }
 
-// Is this caller buffer page-locked?  (One driver query per new pointer; a training loop
-// passes the same buffers every step.)
-bool host_is_pinned(navsim* h, int slot, const void* p) {
-  if (h->pin_seen[slot] == p) return h->pin_is[slot];
+// Device-side alias of a caller's host buffer when it is page-locked and mapped (else null).
+// One driver query per new pointer; a training loop passes the same buffers every step.
+const float* host_device_alias(navsim* h, int slot, const void* p) {
+  if (h->pin_seen[slot] == p) return h->pin_alias[slot];
   cudaPointerAttributes at;
-  bool pinned = false;
-  if (cudaPointerGetAttributes(&at, p) == cudaSuccess) pinned = (at.type == cudaMemoryTypeHost);
-  else cudaGetLastError();
+  const float* alias = nullptr;
+  if (cudaPointerGetAttributes(&at, p) == cudaSuccess) {
+    if (at.type == cudaMemoryTypeHost && at.devicePointer) alias = static_cast<const float*>(at.devicePointer);
+  } else {
+    cudaGetLastError();
+  }
   h->pin_seen[slot] = p;
-  h->pin_is[slot] = pinned;
-  return pinned;
+  h->pin_alias[slot] = alias;
+  return alias;
 }
 
 int check_ready(const navsim* h) {
@@ -841,23 +846,28 @@ int check_ready(const navsim* h) {
 typedef void (*step_kernel_t)(SimConst, SimState, const float*, const uint16_t*, StepIO, DevStats*, uint64_t, uint32_t,
                               int);
 
-template <int KB, bool SCR>
+template <int KB, bool SCR, bool CW>
 step_kernel_t step_kernel_for_lanes(int g) {
   switch (g) {
-    case 1: return navsim_step_kernel<1, KB, SCR>;
-    case 2: return navsim_step_kernel<2, KB, SCR>;
-    case 4: return navsim_step_kernel<4, KB, SCR>;
-    case 8: return navsim_step_kernel<8, KB, SCR>;
-    case 16: return navsim_step_kernel<16, KB, SCR>;
-    default: return navsim_step_kernel<32, KB, SCR>;
+    case 1: return navsim_step_kernel<1, KB, SCR, CW>;
+    case 2: return navsim_step_kernel<2, KB, SCR, CW>;
+    case 4: return navsim_step_kernel<4, KB, SCR, CW>;
+    case 8: return navsim_step_kernel<8, KB, SCR, CW>;
+    case 16: return navsim_step_kernel<16, KB, SCR, CW>;
+    default: return navsim_step_kernel<32, KB, SCR, CW>;
   }
 }
 
-step_kernel_t step_kernel_of(const navsim* h, bool scripted) {
+template <int KB, bool SCR>
+step_kernel_t step_kernel_for_map(const navsim* h) {
   const int g = lanes_of(h);
+  return h->c.S > kCompactWalls ? step_kernel_for_lanes<KB, SCR, true>(g) : step_kernel_for_lanes<KB, SCR, false>(g);
+}
+
+step_kernel_t step_kernel_of(const navsim* h, bool scripted) {
   if (variant_of(h) == 0)
-    return scripted ? step_kernel_for_lanes<NAVSIM_LIDAR_FEATS, true>(g) : step_kernel_for_lanes<NAVSIM_LIDAR_FEATS, false>(g);
-  return scripted ? step_kernel_for_lanes<kPadBeams, true>(g) : step_kernel_for_lanes<kPadBeams, false>(g);
+    return scripted ? step_kernel_for_map<NAVSIM_LIDAR_FEATS, true>(h) : step_kernel_for_map<NAVSIM_LIDAR_FEATS, false>(h);
+  return scripted ? step_kernel_for_map<kPadBeams, true>(h) : step_kernel_for_map<kPadBeams, false>(h);
 }
 
 // One launch = `nsteps` consecutive Env.step calls for every agent.
@@ -999,6 +1009,11 @@ int navsim_create(navsim_t** out, const navsim_cfg* cfg) {
   // reward + the three flag arrays share one block (one D2H copy): [N floats][3N bytes]
   TRY_OR_CLEAN(cudaMallocHost(&h->h_rew, N * sizeof(float) + N * 3));
   h->h_flags = reinterpret_cast<uint8_t*>(h->h_rew + N);
+  {
+    void* dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, h->h_rew, 0) == cudaSuccess) h->h_rew_dev = static_cast<float*>(dp);
+    else cudaGetLastError();
+  }
   TRY_OR_CLEAN(cudaMalloc(&h->d_act, N * 2 * sizeof(float)));
   TRY_OR_CLEAN(cudaMalloc(&h->d_obs, N * NAVSIM_OBS_DIM * sizeof(float)));
   TRY_OR_CLEAN(cudaMalloc(&h->d_rew, N * sizeof(float) + N * 3));
@@ -1175,23 +1190,36 @@ int navsim_step_host(navsim_t* h, const float* act_host, float* obs_host, float*
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   const size_t N = (size_t)h->c.N;
   cudaStream_t s = h->own_stream;
-  // Page-locked caller buffers (cudaHostRegister / cudaMallocHost / torch pin_memory) are the
-  // DMA endpoints themselves; pageable ones go through the handle's pinned staging.
-  const bool act_pinned = host_is_pinned(h, 0, act_host), obs_pinned = host_is_pinned(h, 1, obs_host);
-  const float* act_src = act_host;
-  if (!act_pinned) {
-    memcpy(h->h_act, act_host, N * 2 * sizeof(float));
-    act_src = h->h_act;
+  // Page-locked caller buffers (cudaMallocHost / cudaHostRegister / torch pin_memory) are mapped
+  // into the device's address space (unified addressing): the step kernel then reads the actions
+  // and writes the observation rows straight over PCIe - no copy engine, no staging, one launch and
+  // one stream synchronisation per step.  Reward and flags (7 bytes per agent) go to the handle's
+  // own mapped block and are handed over with a small host copy.  Pageable caller buffers take
+  // the staged path (pinned bounce buffers + copy engine).
+  const float* act_dev = host_device_alias(h, 0, act_host);
+  float* obs_dev = const_cast<float*>(host_device_alias(h, 1, obs_host));
+  if (act_dev && obs_dev && h->h_rew_dev) {
+    float* rew_dev = h->h_rew_dev;
+    uint8_t* fl_dev = reinterpret_cast<uint8_t*>(rew_dev + N);
+    if (int rc = launch_step(h, make_io(act_dev, obs_dev, rew_dev, fl_dev, fl_dev + N, fl_dev + 2 * N, 0, 0), s, false, 0, 1))
+      return rc;
+    CUDA_TRY(cudaStreamSynchronize(s));
+  } else {
+    const float* act_src = act_host;
+    if (!act_dev) {
+      memcpy(h->h_act, act_host, N * 2 * sizeof(float));
+      act_src = h->h_act;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->d_act, act_src, N * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (int rc = launch_step(h, make_io(h->d_act, h->d_obs, h->d_rew, h->d_flags, h->d_flags + N, h->d_flags + 2 * N, 0, 0), s,
+                             false, 0, 1))
+      return rc;
+    CUDA_TRY(cudaMemcpyAsync(obs_dev ? obs_host : h->h_obs, h->d_obs, N * NAVSIM_OBS_DIM * sizeof(float),
+                             cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(h->h_rew, h->d_rew, N * sizeof(float) + N * 3, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (!obs_dev) memcpy(obs_host, h->h_obs, N * NAVSIM_OBS_DIM * sizeof(float));
   }
-  CUDA_TRY(cudaMemcpyAsync(h->d_act, act_src, N * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
-  if (int rc = launch_step(h, make_io(h->d_act, h->d_obs, h->d_rew, h->d_flags, h->d_flags + N, h->d_flags + 2 * N, 0, 0), s,
-                           false, 0, 1))
-    return rc;
-  CUDA_TRY(cudaMemcpyAsync(obs_pinned ? obs_host : h->h_obs, h->d_obs, N * NAVSIM_OBS_DIM * sizeof(float),
-                           cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(h->h_rew, h->d_rew, N * sizeof(float) + N * 3, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
-  if (!obs_pinned) memcpy(obs_host, h->h_obs, N * NAVSIM_OBS_DIM * sizeof(float));
   memcpy(rew_host, h->h_rew, N * sizeof(float));
   memcpy(done_host, h->h_flags, N);
   memcpy(arrive_host, h->h_flags + N, N);

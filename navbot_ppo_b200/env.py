@@ -71,6 +71,8 @@ class VecEnv:
         self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.arrive = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.trunc = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self._host_ptr_key, self._host_ptrs, self._host_keepalive = None, None, None
+        self._step_host_fn = L.navsim_step_host
 
     # -- lifecycle ----------------------------------------------------------------------
     def close(self):
@@ -164,8 +166,15 @@ class VecEnv:
             out = dict(obs=np.empty((n, self.obs_dim), np.float32), rew=np.empty(n, np.float32), done=np.empty(n, np.uint8),
                        arrive=np.empty(n, np.uint8), trunc=np.empty(n, np.uint8))
         obs, rew, done, arrive, trunc = out["obs"], out["rew"], out["done"], out["arrive"], out["trunc"]
-        _capi.check(_capi.lib().navsim_step_host(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data,
-                                                 done.ctypes.data, arrive.ctypes.data, trunc.ctypes.data))
+        # raw addresses are cached per buffer set: ndarray.ctypes builds a helper object on every access
+        key = (id(a), id(obs), id(rew), id(done), id(arrive), id(trunc))
+        if self._host_ptr_key != key:
+            self._host_ptr_key = key
+            self._host_ptrs = tuple(int(x.__array_interface__["data"][0]) for x in (a, obs, rew, done, arrive, trunc))
+            self._host_keepalive = (a, obs, rew, done, arrive, trunc)
+        rc = self._step_host_fn(self._h, *self._host_ptrs)
+        if rc:
+            _capi.check(rc)
         return obs, rew, done, arrive, trunc
 
     # -- state inspection / injection ------------------------------------------------------

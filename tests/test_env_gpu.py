@@ -402,3 +402,24 @@ def test_house_map_matches_oracle(beams, n):
     for k, f in (("x", _capi.F_X), ("y", _capi.F_Y), ("th", _capi.F_THETA), ("gx", _capi.F_GOAL_X)):
         np.testing.assert_array_equal(env.get_state(f), sim.arr[k], err_msg=k)
     np.testing.assert_array_equal(env.scan().cpu().numpy(), sim.scan())
+
+
+def test_pinned_host_buffers_take_the_zero_copy_path_and_agree():
+    """navsim_step_host with page-locked caller buffers (kernel reads actions / writes observations
+    over PCIe directly) == the staged path with pageable buffers == the device entry point."""
+    n = 3000
+    a = VecEnv(n, seed=6, max_episode_steps=30); b = VecEnv(n, seed=6, max_episode_steps=30)
+    c = VecEnv(n, seed=6, max_episode_steps=30)
+    a.reset(); b.reset_host(); c.reset_host()
+    hb = b.alloc_host_buffers()
+    for t in range(45):
+        act = binding.scripted_actions(8, 0, t, n)
+        obs, rew, done, arrive = a.step(torch.from_numpy(act).cuda())
+        hb["act"][:] = act
+        pobs, prew, pdone, parr, ptr = b.step_host(hb["act"], out=hb)
+        assert pobs is hb["obs"]
+        sobs, srew, sdone, sarr, str_ = c.step_host(act)
+        for x, y, z in ((obs, pobs, sobs), (rew, prew, srew), (done, pdone, sdone), (arrive, parr, sarr), (a.trunc, ptr, str_)):
+            np.testing.assert_array_equal(x.cpu().numpy(), y)
+            np.testing.assert_array_equal(y, z)
+    assert a.stats().episodes == b.stats().episodes > 0

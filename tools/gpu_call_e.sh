@@ -7,4 +7,4 @@ timeout 900 python bench.py --warmup 3 --precision bf16x3 > gpurun_out/e_bench.j
 tail -3 gpurun_out/e_bench.err
 python -c "
 import json; d=json.load(open('gpurun_out/e_bench.json'))
-print({k:d[k] for k in ('value','ms_per_step','e2e','gpu_launches','clocks')}); print(d['training'])"
+print({k:d[k] for k in ('value','ms_per_step','e2e','gpu_launches','clocks')}); print(d['training']); print(d['other_configs']); print(d['roofline_sweep'])"
