@@ -128,7 +128,7 @@ def training_bench(args, torch, dist, dev, rank, world, barrier):
     from navbot_ppo_b200.nets import NetActor, NetCritic
     from navbot_ppo_b200.ppo import PPO
     N, H = args.agents, args.horizon
-    prec = {"fp32": _capi.PREC_FP32, "bf16x3": _capi.PREC_BF16X3, "bf16": _capi.PREC_BF16}[args.precision]
+    prec = {"fp32": _capi.PREC_FP32, "bf16x3": _capi.PREC_BF16X3, "bf16": _capi.PREC_BF16}[args.precision_one]
     env = VecEnv(N, map="stage_1", device=dev.index, seed=0, max_episode_steps=500, agent_id_offset=rank * N)
     with tempfile.TemporaryDirectory() as tmp:
         agent = PPO(NetActor, NetCritic, env, 16, 2, timesteps_per_batch=N * H, max_timesteps_per_episode=500,
@@ -159,7 +159,7 @@ def training_bench(args, torch, dist, dev, rank, world, barrier):
     flops = 3.0 * (98432 + 98368) * N * H * args.epochs       # fwd + bwd of both networks, SURVEY 8(d)
     return {"rollout_env_steps_per_s": steps / (ro_ms * 1e-3), "train_env_steps_per_s": steps / (tot_ms * 1e-3),
             "rollout_ms": ro_ms, "update_ms": up_ms, "iteration_ms": tot_ms, "epochs": args.epochs, "horizon": H,
-            "samples_per_gpu": N * H, "precision": args.precision,
+            "samples_per_gpu": N * H, "precision": args.precision_one,
             "update_tflops_per_gpu": flops / (up_ms * 1e-3) / 1e12,
             "final_actor_loss": float(res["actor_losses"][-1]), "final_critic_loss": float(res["critic_losses"][-1]),
             "sim_launches_per_iteration": int(launches_per_iter)}
@@ -211,7 +211,9 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the PPO rollout / training-iteration figures")
     ap.add_argument("--train-iters", type=int, default=2)
     ap.add_argument("--epochs", type=int, default=50, help="PPO epochs per iteration (main.py:471)")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--precision", default="fp32,bf16x3",
+                    help="comma list of GEMM arithmetic modes for the training figures: fp32 (CUDA cores, the reference's "
+                         "arithmetic), bf16x3 (tcgen05, split-bf16 operands, ~16 mantissa bits), bf16 (tcgen05)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -319,7 +321,10 @@ def main():
     # ---- full training iteration (rollout + reward-to-go + 50-epoch update), SURVEY.md 8(d)
     training = None
     if not args.no_train:
-        training = training_bench(args, torch, dist, dev, rank, world, barrier)
+        training = {}
+        for prec_name in args.precision.split(","):
+            args.precision_one = prec_name.strip()
+            training[args.precision_one] = training_bench(args, torch, dist, dev, rank, world, barrier)
 
     if rank != 0:
         if world > 1:

@@ -94,10 +94,13 @@ constexpr uint32_t OFF_SX = 0;
 constexpr uint32_t OFF_SGU = OFF_SX + 2 * SX_PART;          // 24 KB
 constexpr uint32_t OFF_SH = OFF_SGU + 2 * SGU_PART;         // 40 KB
 constexpr uint32_t OFF_SGZ = OFF_SH + 2 * SH_PART;          // 104 KB
-constexpr uint32_t OFF_SW = OFF_SGZ + 2 * SH_PART;          // 168 KB: one weight chunk blob
-constexpr uint32_t OFF_RED = OFF_SW + chunk_blob_bytes(X1); // head / bias-b gradient partials [4 warps][128] floats
+constexpr uint32_t SWA_BYTES = 2 * wtile_bytes(X1);         // one fc1 weight chunk, hi | lo (16 KB)
+constexpr uint32_t OFF_SWA = OFF_SGZ + 2 * SH_PART;         // 168 KB: TWO fc1 chunk buffers (prefetch ring)
+constexpr uint32_t OFF_SWB = OFF_SWA + 2 * SWA_BYTES;       // one fc2 chunk buffer, hi | lo (16 KB)
+constexpr uint32_t OFF_BIAS = OFF_SWB + SWA_BYTES;          // fc1 biases of both blocks, resident: 2 x 512 floats
+constexpr uint32_t OFF_RED = OFF_BIAS + 2 * HID * 4;        // head / bias-b gradient partials [4 warps][128] floats
 constexpr uint32_t OFF_MISC = OFF_RED + 4 * 128 * 4;        // barriers, tmem base
-constexpr uint32_t TC_SMEM_BYTES = OFF_MISC + 64;           // 207,424 B
+constexpr uint32_t TC_SMEM_BYTES = OFF_MISC + 64;           // 227,392 B of the 232,448 B a CTA may have
 
 // TMEM columns
 constexpr uint32_t TM_Z = 0, TM_GH = 128, TM_DWA = 256, TM_DWB = 304, TM_U = 336, TM_GX = 368, TM_COLS = 512;
@@ -146,6 +149,18 @@ __device__ __forceinline__ void tma_load(unsigned char* dst, const unsigned char
                : "memory");
 }
 
+// fire-and-forget accumulation into the CTA's own partial-gradient row: the L2 does the fp32 add,
+// so the thread never waits for the old value (every address has ONE writer, in tile order ->
+// the sum is the same sequence of IEEE additions as a load-add-store)
+__device__ __forceinline__ void red_add4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add1(float* addr, float a) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
+}
+// LeakyReLU(0.2) as one multiply and one max (x > 0.2 x exactly when x > 0)
+__device__ __forceinline__ float lrelu_fast(float x) { return fmaxf(x, LEAK * x); }
+
 template <int PASSES>
 __global__ void __launch_bounds__(256, 1) mlp_grad_tc_kernel(TcGradArgs ta) {
   const GradArgs& a = ta.g;
@@ -154,11 +169,14 @@ __global__ void __launch_bounds__(256, 1) mlp_grad_tc_kernel(TcGradArgs ta) {
   unsigned char* sGU = smem + OFF_SGU;
   unsigned char* sH = smem + OFF_SH;
   unsigned char* sGZ = smem + OFF_SGZ;
-  unsigned char* sW = smem + OFF_SW;
+  unsigned char* sWa = smem + OFF_SWA;                                  // two buffers of SWA_BYTES
+  unsigned char* sWb = smem + OFF_SWB;
+  float* sBias = reinterpret_cast<float*>(smem + OFF_BIAS);
   float* sRed = reinterpret_cast<float*>(smem + OFF_RED);
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + OFF_MISC);        // MMA completion
-  uint64_t* wbar = reinterpret_cast<uint64_t*>(smem + OFF_MISC + 8);    // weight chunk arrival
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 16);
+  uint64_t* wabar = reinterpret_cast<uint64_t*>(smem + OFF_MISC + 8);   // fc1 chunk arrival, one per buffer (2)
+  uint64_t* wbbar = reinterpret_cast<uint64_t*>(smem + OFF_MISC + 24);  // fc2 chunk arrival
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_MISC + 32);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, half = warp >> 2;          // TMEM lane quarter / column half of this warp
@@ -169,9 +187,11 @@ __global__ void __launch_bounds__(256, 1) mlp_grad_tc_kernel(TcGradArgs ta) {
   const unsigned char* __restrict__ wblob = ta.wprep + (size_t)net * NET_BLOB;
   float* __restrict__ grow = a.gpart + ((size_t)net * gridDim.x + blockIdx.x) * NET_ROW;
 
-  if (tid == 0) { tc::mbar_init(mbar, 1); tc::mbar_init(wbar, 1); }
+  if (tid == 0) { tc::mbar_init(mbar, 1); tc::mbar_init(wabar, 1); tc::mbar_init(wabar + 1, 1); tc::mbar_init(wbbar, 1); }
   if (warp == 0) tc::tmem_alloc(tmem_slot, TM_COLS);
   for (int i = tid; i < NET_ROW; i += 256) grow[i] = 0.f;
+  __threadfence();   // the zeros are in L2 before any red.add of this CTA
+  for (int i = tid; i < 2 * HID; i += 256) sBias[i] = p[(i < HID ? O_B1A : O_B2A - HID) + i];
   // constant part of the X tile: columns 32..47 = (1, 0, 0, ...) in every row
   if (owner) {
     float ones[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, zeros[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -184,11 +204,26 @@ __global__ void __launch_bounds__(256, 1) mlp_grad_tc_kernel(TcGradArgs ta) {
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);   // this warp's lane quarter
-  uint32_t mphase = 0, wphase = 0;
+  uint32_t mphase = 0;
+  uint32_t wa_ph[2] = {0, 0}, wb_ph = 0;             // used by thread 0 only (it issues TMA and MMA)
 
   // shared-memory addresses of the operand tiles
   const uint32_t aX = tc::smem_u32(sX), aGU = tc::smem_u32(sGU), aH = tc::smem_u32(sH), aGZ = tc::smem_u32(sGZ),
-                 aW = tc::smem_u32(sW);
+                 aWa = tc::smem_u32(sWa), aWb = tc::smem_u32(sWb);
+  // Weight pipeline (thread 0): a chunk blob is [Wa hi | Wa lo | Wb hi | Wb lo | ba]; the fc1 half
+  // goes to ring buffer c & 1, the fc2 half to the single fc2 buffer, each as one TMA bulk copy on
+  // its own mbarrier.  A region is refilled as soon as the last MMA that reads it has completed,
+  // i.e. one chunk ahead, so the copies fly behind the CUDA-core epilogues.
+  auto load_wa = [&](int blk, int c) {
+    const uint32_t wt = wtile_bytes(blk ? X1 : OBS);
+    tma_load(sWa + (c & 1) * SWA_BYTES, wblob + blob_offset(blk, c), 2 * wt, wabar + (c & 1));
+  };
+  auto load_wb = [&](int blk, int c) {
+    const uint32_t wt = wtile_bytes(blk ? X1 : OBS);
+    tma_load(sWb, wblob + blob_offset(blk, c) + 2 * wt, 2 * wt, wbbar);
+  };
+  auto wait_wa = [&](int c) { tc::mbar_wait(wabar + (c & 1), wa_ph[c & 1]); wa_ph[c & 1] ^= 1; };
+  auto wait_wb = [&]() { tc::mbar_wait(wbbar, wb_ph); wb_ph ^= 1; };
 
   double macc[4] = {0.0, 0.0, 0.0, 0.0};
   const int ntiles = (a.T + 127) / 128;
@@ -221,27 +256,36 @@ __global__ void __launch_bounds__(256, 1) mlp_grad_tc_kernel(TcGradArgs ta) {
     for (int blk = 0; blk < 2; ++blk) {
       const int IN = blk ? X1 : OBS;
       const uint32_t wt = wtile_bytes(IN);
+      // Z = X Wa^T : A = X (rows = samples), B = Wa (rows = hidden units), K = IN
+      auto issue_z = [&](int c) {
+        const uint32_t w = aWa + (c & 1) * SWA_BYTES;
+        issue_gemm<PASSES>(tmem + TM_Z, aX, aX + SX_PART, ROWG, 128, 2 * ROWG, 0, w, w + wt, ROWG, 128, 2 * ROWG, 0, 128,
+                           IN / 16, false);
+      };
+      if (tid == 0) {
+        load_wa(blk, 0);
+        load_wb(blk, 0);
+        wait_wa(0);
+        tc::fence_after_sync();
+        issue_z(0);
+        tc::mma_commit(mbar);
+      }
 #pragma unroll 1
       for (int c = 0; c < NCHUNK; ++c) {
-        if (tid == 0) tma_load(sW, wblob + blob_offset(blk, c), chunk_blob_bytes(IN), wbar);
-        tc::mbar_wait(wbar, wphase); wphase ^= 1;
-        if (tid == 0) {
-          tc::fence_after_sync();
-          // Z = X Wa^T : A = X (rows = samples), B = Wa (rows = hidden units), K = IN
-          issue_gemm<PASSES>(tmem + TM_Z, aX, aX + SX_PART, ROWG, 128, 2 * ROWG, 0, aW, aW + wt, ROWG, 128, 2 * ROWG, 0,
-                             128, IN / 16, false);
-          tc::mma_commit(mbar);
-        }
-        tc::mbar_wait(mbar, mphase); mphase ^= 1;
+        tc::mbar_wait(mbar, mphase); mphase ^= 1;   // Z(c) is in TMEM (and U(c-1) has been accumulated)
         tc::fence_after_sync();
+        if (tid == 0) {
+          if (c > 0) load_wb(blk, c);               // U(c-1) done: the fc2 buffer is free
+          if (c + 1 < NCHUNK) load_wa(blk, c + 1);  // ring slot (c+1)&1 was last read by Z(c-1)
+        }
         {  // H = lrelu(Z + ba): this warp's 32 rows x 64 columns
-          const float* sBa = reinterpret_cast<const float*>(sW + 4 * wt);
+          const float* sBa = sBias + blk * HID + c * CHUNK;
 #pragma unroll 1
           for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 16) {
             float v[16];
             tc::tmem_ld16(trow + TM_Z + c0, v);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i] + sBa[c0 + i]);
+            for (int i = 0; i < 16; ++i) v[i] = lrelu_fast(v[i] + sBa[c0 + i]);
             store8<PASSES>(sH, SH_PART, row, c0, v);
             store8<PASSES>(sH, SH_PART, row, c0 + 8, v + 8);
           }
@@ -251,14 +295,19 @@ __global__ void __launch_bounds__(256, 1) mlp_grad_tc_kernel(TcGradArgs ta) {
         __syncthreads();
         if (tid == 0) {
           tc::fence_after_sync();
+          wait_wb();
           // U += H Wb^T : A = H (rows = samples), B = Wb (rows = output features, R = IN), K = 128
-          issue_gemm<PASSES>(tmem + TM_U, aH, aH + SH_PART, ROWG, 128, 2 * ROWG, 0, aW + 2 * wt, aW + 3 * wt,
-                             (uint32_t)IN * 16, 128, 2u * IN * 16, 0, IN, CHUNK / 16, c > 0);
+          issue_gemm<PASSES>(tmem + TM_U, aH, aH + SH_PART, ROWG, 128, 2 * ROWG, 0, aWb, aWb + wt, (uint32_t)IN * 16, 128,
+                             2u * IN * 16, 0, IN, CHUNK / 16, c > 0);
+          if (c + 1 < NCHUNK) {                     // next chunk's Z rides on the same commit
+            wait_wa(c + 1);
+            issue_z(c + 1);
+          }
           tc::mma_commit(mbar);
         }
-        tc::mbar_wait(mbar, mphase); mphase ^= 1;
-        tc::fence_after_sync();
       }
+      tc::mbar_wait(mbar, mphase); mphase ^= 1;     // U complete
+      tc::fence_after_sync();
       // block output: u = x + U + bb
       if (owner) {
         if (blk == 0) {
@@ -368,24 +417,59 @@ __global__ void __launch_bounds__(256, 1) mlp_grad_tc_kernel(TcGradArgs ta) {
       const int IN = blk ? X1 : OBS;
       const uint32_t wt = wtile_bytes(IN);
       const int o_wa = blk ? O_W2A : O_W1A, o_ba = blk ? O_B2A : O_B1A, o_wb = blk ? O_W2B : O_W1B;
+      // phase 1 of chunk c: Z (recomputed) and GH = GU Wb (Wb read MN-major: rows = K = output
+      // features, R = IN; columns = hidden units = N)
+      auto issue_phase1 = [&](int c) {
+        const uint32_t w = aWa + (c & 1) * SWA_BYTES;
+        issue_gemm<PASSES>(tmem + TM_Z, aX, aX + SX_PART, ROWG, 128, 2 * ROWG, 0, w, w + wt, ROWG, 128, 2 * ROWG, 0, 128,
+                           IN / 16, false);
+        issue_gemm<PASSES>(tmem + TM_GH, aGU, aGU + SGU_PART, ROWG, 128, 2 * ROWG, 0, aWb, aWb + wt, 128, (uint32_t)IN * 16,
+                           256, 1, 128, IN / 16, false);
+      };
+      // weight-gradient chunk c out of TMEM (lane = hidden unit j of the chunk) into the CTA's row
+      auto flush_dw = [&](int c) {
+        const int j = c * CHUNK + row;
+        if (half == 0) {
+          float* ga = grow + o_wa + j * IN;
+          for (int c0 = 0; c0 < IN; c0 += 16) {
+            float v[16];
+            tc::tmem_ld16(trow + TM_DWA + c0, v);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) red_add4(ga + c0 + 4 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+          float v[16];
+          tc::tmem_ld16(trow + TM_DWA + 32, v);       // column 32 = sum over samples of g_z = bias gradient
+          red_add1(grow + o_ba + j, v[0]);
+        } else {
+          float* gb = grow + o_wb + j * IN;            // kernel layout: fc2 transposed
+          for (int c0 = 0; c0 < IN; c0 += 16) {
+            float v[16];
+            tc::tmem_ld16(trow + TM_DWB + c0, v);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) red_add4(gb + c0 + 4 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+        }
+      };
+      if (tid == 0) {
+        load_wa(blk, 0);
+        load_wb(blk, 0);
+        wait_wa(0);
+        wait_wb();
+        tc::fence_after_sync();
+        issue_phase1(0);
+        tc::mma_commit(mbar);
+      }
 #pragma unroll 1
       for (int c = 0; c < NCHUNK; ++c) {
-        if (tid == 0) tma_load(sW, wblob + blob_offset(blk, c), chunk_blob_bytes(IN), wbar);
-        tc::mbar_wait(wbar, wphase); wphase ^= 1;
-        if (tid == 0) {
-          tc::fence_after_sync();
-          issue_gemm<PASSES>(tmem + TM_Z, aX, aX + SX_PART, ROWG, 128, 2 * ROWG, 0, aW, aW + wt, ROWG, 128, 2 * ROWG, 0,
-                             128, IN / 16, false);
-          // GH = GU Wb : A = GU (rows = samples, K = output features), B = Wb read MN-major
-          // (rows = K = output features, R = IN; columns = hidden units = N)
-          issue_gemm<PASSES>(tmem + TM_GH, aGU, aGU + SGU_PART, ROWG, 128, 2 * ROWG, 0, aW + 2 * wt, aW + 3 * wt, 128,
-                             (uint32_t)IN * 16, 256, 1, 128, IN / 16, false);
-          tc::mma_commit(mbar);
-        }
-        tc::mbar_wait(mbar, mphase); mphase ^= 1;
+        tc::mbar_wait(mbar, mphase); mphase ^= 1;   // phase 1 of c (and phase 2 of c-1) complete
         tc::fence_after_sync();
+        if (tid == 0 && c + 1 < NCHUNK) {
+          load_wb(blk, c + 1);                      // GH(c) done: the fc2 buffer is free
+          load_wa(blk, c + 1);                      // ring slot (c+1)&1 was last read by Z / GX of c-1
+        }
+        if (c > 0) flush_dw(c - 1);
         {  // H = lrelu(z), GZ = GH * lrelu'(z), z = Z + ba
-          const float* sBa = reinterpret_cast<const float*>(sW + 4 * wt);
+          const float* sBa = sBias + blk * HID + c * CHUNK;
 #pragma unroll 1
           for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 16) {
             float z[16], g[16];
@@ -394,7 +478,7 @@ __global__ void __launch_bounds__(256, 1) mlp_grad_tc_kernel(TcGradArgs ta) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float zz = z[i] + sBa[c0 + i];
-              z[i] = lrelu(zz);
+              z[i] = lrelu_fast(zz);
               g[i] = g[i] * dlrelu(zz);
             }
             store8<PASSES>(sH, SH_PART, row, c0, z);
@@ -408,55 +492,30 @@ __global__ void __launch_bounds__(256, 1) mlp_grad_tc_kernel(TcGradArgs ta) {
         __syncthreads();
         if (tid == 0) {
           tc::fence_after_sync();
-          if (blk)  // GX += GZ Wa : A = GZ (rows = samples, K = hidden), B = Wa read MN-major (rows = K = hidden)
-            issue_gemm<PASSES>(tmem + TM_GX, aGZ, aGZ + SH_PART, ROWG, 128, 2 * ROWG, 0, aW, aW + wt, 128, ROWG, 256, 1,
-                               IN, CHUNK / 16, c > 0);
+          if (blk) {  // GX += GZ Wa : A = GZ (rows = samples, K = hidden), B = Wa read MN-major (rows = K = hidden)
+            const uint32_t w = aWa + (c & 1) * SWA_BYTES;
+            issue_gemm<PASSES>(tmem + TM_GX, aGZ, aGZ + SH_PART, ROWG, 128, 2 * ROWG, 0, w, w + wt, 128, ROWG, 256, 1, IN,
+                               CHUNK / 16, c > 0);
+          }
           // dWa = GZ^T [X | 1] : both operands MN-major (rows = K = samples)
           issue_gemm<PASSES>(tmem + TM_DWA, aGZ, aGZ + SH_PART, 128, ROWG, 256, 1, aX, aX + SX_PART, 128, ROWG, 256, 1, XCOLS,
                              128 / 16, false);
           // dWbT = H^T GU
           issue_gemm<PASSES>(tmem + TM_DWB, aH, aH + SH_PART, 128, ROWG, 256, 1, aGU, aGU + SGU_PART, 128, ROWG, 256, 1, IN,
                              128 / 16, false);
+          if (c + 1 < NCHUNK) {                     // next chunk's phase 1 rides on the same commit
+            wait_wa(c + 1);
+            wait_wb();
+            issue_phase1(c + 1);
+          }
           tc::mma_commit(mbar);
         }
-        tc::mbar_wait(mbar, mphase); mphase ^= 1;
-        tc::fence_after_sync();
-        {  // weight-gradient chunk: TMEM lane = hidden unit j of the chunk
-          const int j = c * CHUNK + row;
-          if (half == 0) {
-            float* ga = grow + o_wa + j * IN;
-            for (int c0 = 0; c0 < IN; c0 += 16) {
-              float v[16];
-              tc::tmem_ld16(trow + TM_DWA + c0, v);
-              float4* g4 = reinterpret_cast<float4*>(ga + c0);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float4 t = g4[i];
-                t.x += v[4 * i]; t.y += v[4 * i + 1]; t.z += v[4 * i + 2]; t.w += v[4 * i + 3];
-                g4[i] = t;
-              }
-            }
-            float v[16];
-            tc::tmem_ld16(trow + TM_DWA + 32, v);       // column 32 = sum over samples of g_z = bias gradient
-            grow[o_ba + j] += v[0];
-          } else {
-            float* gb = grow + o_wb + j * IN;            // kernel layout: fc2 transposed
-            for (int c0 = 0; c0 < IN; c0 += 16) {
-              float v[16];
-              tc::tmem_ld16(trow + TM_DWB + c0, v);
-              float4* g4 = reinterpret_cast<float4*>(gb + c0);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float4 t = g4[i];
-                t.x += v[4 * i]; t.y += v[4 * i + 1]; t.z += v[4 * i + 2]; t.w += v[4 * i + 3];
-                g4[i] = t;
-              }
-            }
-          }
-        }
-        tc::fence_before_sync();
-        __syncthreads();
       }
+      tc::mbar_wait(mbar, mphase); mphase ^= 1;     // phase 2 of the last chunk complete
+      tc::fence_after_sync();
+      flush_dw(NCHUNK - 1);
+      tc::fence_before_sync();
+      __syncthreads();
       if (blk) {
         // dL/dx1 = g_u2 (skip connection) + GX; dL/du1 = dL/dy1 * lrelu'(u1); publish GU1 for block 1
         if (owner) {
