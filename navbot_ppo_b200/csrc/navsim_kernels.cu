@@ -229,7 +229,8 @@ __device__ __forceinline__ void sample_goal(const SimConst& c, const double* rec
 // (turtlebot3_stage_1.launch:3-5), so its first LaserScan is a per-map constant: the B
 // sanitised ranges were cast once by navsim_set_map (host build of the same physics) and sit
 // behind the beam table in shared memory.  Row ownership follows the step kernel: the lane
-// with (i mod lidar_mod) == lidar_lane writes lidar feature i, `feats` lanes write obs[10..15].
+// with (beam mod lidar_mod) == lidar_lane writes the lidar features sampling that beam, `feats`
+// lanes write obs[10..15].
 __device__ __forceinline__ void reset_agent(const SimConst& c, const MapView& mv, const uint16_t* __restrict__ rt_tab,
                                             uint64_t agent, Agent* a, float* obs, bool feats, int lidar_mod,
                                             int lidar_lane) {
@@ -243,7 +244,7 @@ __device__ __forceinline__ void reset_agent(const SimConst& c, const MapView& mv
   odom_features(c, rt_tab, a->x, a->y, a->th, a->gx, a->gy, &yaw, &rel, &diff);
 #pragma unroll
   for (int i = 0; i < NAVSIM_LIDAR_FEATS; ++i)
-    if ((i & (lidar_mod - 1)) == lidar_lane) obs[i] = mv.start_r[c.pick[i]] * kInvRmax;      // :361-369
+    if ((c.pick[i] & (lidar_mod - 1)) == lidar_lane) obs[i] = mv.start_r[c.pick[i]] * kInvRmax;   // :361-369
   if (feats) write_goal_feats(c, obs, 0.f, 0.f, a->past, yaw, rel, diff);                    // :372-376
 }
 
@@ -267,26 +268,21 @@ __device__ __forceinline__ void store_agent(const SimState& st, int i, const Age
 }
 
 // ----------------------------------------------------------------------------------------
-// LaserScan (row R) of one agent by the G lanes of its group.  Wall k is handled by lane
-// k mod G: that lane culls / orients the wall once and tests all beams against it, keeping
-// the best inverse hit distance per beam in registers; the group then combines the per-beam
-// maxima with one warp reduction (redux.sync over the group's lane mask) per beam.  q >= +0
-// always, so the unsigned-integer maximum of the bit patterns is the float maximum, and a
-// maximum does not depend on the order the walls were visited in: the result is bit-identical
-// to the serial sweep of the host build (nv_beam_q).
-// KB = beams held in registers: exactly B when KB == 10 (the reference's sensor), else B <= KB.
-// Output: r[b] = range with the Gazebo gates applied, +inf already mapped to 3.5 (:193-194).
+// LaserScan (row R) of one agent by the G lanes of its group.
+//   cull   lane g examines walls g, g + G, ..: is the wall in reach and facing the sensor?
+//          S <= 32 (stage maps): each lane's verdicts are bits of a mask, OR-combined over the
+//          group with shuffle-xor rounds.  Larger maps (house: 208 walls, CW): the survivors go to
+//          the agent's list in shared memory (atomics) - a robot sees a handful of the walls of
+//          a house, and without the list a warp would run the beam loop for a wall whenever ANY
+//          of its lanes sees it.
+//   cast   lane g owns beams g, g + G, ..: it walks the group's visible walls and keeps the
+//          largest inverse hit distance of each of its beams.  No reduction is needed (a beam
+//          has one owner) and the lanes of a group run in lockstep.
+// The maximum over walls does not depend on the order they are visited in, so the result is
+// bit-identical to the serial sweep of the host build (nv_beam_q).
+// KB = beams the group holds in registers: exactly B when KB == 10 (the reference's sensor),
+// else B <= KB.  q[j] belongs to beam g + j G.
 // ----------------------------------------------------------------------------------------
-template <int G>
-__device__ __forceinline__ float group_max(float v) {
-#pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) {
-    const float w = __shfl_xor_sync(0xffffffffu, v, o);
-    v = (w > v) ? w : v;
-  }
-  return v;
-}
-
 template <int G>
 __device__ __forceinline__ float group_min(float v) {
 #pragma unroll
@@ -297,33 +293,51 @@ __device__ __forceinline__ float group_min(float v) {
   return v;
 }
 
-// Sweeps the walls and leaves in q[b] the largest inverse hit distance of beam b over ALL
-// walls (every lane of the group holds all of them).
-// Maps with more than kCompactWalls walls (house: 208) are swept in two phases: the lanes first
-// cull their share of the walls and append the survivors to the agent's list in shared memory
-// (a robot sees a handful of the walls of a house), then share out the survivors and cast the
-// beams.  Without the list a warp would run the beam loop for a wall whenever ANY of its lanes
-// sees it.  The list order is arbitrary (shared-memory atomics); the per-beam maximum is not.
 constexpr int kCompactWalls = 32;
+
+// The G lanes of a group form a GB x GW grid: lane g owns beams (g mod GB) + j GB and every GW-th
+// visible wall.  GB grows with G up to 4 (10-beam sensor) / 8 (padded variant); lanes beyond
+// that split the walls, and their per-beam maxima are combined with log2(GW) shuffle rounds.
+template <int G, int KB>
+struct BeamShare {
+  static constexpr int GBMAX = (KB == NAVSIM_LIDAR_FEATS) ? 4 : 8;
+  static constexpr int GB = (G < GBMAX) ? G : GBMAX;
+  static constexpr int GW = G / GB;
+  static constexpr int PER = (KB + GB - 1) / GB;   // beams per lane
+};
 
 template <int G, int KB, bool CW>
 __device__ __forceinline__ void group_sweep(const SimConst& c, const MapView& mv, float ox, float oy, float ch, float sh,
                                             int g, uint16_t* vis_list, int* vis_count, float* q) {
+  constexpr int PER = BeamShare<G, KB>::PER, GB = BeamShare<G, KB>::GB, GW = BeamShare<G, KB>::GW;
   const int B = (KB == NAVSIM_LIDAR_FEATS) ? KB : c.B;
-  float dx[KB], dy[KB];
+  const int gb = g & (GB - 1), gw = g / GB;
+  float dx[PER], dy[PER];
 #pragma unroll
-  for (int b = 0; b < KB; ++b) {
-    if (b < B) nv_beam_dir(ch, sh, mv.bc[b], mv.bs[b], &dx[b], &dy[b]);
-    else { dx[b] = 0.f; dy[b] = 0.f; }
-    q[b] = 0.0f;
+  for (int j = 0; j < PER; ++j) {
+    const int b = gb + j * GB;
+    if (b < B) nv_beam_dir(ch, sh, mv.bc[b], mv.bs[b], &dx[j], &dy[j]);
+    else { dx[j] = 0.f; dy[j] = 0.f; }            // never hits: q stays 0
+    q[j] = 0.0f;
   }
   if (!CW) {
+    unsigned vis = 0;
     for (int k = g; k < c.S; k += G) {
-      nv_seg_view v;
-      if (!nv_seg_setup(mv.seg + NV_SEG_FLOATS * k, ox, oy, c.closed_boxes, &v)) continue;
+      float wx, wy, ex, ey, tn;
+      if (nv_seg_cull(mv.seg + NV_SEG_FLOATS * k, ox, oy, c.closed_boxes, &wx, &wy, &ex, &ey, &tn)) vis |= 1u << k;
+    }
 #pragma unroll
-      for (int b = 0; b < KB; ++b)
-        if (b < B) q[b] = nv_ray_q(&v, dx[b], dy[b], q[b]);
+    for (int o = G / 2; o > 0; o >>= 1) vis |= __shfl_xor_sync(0xffffffffu, vis, o);
+    int turn = 0;
+    while (vis) {
+      const int k = __ffs(vis) - 1;
+      vis &= vis - 1;
+      if (GW == 1 || ((turn++) & (GW - 1)) == gw) {
+        nv_seg_view v;
+        nv_seg_setup(mv.seg + NV_SEG_FLOATS * k, ox, oy, c.closed_boxes, &v);
+#pragma unroll
+        for (int j = 0; j < PER; ++j) q[j] = nv_ray_q(&v, dx[j], dy[j], q[j]);
+      }
     }
   } else {
     int n = 0;
@@ -342,19 +356,22 @@ __device__ __forceinline__ void group_sweep(const SimConst& c, const MapView& mv
       __syncwarp();
       n = *vis_count;
     }
-    for (int idx = g; idx < n; idx += G) {
+    for (int idx = gw; idx < n; idx += GW) {
       nv_seg_view v;
       nv_seg_setup(mv.seg + NV_SEG_FLOATS * (int)vis_list[idx], ox, oy, c.closed_boxes, &v);
 #pragma unroll
-      for (int b = 0; b < KB; ++b)
-        if (b < B) q[b] = nv_ray_q(&v, dx[b], dy[b], q[b]);
+      for (int j = 0; j < PER; ++j) q[j] = nv_ray_q(&v, dx[j], dy[j], q[j]);
     }
     if (G > 1) __syncwarp();   // the list is rewritten next step
   }
-  if (G > 1) {
+  if (GW > 1) {
 #pragma unroll
-    for (int b = 0; b < KB; ++b)
-      if (b < B) q[b] = group_max<G>(q[b]);
+    for (int j = 0; j < PER; ++j)
+#pragma unroll
+      for (int o = GB; o < G; o <<= 1) {
+        const float w = __shfl_xor_sync(0xffffffffu, q[j], o);
+        q[j] = (w > q[j]) ? w : q[j];
+      }
   }
 }
 
@@ -451,48 +468,34 @@ __global__ void __launch_bounds__(kBlock) navsim_step_kernel(SimConst c, SimStat
     // LaserScan + getState (:183-207).  The map is first needed here: its TMA copy has been
     // in flight behind the state loads and the drive arithmetic.
     if (t == 0) wait_map(bar);
-    float q[KB];
+    constexpr int PER = BeamShare<G, KB>::PER;
+    float q[PER];
     group_sweep<G, KB, CW>(c, mv, (float)(a.x + c.off_x * c_new), (float)(a.y + c.off_x * s_new), (float)c_new, (float)s_new,
                            g, CW ? s_list + (size_t)slot * c.S : nullptr, CW ? s_cnt + slot : nullptr, q);
     const int B = (KB == NAVSIM_LIDAR_FEATS) ? KB : c.B;
     const float rmin = (float)c.rmin, rmax = (float)c.rmax;
     float mn = NV_INF_F;
-    if (G == 1 || KB != NAVSIM_LIDAR_FEATS) {
-      // every lane turns all beams into ranges; lane 0 of the group fills the row (:289-294)
-      int pickn = 0;
+    // each lane turns its own beams into ranges (one IEEE division each), writes the lidar
+    // features that sample them (:289-294), and the group combines the minimum (:200)
+    constexpr int GB = BeamShare<G, KB>::GB;
+    const int gb = g & (GB - 1);
+    const bool lidar_writer = valid && g < GB;           // wall-group 0 of the GB x GW lane grid
 #pragma unroll
-      for (int b = 0; b < KB; ++b) {
-        if (b < B) {
-          const float rb = sanitised_range(q[b], rmin, rmax);
-          mn = (rb < mn) ? rb : mn;
-          if (KB == NAVSIM_LIDAR_FEATS) {
-            if (writer) my_obs[b] = rb * kInvRmax;                   // idx_i == i when L == 10
-          } else {
-            while (pickn < NAVSIM_LIDAR_FEATS && c.pick[pickn] == b) {
-              if (writer) my_obs[pickn] = rb * kInvRmax;
-              ++pickn;
-            }
-          }
+    for (int j = 0; j < PER; ++j) {
+      const int b = gb + j * GB;
+      if (b < B) {
+        const float rb = sanitised_range(q[j], rmin, rmax);
+        mn = (rb < mn) ? rb : mn;
+        if (KB == NAVSIM_LIDAR_FEATS) {
+          if (lidar_writer) my_obs[b] = rb * kInvRmax;               // idx_i == i when L == 10
+        } else if (lidar_writer) {
+#pragma unroll
+          for (int i = 0; i < NAVSIM_LIDAR_FEATS; ++i)
+            if (c.pick[i] == b) my_obs[i] = rb * kInvRmax;
         }
       }
-    } else {
-      // 10 beams over G lanes: lane g owns beams g, g + G, ..; it divides only those, writes
-      // their features, and the group combines the minimum.
-      constexpr int PER = (KB + G - 1) / G;
-#pragma unroll
-      for (int j = 0; j < PER; ++j) {
-        const int mine = g + j * G;
-        float qm = 0.0f;
-#pragma unroll
-        for (int b = j * G; b < KB && b < (j + 1) * G; ++b) qm = (b == mine) ? q[b] : qm;
-        if (mine < KB) {
-          const float rb = sanitised_range(qm, rmin, rmax);
-          mn = (rb < mn) ? rb : mn;
-          if (valid) my_obs[mine] = rb * kInvRmax;
-        }
-      }
-      mn = group_min<G>(mn);
     }
+    if (G > 1) mn = group_min<G>(mn);
     const bool done = (c.collide > (double)mn) && (mn > 0.0f);       // :200
     const double ddx = a.gx - a.x, ddy = a.gy - a.y;
     const double d = sqrt(ddx * ddx + ddy * ddy);                    // :203
@@ -530,8 +533,8 @@ __global__ void __launch_bounds__(kBlock) navsim_step_kernel(SimConst c, SimStat
           atomicAdd(&stats->length_sum, (double)a.steps);
           atomicAdd(&stats->path_sum, (double)a.ep_path);
         }
-        if (G == 1 || KB != NAVSIM_LIDAR_FEATS) reset_agent(c, mv, rt_tab, agent, &a, my_obs, writer, 1, writer ? 0 : -1);
-        else reset_agent(c, mv, rt_tab, agent, &a, my_obs, writer, G, valid ? g : -1);
+        reset_agent(c, mv, rt_tab, agent, &a, my_obs, writer, BeamShare<G, KB>::GB,
+                    (valid && g < BeamShare<G, KB>::GB) ? g : -1);
         goal_dirty = true;
       }
     } else if (arrive) {                                             // :245-267
@@ -784,9 +787,9 @@ int variant_of(const navsim* h) { return h->c.B == NAVSIM_LIDAR_FEATS ? 0 : (h->
 int lanes_of(const navsim* h) {
   if (variant_of(h) == 2) return 32;
   int g = h->lanes;
-  // measured (tools/lane_sweep.py house 10 beams, 4096 agents): with hundreds of walls and few
-  // beams the cull phase dominates and one more doubling pays
-  if (h->cfg.lanes_per_agent <= 0 && h->c.S > 64 && h->c.B <= 12 && g < 32 && (long long)h->c.N * g <= 32768) g *= 2;
+  // measured (tools/lane_sweep.py, house map, 4096 agents, 10 and 36 beams): with hundreds of walls
+  // the cull phase dominates and one more doubling pays
+  if (h->cfg.lanes_per_agent <= 0 && h->c.S > 64 && g < 32 && (long long)h->c.N * g <= 32768) g *= 2;
   while (g < 32 && (size_t)(kBlock / g) * (size_t)h->c.S * 2 > 65536) g *= 2;
   return g;
 }
