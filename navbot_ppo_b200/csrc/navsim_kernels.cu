@@ -104,6 +104,9 @@ struct Agent {
 };
 
 constexpr int kBlock = 128;                  // threads per CTA of every simulator kernel
+#ifndef NAVSIM_G1_MINBLOCKS
+#define NAVSIM_G1_MINBLOCKS 6                // thread-per-agent variant: cap registers for 24 warps / SM
+#endif
 constexpr int kObsPad = NAVSIM_OBS_DIM + 1;  // +1 float: conflict-free column access
 constexpr int kPadBeams = 36;                // register-resident beam count of the padded variant
 constexpr float kInvRmax = 1.0f / 3.5f;      // environment_new.py:289 (lidar / 3.5)
@@ -396,7 +399,7 @@ extern __shared__ __align__(16) unsigned char dyn_smem[];
 //   CW       two-phase wall sweep with a compacted visible-wall list (maps with > kCompactWalls walls).
 // ----------------------------------------------------------------------------------------
 template <int G, int KB, bool SCRIPTED, bool CW>
-__global__ void __launch_bounds__(kBlock) navsim_step_kernel(SimConst c, SimState st, const float* __restrict__ g_map,
+__global__ void __launch_bounds__(kBlock, (G == 1 && KB == NAVSIM_LIDAR_FEATS) ? NAVSIM_G1_MINBLOCKS : 1) navsim_step_kernel(SimConst c, SimState st, const float* __restrict__ g_map,
                                                              const uint16_t* __restrict__ rt_tab, StepIO io,
                                                              DevStats* stats, uint64_t action_seed,
                                                              uint32_t script_step0, int nsteps) {
