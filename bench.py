@@ -34,7 +34,7 @@ BYTES_PER_ENV_STEP = 84 + 127
 BYTES_PER_ENV_STEP_SCRIPTED = BYTES_PER_ENV_STEP - 8  # actions drawn in-kernel, not read
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full`
 # capture of the same kernel and shape (profiles/README.md names the file); keyed by (N, H)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {}
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {(8192, 128): 739072 + 17440768}   # profiles/r01p_step_8192_fused_ncu.csv
 
 
 def load_peaks():
@@ -341,6 +341,8 @@ def main():
                 "env_steps_per_launch": N * H, "us_per_launch": per_launch_s * 1e6, "us_per_env_step_batch": per_launch_s * 1e6 / H,
                 "lanes_per_agent": env.lanes_per_agent,
                 "fused_launch_bytes_per_env_step": fused_bytes,
+                "traffic_note": "DRAM bytes of one launch under ncu (cold caches): below even the 72 B/step of outputs because "
+                                "most of the 75 MB of rollout rows is still in the 126 MB L2 when the kernel ends",
                 "note": "one launch = H steps with the agent state in registers: per env-step it really moves "
                         f"{fused_bytes:.1f} B (outputs + state/H) instead of the per-step-launch figure {BYTES_PER_ENV_STEP_SCRIPTED} B "
                         "that `achieved` is defined on; N=8192 agents = 55 per SM, so the launch is bound by one "
