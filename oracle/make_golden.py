@@ -12,6 +12,8 @@ The fixtures travel to the GPU box, where /root/reference does not exist.
                           wall-seeking, goal-seeking and spinning controllers so that
                           collisions, arrivals, timeouts, all quadrants of the bearing
                           computation and many rounding boundaries occur.
+  env_rollout_house*.npz  the same on the 208-wall house map (10 beams, and 36 beams through the
+                          reference's lidar subsampling rule)
   env_raw_stage_1.npz     Env.step used without resets (DDPG/TD3-style callers):
                           arrival respawns the goal inside step (environment_new.py:245-267).
   ppo_*.npz               see make_golden_ppo() — nets, reward-to-go, evaluate, update epochs.
@@ -49,10 +51,12 @@ def controller(kind, rng, st, t):
     raise ValueError(kind)
 
 
-def gen_env_rollout(map_name, agents, steps, max_ep, seed, is_training=True):
+def gen_env_rollout(map_name, agents, steps, max_ep, seed, is_training=True, num_beams=10):
     seg = maps.get_map(map_name)
+    start = maps.SPAWN.get(map_name, (0.0, 0.0, 0.0))
     rng = np.random.RandomState(1234 + seed)
-    envs = [fake_ros.RefEnv(seg, seed=seed, agent=a, is_training=is_training) for a in range(agents)]
+    envs = [fake_ros.RefEnv(seg, seed=seed, agent=a, is_training=is_training, start=start, num_beams=num_beams)
+            for a in range(agents)]
     rec = {k: [] for k in ("act", "obs_next", "obs_step", "rew", "done", "arrive", "trunc", "x", "y", "th", "gx", "gy",
                            "past", "draws")}
     obs0 = np.stack([e.reset() for e in envs])
@@ -83,7 +87,8 @@ def gen_env_rollout(map_name, agents, steps, max_ep, seed, is_training=True):
             rec[k].append(np.asarray(row[k]))
     out = {k: np.stack(v) for k, v in rec.items()}
     out.update(obs0=obs0, segments=seg, seed=np.int64(seed), max_episode_steps=np.int32(max_ep),
-               arrive_threshold=np.float64(0.2 if is_training else 0.4))
+               arrive_threshold=np.float64(0.2 if is_training else 0.4), start=np.asarray(start, np.float64),
+               num_beams=np.int32(num_beams))
     return out
 
 
@@ -130,6 +135,12 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "env_rollout_stage_1_eval.npz"),
                         **gen_env_rollout("stage_1", 8, 200, 90, seed=3, is_training=False))
     np.savez_compressed(os.path.join(GOLD, "env_raw_stage_1.npz"), **gen_env_raw("stage_1", 12, 260, seed=5))
+    # house geometry (208 walls, spawn (-3, 1)) under the reference Env's own hard-coded goal sampler
+    # (environment_new.py:337-345), and a 36-beam scan through its subsampling rule idx_i = int(i*L/10)
+    # (:292-294)
+    np.savez_compressed(os.path.join(GOLD, "env_rollout_house.npz"), **gen_env_rollout("house", 16, 160, 60, seed=11))
+    np.savez_compressed(os.path.join(GOLD, "env_rollout_house_36beams.npz"),
+                        **gen_env_rollout("house", 12, 120, 50, seed=12, num_beams=36))
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
     if "--env-only" not in sys.argv:

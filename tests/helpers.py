@@ -29,4 +29,8 @@ def cfg_from_golden(g, auto_reset=1):
         cfg.max_episode_steps = 1 << 30
     if "arrive_threshold" in g.files:
         cfg.arrive_threshold = float(g["arrive_threshold"])
+    if "start" in g.files:
+        cfg.start_x, cfg.start_y, cfg.start_theta = (float(v) for v in g["start"])
+    if "num_beams" in g.files:
+        cfg.num_beams = int(g["num_beams"])
     return cfg

@@ -20,7 +20,8 @@ def _vec_from_cfg(cfg, segments):
     return VecEnv(cfg.num_agents, map=segments, device=0, cfg=cfg)
 
 
-@pytest.mark.parametrize("name", ["env_rollout_stage_1", "env_rollout_stage_2", "env_rollout_stage_1_eval"])
+@pytest.mark.parametrize("name", ["env_rollout_stage_1", "env_rollout_stage_2", "env_rollout_stage_1_eval",
+                                  "env_rollout_house", "env_rollout_house_36beams"])
 def test_step_matches_reference_golden_rollout(name):
     g = golden(name)
     env = _vec_from_cfg(cfg_from_golden(g, auto_reset=1), g["segments"])

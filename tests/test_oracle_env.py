@@ -7,7 +7,8 @@ from oracle import binding
 from tests.helpers import cfg_from_golden, golden
 
 
-@pytest.mark.parametrize("name", ["env_rollout_stage_1", "env_rollout_stage_2", "env_rollout_stage_1_eval"])
+@pytest.mark.parametrize("name", ["env_rollout_stage_1", "env_rollout_stage_2", "env_rollout_stage_1_eval",
+                                  "env_rollout_house", "env_rollout_house_36beams"])
 def test_oracle_reproduces_reference_rollout(name):
     g = golden(name)
     cfg = cfg_from_golden(g, auto_reset=1)
