@@ -133,7 +133,7 @@ def training_bench(args, torch, dist, dev, rank, world, barrier):
     with tempfile.TemporaryDirectory() as tmp:
         agent = PPO(NetActor, NetCritic, env, 16, 2, timesteps_per_batch=N * H, max_timesteps_per_episode=500,
                     n_updates_per_iteration=args.epochs, gamma=0.99, lr=3e-4, clip=0.2, seed=0, output_dir=tmp,
-                    method_name=f"bench{rank}", verbose=False, precision=prec)
+                    method_name=f"bench{rank}", verbose=False, precision=prec, log_episodes=False)
         l0 = env.launch_count
         batch = agent.rollout([0, 0], 0)            # warm-up iteration
         agent.update(*batch[:4])
@@ -159,7 +159,7 @@ def training_bench(args, torch, dist, dev, rank, world, barrier):
     flops = 3.0 * (98432 + 98368) * N * H * args.epochs       # fwd + bwd of both networks, SURVEY 8(d)
     return {"rollout_env_steps_per_s": steps / (ro_ms * 1e-3), "train_env_steps_per_s": steps / (tot_ms * 1e-3),
             "rollout_ms": ro_ms, "update_ms": up_ms, "iteration_ms": tot_ms, "epochs": args.epochs, "horizon": H,
-            "samples_per_gpu": N * H, "precision": args.precision_one,
+            "samples_per_gpu": N * H, "precision": args.precision_one, "episode_csv": False,
             "update_tflops_per_gpu": flops / (up_ms * 1e-3) / 1e12,
             "final_actor_loss": float(res["actor_losses"][-1]), "final_critic_loss": float(res["critic_losses"][-1]),
             "sim_launches_per_iteration": int(launches_per_iter)}

@@ -103,11 +103,13 @@ int navppo_evaluate(navppo_t* h, const float* params, const float* obs, const fl
  * back to back with no host round trip: for t < H  { act[t], logp[t] = get_action(obs[t]);
  * obs[t+1], rew[t], flags[t] = sim.step(act[t]) }.  obs[H,N,16] must hold the first
  * observation (Env.reset) in row 0; the observation after the last step goes to next_obs[N,16].
- * act[H,N,2], logp[H,N], rew[H,N], done/arrive/trunc[H,N] are the time-major rollout buffers.
+ * act[H,N,2], logp[H,N], rew[H,N], done/arrive/trunc[H,N] are the time-major rollout buffers;
+ * ep_return[H,N] / ep_path[H,N] (both or neither, may be NULL) receive, at the step that ends an
+ * episode, its return and path length (the per-episode csv of ppo.py:739-746).
  * Action noise: Philox counter draw0 + t (see navppo_act). */
 int navppo_rollout(navppo_t* h, navsim_t* sim, const float* params, int32_t H, double var, uint64_t seed,
                    int64_t agent_id_offset, uint32_t draw0, float* obs, float* next_obs, float* act, float* logp, float* rew,
-                   uint8_t* done, uint8_t* arrive, uint8_t* trunc, void* stream);
+                   uint8_t* done, uint8_t* arrive, uint8_t* trunc, float* ep_return, float* ep_path, void* stream);
 
 /* Advantage, ppo.py:277,284, in two halves so a multi-GPU run can all-reduce the three
  * doubles in between: stats[0..2] += (sum, sum of squares, count) of A = rtg - v over T rows;

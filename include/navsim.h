@@ -123,6 +123,21 @@ int navsim_reset(navsim_t* h, const uint8_t* mask_dev, float* obs_dev, void* str
 int navsim_step(navsim_t* h, const float* act_dev, float* obs_dev, float* rew_dev,
                 uint8_t* done_dev, uint8_t* arrive_dev, uint8_t* trunc_dev, void* stream);
 
+/* navsim_step with the optional per-episode outputs: at the step that ends an episode (auto_reset)
+ * ep_return[i] / ep_path[i] receive the episode's return and path length - the `return` and
+ * `path_length` columns of the reference's per-episode csv (ppo.py:739-746); other entries are
+ * left untouched.  trunc, ep_return, ep_path may be NULL (the last two together). */
+typedef struct navsim_step_out {
+  float* obs;          /* [N,16] */
+  float* rew;          /* [N] */
+  uint8_t* done;       /* [N] */
+  uint8_t* arrive;     /* [N] */
+  uint8_t* trunc;      /* [N] or NULL */
+  float* ep_return;    /* [N] or NULL */
+  float* ep_path;      /* [N] or NULL */
+} navsim_step_out;
+int navsim_step_ex(navsim_t* h, const float* act_dev, const navsim_step_out* out, void* stream);
+
 /* Same two calls with HOST buffers: pinned staging, H2D, kernel, D2H, synchronise. */
 int navsim_reset_host(navsim_t* h, const uint8_t* mask_host, float* obs_host);
 int navsim_step_host(navsim_t* h, const float* act_host, float* obs_host, float* rew_host,

@@ -44,6 +44,10 @@ class NavsimCfg(ctypes.Structure):
     ]
 
 
+class NavsimStepOut(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("obs", "rew", "done", "arrive", "trunc", "ep_return", "ep_path")]
+
+
 class NavsimStats(ctypes.Structure):
     _fields_ = [
         ("episodes", ctypes.c_uint64), ("successes", ctypes.c_uint64), ("collisions", ctypes.c_uint64),
@@ -71,6 +75,7 @@ NAVSIM_SYMBOLS = {
     "navsim_set_map": (ctypes.c_int, [_vp, _vp, _i32, _i32]),
     "navsim_reset": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "navsim_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "navsim_step_ex": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "navsim_reset_host": (ctypes.c_int, [_vp, _vp, _vp]),
     "navsim_step_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "navsim_step_scripted": (ctypes.c_int, [_vp, _i32, _u64, _vp, _vp, _vp, _vp, _vp]),
@@ -111,7 +116,7 @@ NAVPPO_SYMBOLS = {
     "navppo_forward": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "navppo_act": (ctypes.c_int, [_vp, _vp, _vp, _i32, _f64, _u64, _i64, _u32, _vp, _vp, _vp, _vp, _vp]),
     "navppo_evaluate": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _f64, _vp, _vp, _vp]),
-    "navppo_rollout": (ctypes.c_int, [_vp, _vp, _vp, _i32, _f64, _u64, _i64, _u32] + [_vp] * 9),
+    "navppo_rollout": (ctypes.c_int, [_vp, _vp, _vp, _i32, _f64, _u64, _i64, _u32] + [_vp] * 11),
     "navppo_adv_stats": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp]),
     "navppo_adv_normalize": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "navppo_grad": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _f64, _vp, _vp, _vp]),

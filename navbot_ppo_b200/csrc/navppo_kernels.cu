@@ -965,7 +965,7 @@ int navppo_adam(navppo_t* h, float* params, const float* grad, float* exp_avg, f
 
 int navppo_rollout(navppo_t* h, navsim_t* sim, const float* params, int32_t H, double var, uint64_t seed,
                    int64_t agent_id_offset, uint32_t draw0, float* obs, float* next_obs, float* act, float* logp, float* rew,
-                   uint8_t* done, uint8_t* arrive, uint8_t* trunc, void* stream) {
+                   uint8_t* done, uint8_t* arrive, uint8_t* trunc, float* ep_return, float* ep_path, void* stream) {
   if (int rc = check_handle(h)) return rc;
   if (!sim || !params || !obs || !next_obs || !act || !logp || !rew || !done || !arrive || !trunc)
     return nav_fail(NAVSIM_EINVAL, "null buffer");
@@ -977,9 +977,12 @@ int navppo_rollout(navppo_t* h, navsim_t* sim, const float* params, int32_t H, d
     if (int rc = navppo_act(h, params, o_t, (int32_t)N, var, seed, agent_id_offset, draw0 + (uint32_t)t, nullptr,
                             act + (size_t)t * N * 2, logp + (size_t)t * N, nullptr, stream))
       return rc;
-    if (int rc = navsim_step(sim, act + (size_t)t * N * 2, o_next, rew + (size_t)t * N, done + (size_t)t * N,
-                             arrive + (size_t)t * N, trunc + (size_t)t * N, stream))
-      return rc;
+    navsim_step_out out;
+    out.obs = o_next; out.rew = rew + (size_t)t * N; out.done = done + (size_t)t * N; out.arrive = arrive + (size_t)t * N;
+    out.trunc = trunc + (size_t)t * N;
+    out.ep_return = ep_return ? ep_return + (size_t)t * N : nullptr;
+    out.ep_path = ep_path ? ep_path + (size_t)t * N : nullptr;
+    if (int rc = navsim_step_ex(sim, act + (size_t)t * N * 2, &out, stream)) return rc;
   }
   return NAVSIM_OK;
 }

@@ -87,6 +87,7 @@ struct StepIO {
   float* obs;         // [N,16]
   float* rew;         // [N]
   uint8_t *done, *arrive, *trunc;  // [N] each, trunc may be null
+  float *ep_ret, *ep_path;         // [N] each or null: return / path length of an episode, written at its last step
   long long obs_stride, vec_stride;
 };
 
@@ -528,6 +529,11 @@ __global__ void __launch_bounds__(kBlock, (G == 1 && KB == NAVSIM_LIDAR_FEATS) ?
         // away by resetting, but the draws it consumed stay consumed
         if (arrive) sample_goal(c, c.respawn_rects, c.n_respawn_rects, agent, &a);
         if (writer) {
+          if (io.ep_ret) {                                           // ppo.py:739-746: the episode's csv row
+            const long long vo = (long long)t * io.vec_stride + i;
+            io.ep_ret[vo] = a.ep_ret;
+            io.ep_path[vo] = a.ep_path;
+          }
           atomicAdd(&stats->episodes, 1ull);
           if (arrive) atomicAdd(&stats->successes, 1ull);            // ppo.py:558-560
           else if (done) atomicAdd(&stats->collisions, 1ull);
@@ -680,6 +686,11 @@ __global__ void __launch_bounds__(kBlock) navsim_step_anybeam_kernel(SimConst c,
       if (done || arrive || timeout) {
         if (arrive) sample_goal(c, c.respawn_rects, c.n_respawn_rects, agent, &a);
         if (writer) {
+          if (io.ep_ret) {
+            const long long vo = (long long)t * io.vec_stride + i;
+            io.ep_ret[vo] = a.ep_ret;
+            io.ep_path[vo] = a.ep_path;
+          }
           atomicAdd(&stats->episodes, 1ull);
           if (arrive) atomicAdd(&stats->successes, 1ull);
           else if (done) atomicAdd(&stats->collisions, 1ull);
@@ -901,6 +912,7 @@ StepIO make_io(const float* act, float* obs, float* rew, uint8_t* done, uint8_t*
                long long obs_stride, long long vec_stride) {
   StepIO io;
   io.act = act; io.obs = obs; io.rew = rew; io.done = done; io.arrive = arrive; io.trunc = trunc;
+  io.ep_ret = nullptr; io.ep_path = nullptr;
   io.obs_stride = obs_stride; io.vec_stride = vec_stride;
   return io;
 }
@@ -1148,6 +1160,17 @@ int navsim_step(navsim_t* h, const float* act_dev, float* obs_dev, float* rew_de
   if (!act_dev || !obs_dev || !rew_dev || !done_dev || !arrive_dev) return fail(NAVSIM_EINVAL, "null buffer");
   return launch_step(h, make_io(act_dev, obs_dev, rew_dev, done_dev, arrive_dev, trunc_dev, 0, 0), (cudaStream_t)stream,
                      false, 0, 1);
+}
+
+int navsim_step_ex(navsim_t* h, const float* act_dev, const navsim_step_out* out, void* stream) {
+  if (int rc = check_ready(h)) return rc;
+  if (!act_dev || !out || !out->obs || !out->rew || !out->done || !out->arrive) return fail(NAVSIM_EINVAL, "null buffer");
+  if ((out->ep_return == nullptr) != (out->ep_path == nullptr))
+    return fail(NAVSIM_EINVAL, "ep_return and ep_path must be given together");
+  StepIO io = make_io(act_dev, out->obs, out->rew, out->done, out->arrive, out->trunc, 0, 0);
+  io.ep_ret = out->ep_return;
+  io.ep_path = out->ep_path;
+  return launch_step(h, io, (cudaStream_t)stream, false, 0, 1);
 }
 
 int navsim_step_scripted(navsim_t* h, int32_t num_steps, uint64_t action_seed, float* obs_dev, float* rew_dev,

@@ -157,6 +157,8 @@ class PPO:
         self.precision = _capi.PREC_FP32
         self.tensorboard = False
         self.verbose = True
+        self.log_episodes = True          # vectorised rollouts: one csv row per completed episode ...
+        self.max_logged_episodes = 4096   # ... up to this many per iteration (None: all)
         for k, v in hyperparameters.items():
             setattr(self, k, v)
         self.config = {k: getattr(self, k) for k in
@@ -177,6 +179,8 @@ class PPO:
         self._b_flags = torch.empty((3, H, N), dtype=torch.uint8, device=d)   # done, arrive, timeout per step
         self._b_term = torch.empty((H, N), dtype=torch.uint8, device=d)
         self._b_rtg = torch.empty((H, N), dtype=torch.float32, device=d)
+        self._b_epret = torch.zeros((H, N), dtype=torch.float32, device=d)    # return / path length of the episode
+        self._b_eppath = torch.zeros((H, N), dtype=torch.float32, device=d)   # that ends at [t, n] (ppo.py:739-746)
         self._next_obs = torch.empty((N, layout.OBS_DIM), dtype=torch.float32, device=d)
 
     def _handle_for(self, T: int):
@@ -320,7 +324,8 @@ class PPO:
         _capi.check(L.navppo_rollout(self._h, env._h, self.flat.data_ptr(), H, self.var, seed, int(env.cfg.agent_id_offset),
                                      self._draw, self._b_obs.data_ptr(), self._next_obs.data_ptr(), self._b_act.data_ptr(),
                                      self._b_logp.data_ptr(), self._b_rew.data_ptr(), self._b_flags[0].data_ptr(),
-                                     self._b_flags[1].data_ptr(), self._b_flags[2].data_ptr(), sp))
+                                     self._b_flags[1].data_ptr(), self._b_flags[2].data_ptr(), self._b_epret.data_ptr(),
+                                     self._b_eppath.data_ptr(), sp))
         self._draw += H
         torch.amax(self._b_flags, dim=0, out=self._b_term)                       # done | arrive | timeout, ppo.py:553
         _capi.check(L.navppo_rtg_scan(self._b_rew.data_ptr(), self._b_term.data_ptr(), None, None, float(self.gamma), 1.0,
@@ -339,6 +344,8 @@ class PPO:
             batch_lens = np.zeros(0, np.int64)
         self.logger["batch_lens"] = batch_lens
         self.logger["batch_rews"] = []
+        if self.log_episodes and tt.size and self.rank == 0:
+            self._log_vec_episodes(t_so_far, nn_, tt, batch_lens)
         T = H * N
         return (self._b_obs.view(T, -1), self._b_act.view(T, 2), self._b_logp.view(T), self._b_rtg.view(T), batch_lens,
                 it, None)
@@ -452,6 +459,28 @@ class PPO:
         with open(self.episode_csv_path, "a", newline="") as f:
             csv.writer(f).writerow([episode_num, timestep, success, collision, timeout, length, ep_return, path_length,
                                     ep_time])
+
+    def _log_vec_episodes(self, t_so_far, agents, steps, lengths):
+        """One csv row per episode completed in this rollout, the reference's columns (ppo.py:739-746).
+        Episodes are listed agent by agent; `timestep` counts completed steps the way the one-robot
+        loop would if it played the agents one after another; `time` is simulated time (0.2 s per
+        step, gazebo.xacro:107) because N robots share the wall clock."""
+        flags = self._b_flags.cpu().numpy()
+        arrive = flags[1][steps, agents].astype(bool)
+        done = flags[0][steps, agents].astype(bool)
+        ret = self._b_epret.cpu().numpy()[steps, agents]
+        path = self._b_eppath.cpu().numpy()[steps, agents]
+        n = len(lengths)
+        if self.max_logged_episodes is not None and n > self.max_logged_episodes:
+            n = int(self.max_logged_episodes)
+        ts = t_so_far + np.cumsum(lengths)
+        with open(self.episode_csv_path, "a", newline="") as f:
+            w = csv.writer(f)
+            for e in range(n):
+                w.writerow([self.episode_count + e, int(ts[e]), int(arrive[e]), int(done[e] and not arrive[e]),
+                            int(not done[e] and not arrive[e]), int(lengths[e]), float(ret[e]), float(path[e]),
+                            0.2 * float(lengths[e])])
+        self.episode_count += len(lengths)
 
     def _log_summary(self):
         """ppo.py:813-946 (condensed): stdout block + the same TensorBoard tags."""

@@ -319,6 +319,20 @@ def test_learn_on_vecenv_trains_and_writes_reference_checkpoints(tmp_path):
     # rollout buffers against the oracle scan of the recorded rewards / flags
     np.testing.assert_allclose(agent._b_rtg.cpu().numpy(), po.rtg_scan(agent._b_rew.cpu().numpy(), agent._b_term.cpu().numpy(), 0.99),
                                rtol=1e-6, atol=1e-4)
+    # per-episode csv (ppo.py:739-746): one row per completed episode, reference columns; the return
+    # column is the sum of the rewards the rollout buffer holds for that episode
+    import csv as _csv
+    rows = list(_csv.reader(open(agent.episode_csv_path)))
+    assert rows[0] == ["episode", "timestep", "success", "collision", "timeout", "length", "return", "path_length", "time"]
+    assert len(rows) - 1 == it["ep_count"] == agent.episode_count
+    rew = agent._b_rew.cpu().numpy(); term = agent._b_term.cpu().numpy()
+    first_end = int(np.nonzero(term[:, 0])[0][0])            # agent 0's first episode is row 0
+    r0 = rows[1]
+    assert int(r0[5]) == first_end + 1 and abs(float(r0[6]) - rew[:first_end + 1, 0].sum()) < 1e-2
+    assert int(r0[2]) + int(r0[3]) + int(r0[4]) == 1 and float(r0[7]) >= 0.0
+    assert sum(int(r[2]) for r in rows[1:]) == it["successes"] and sum(int(r[3]) for r in rows[1:]) == it["collisions"]
+    assert abs(sum(float(r[6]) for r in rows[1:]) - it["return_sum"]) < 1e-3 * max(1.0, abs(it["return_sum"]))
+    assert abs(sum(float(r[7]) for r in rows[1:]) - it["path_sum"]) < 1e-3 * max(1.0, abs(it["path_sum"]))
     # stored log-probs are those of the stored actions under the rollout policy
     V, lp2 = agent.evaluate(obs, acts)
     np.testing.assert_allclose(lp2.cpu().numpy(), logp.cpu().numpy(), atol=1e-4, rtol=1e-5)
