@@ -350,7 +350,7 @@ def main():
                 "single_step_launch_us": single_launch_us,
                 "single_step_launch_env_steps_per_s": N / (single_launch_us * 1e-6)}
     sweep = []
-    if not args.no_sweep:
+    if not args.no_sweep and world == 1:
         for n_big, h_big in ((65536, 64), (1 << 20, 16), (1 << 22, 8)):
             e2 = VecEnv(n_big, map="stage_1", device=local, seed=0)
             e2.reset()
@@ -382,7 +382,7 @@ def main():
 
     # ---- the other BASELINE.json configurations, per GPU (parity-tested in tests/; shown for scale)
     other = []
-    if not args.no_sweep:
+    if not args.no_sweep and world == 1:
         for label, mp, n_c, beams in (("configs[2] stage_2 16384 agents", "stage_2", 16384, 10),
                                       ("configs[4] house 4096 agents/GPU 10 beams", "house", 4096, 10),
                                       ("configs[4] house 4096 agents/GPU 36 beams", "house", 4096, 36)):
@@ -404,9 +404,16 @@ def main():
             e3.close()
             del e3, ob
 
+    # CPU baseline: rank 0 at N = 1 only (the contract); multi-GPU lines carry null
     threads = os.cpu_count() or 1
-    cpu_v, cpu_steps, cpu_dt = cpu_port_throughput(N, args.cpu_seconds, threads)
-    cpu1_v, _, _ = cpu_port_throughput(N, min(3.0, args.cpu_seconds), 1)
+    cpu_baseline = None
+    if world == 1:
+        cpu_v, cpu_steps, cpu_dt = cpu_port_throughput(N, args.cpu_seconds, threads)
+        cpu1_v, _, _ = cpu_port_throughput(N, min(3.0, args.cpu_seconds), 1)
+        cpu_baseline = {"value": cpu_v, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                        "single_core_value": cpu1_v,
+                        "sample": f"{cpu_dt:.1f} s ({cpu_steps} Env.step batches over {N} agents) of the C port "
+                                  f"oracle/navsim_oracle.c on {threads} pthreads"}
 
     line = {
         "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -429,10 +436,7 @@ def main():
         "roofline_sweep": sweep,
         "other_configs": other,
         "training": training,
-        "cpu_baseline": {"value": cpu_v, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                         "single_core_value": cpu1_v,
-                         "sample": f"{cpu_dt:.1f} s ({cpu_steps} Env.step batches over {N} agents) of the C port "
-                                   f"oracle/navsim_oracle.c on {threads} pthreads"},
+        "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
