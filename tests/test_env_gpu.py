@@ -424,3 +424,43 @@ def test_pinned_host_buffers_take_the_zero_copy_path_and_agree():
             np.testing.assert_array_equal(x.cpu().numpy(), y)
             np.testing.assert_array_equal(y, z)
     assert a.stats().episodes == b.stats().episodes > 0
+
+
+def test_step_and_policy_calls_are_cuda_graph_capturable():
+    """include/navsim.h / navppo.h promise graph-capturable device entry points: capture
+    act + step for 4 steps in one CUDA graph, replay it, compare with eager calls."""
+    from navbot_ppo_b200.nets import NetActor, _Handles, _stream
+    n, steps = 1024, 4
+    torch.manual_seed(0)
+    actor = NetActor(16, 2)
+    flat = actor._ensure_bound(torch.device("cuda:0"))
+    h = _Handles.get(torch.device("cuda:0"))
+    L = _capi.lib()
+
+    def run(env, obs, act, logp, rew, done, arrive, trunc, stream_ptr):
+        for t in range(steps):
+            _capi.check(L.navppo_act(h, flat.data_ptr(), obs.data_ptr(), n, 0.8, 0, 0, t, None, act[t].data_ptr(),
+                                     logp[t].data_ptr(), None, stream_ptr))
+            _capi.check(L.navsim_step(env._h, act[t].data_ptr(), obs.data_ptr(), rew[t].data_ptr(), done[t].data_ptr(),
+                                      arrive[t].data_ptr(), trunc[t].data_ptr(), stream_ptr))
+
+    def bufs():
+        return (torch.zeros(steps, n, 2, device="cuda"), torch.zeros(steps, n, device="cuda"), torch.zeros(steps, n, device="cuda"),
+                torch.zeros(steps, n, dtype=torch.uint8, device="cuda"), torch.zeros(steps, n, dtype=torch.uint8, device="cuda"),
+                torch.zeros(steps, n, dtype=torch.uint8, device="cuda"))
+
+    eager, graphed = VecEnv(n, seed=4, max_episode_steps=3), VecEnv(n, seed=4, max_episode_steps=3)
+    o1 = eager.reset().clone(); o2 = graphed.reset().clone()
+    b1, b2 = bufs(), bufs()
+    run(eager, o1, *b1, torch.cuda.current_stream().cuda_stream)
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.graph(g, stream=side):
+        run(graphed, o2, *b2, torch.cuda.current_stream().cuda_stream)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(o1, o2)
+    for x, y in zip(b1, b2):
+        assert torch.equal(x, y)
+    assert b1[3].sum() + b1[4].sum() + b1[5].sum() > 0      # episodes ended (cap 3): auto-reset ran inside the graph
