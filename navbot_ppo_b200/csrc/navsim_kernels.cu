@@ -400,7 +400,7 @@ extern __shared__ __align__(16) unsigned char dyn_smem[];
 //   CW       two-phase wall sweep with a compacted visible-wall list (maps with > kCompactWalls walls).
 // ----------------------------------------------------------------------------------------
 template <int G, int KB, bool SCRIPTED, bool CW>
-__global__ void __launch_bounds__(kBlock, (G == 1 && KB == NAVSIM_LIDAR_FEATS) ? NAVSIM_G1_MINBLOCKS : 1) navsim_step_kernel(SimConst c, SimState st, const float* __restrict__ g_map,
+__global__ void __launch_bounds__(kBlock, KB != NAVSIM_LIDAR_FEATS ? 1 : (G == 1 ? NAVSIM_G1_MINBLOCKS : 4)) navsim_step_kernel(SimConst c, SimState st, const float* __restrict__ g_map,
                                                              const uint16_t* __restrict__ rt_tab, StepIO io,
                                                              DevStats* stats, uint64_t action_seed,
                                                              uint32_t script_step0, int nsteps) {
@@ -429,15 +429,14 @@ __global__ void __launch_bounds__(kBlock, (G == 1 && KB == NAVSIM_LIDAR_FEATS) ?
   Agent a;
   load_agent(st, i, &a);
   bool goal_dirty = false;
+  uint32_t script_words[4] = {0u, 0u, 0u, 0u};   // one Philox block = the scripted actions of two steps
 
   for (int t = 0; t < nsteps; ++t) {
     float a0, a1;
     if (SCRIPTED) {
-      uint32_t o[4];
-      nv_philox4x32_10(script_step0 + (uint32_t)t, 1u, (uint32_t)agent, (uint32_t)(agent >> 32), (uint32_t)action_seed,
-                       (uint32_t)(action_seed >> 32), o);
-      a0 = (float)(o[0] >> 8) * (1.0f / 16777216.0f);
-      a1 = (float)(o[1] >> 8) * (2.0f / 16777216.0f) - 1.0f;
+      const uint32_t sstep = script_step0 + (uint32_t)t;
+      if (t == 0 || (sstep & 1u) == 0u) nv_scripted_block(action_seed, agent, sstep, script_words);
+      nv_scripted_action(script_words, sstep, &a0, &a1);
     } else {
       const float2 av = reinterpret_cast<const float2*>(io.act)[i];
       a0 = av.x; a1 = av.y;
@@ -607,10 +606,9 @@ __global__ void __launch_bounds__(kBlock) navsim_step_anybeam_kernel(SimConst c,
     float a0, a1;
     if (scripted) {
       uint32_t o[4];
-      nv_philox4x32_10(script_step0 + (uint32_t)t, 1u, (uint32_t)agent, (uint32_t)(agent >> 32), (uint32_t)action_seed,
-                       (uint32_t)(action_seed >> 32), o);
-      a0 = (float)(o[0] >> 8) * (1.0f / 16777216.0f);
-      a1 = (float)(o[1] >> 8) * (2.0f / 16777216.0f) - 1.0f;
+      const uint32_t sstep = script_step0 + (uint32_t)t;
+      nv_scripted_block(action_seed, agent, sstep, o);
+      nv_scripted_action(o, sstep, &a0, &a1);
     } else {
       const float2 av = reinterpret_cast<const float2*>(io.act)[i];
       a0 = av.x; a1 = av.y;

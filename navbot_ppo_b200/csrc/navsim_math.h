@@ -210,6 +210,19 @@ NV_HD void nv_goal_uniforms(uint64_t seed, uint64_t agent, uint32_t draw, double
   *uy = nv_u53(o[2], o[3]);
 }
 
+// Scripted benchmark actions a0 ~ U[0,1), a1 ~ U[-1,1): step s of an agent uses words
+// 2 (s & 1), 2 (s & 1) + 1 of the Philox block with counter (s >> 1, 1, agent) keyed by the
+// action seed - one block serves two consecutive steps.
+NV_HD void nv_scripted_block(uint64_t action_seed, uint64_t agent, uint32_t step, uint32_t o[4]) {
+  nv_philox4x32_10(step >> 1, 1u, (uint32_t)agent, (uint32_t)(agent >> 32), (uint32_t)action_seed,
+                   (uint32_t)(action_seed >> 32), o);
+}
+NV_HD void nv_scripted_action(const uint32_t o[4], uint32_t step, float* a0, float* a1) {
+  const uint32_t w0 = (step & 1u) ? o[2] : o[0], w1 = (step & 1u) ? o[3] : o[1];
+  *a0 = (float)(w0 >> 8) * (1.0f / 16777216.0f);
+  *a1 = (float)(w1 >> 8) * (2.0f / 16777216.0f) - 1.0f;
+}
+
 // ---------------------------------------------------------------------------------------
 // Row K — differential drive over one LiDAR period.  The reference's fake node splits
 // (v, w) into wheel speeds and recombines them (turtlebot3_fake.cpp:117-118,150-151);
