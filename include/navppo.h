@@ -79,6 +79,9 @@ int64_t navppo_launch_count(const navppo_t* h);
  * episode: done | arrive | timeout, ppo.py:552-553) and at t = H-1 (no bootstrap, ppo.py:601).
  * With values != NULL it computes GAE(gamma, lam) advantages instead (delta_t = r_t + gamma
  * V_{t+1} - V_t, last_value[N] = V_H or NULL for 0); lam = 1 and zero values give rtg - V.
+ * With values == NULL and last_value != NULL the reward-to-go of the trailing partial episode is
+ * bootstrapped: R_{H-1} = r_{H-1} + gamma last_value (not in the reference; PPO's
+ * `bootstrap_value` option for rollouts that continue episodes across iterations).
  * Accumulates in fp64 like the reference's Python floats, stores fp32 (ppo.py:669). */
 int navppo_rtg_scan(const float* rew, const uint8_t* term, const float* values, const float* last_value, double gamma,
                     double lam, float* out, int32_t H, int32_t N, void* stream);

@@ -49,7 +49,8 @@ __global__ void rtg_scan_kernel(const float* __restrict__ rew, const uint8_t* __
                                 double lam, float* __restrict__ out, int H, int N) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
-  double acc = 0.0;
+  // reward-to-go form with last_value: bootstrap the trailing partial episode from V(s_H)
+  double acc = (!values && last_value) ? (double)last_value[n] : 0.0;
   double next_v = (values && last_value) ? (double)last_value[n] : 0.0;
   for (int t = H - 1; t >= 0; --t) {
     const size_t i = (size_t)t * N + n;

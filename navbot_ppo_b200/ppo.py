@@ -157,6 +157,10 @@ class PPO:
         self.precision = _capi.PREC_FP32
         self.tensorboard = False
         self.verbose = True
+        # vectorised rollouts only, not in the reference (which resets at every rollout, ppo.py:486, and never
+        # bootstraps, :601): keep episodes running across rollouts / bootstrap the cut-off tail from the critic
+        self.continue_episodes = False
+        self.bootstrap_value = False
         self.log_episodes = True          # vectorised rollouts: one csv row per completed episode ...
         self.max_logged_episodes = 4096   # ... up to this many per iteration (None: all)
         for k, v in hyperparameters.items():
@@ -318,7 +322,11 @@ class PPO:
         if t_so_far > 50000 and self.cov_mat[0][0] >= 0.1:   # ppo.py:694-695, once per rollout (episode starts)
             self._decay_cov()
         env.stats(clear=True)
-        obs = env.reset(out=self._b_obs[0])                                      # ppo.py:486
+        if self.continue_episodes and getattr(self, "_rollouts_done", 0) > 0:
+            self._b_obs[0].copy_(self._next_obs)                                 # episodes run on across rollouts
+        else:
+            env.reset(out=self._b_obs[0])                                        # ppo.py:486
+        self._rollouts_done = getattr(self, "_rollouts_done", 0) + 1
         seed = 0 if self.seed is None else int(self.seed)
         # the step loop of ppo.py:505-549 is enqueued by the library: 2 H launches, no Python in between
         _capi.check(L.navppo_rollout(self._h, env._h, self.flat.data_ptr(), H, self.var, seed, int(env.cfg.agent_id_offset),
@@ -328,7 +336,12 @@ class PPO:
                                      self._b_eppath.data_ptr(), sp))
         self._draw += H
         torch.amax(self._b_flags, dim=0, out=self._b_term)                       # done | arrive | timeout, ppo.py:553
-        _capi.check(L.navppo_rtg_scan(self._b_rew.data_ptr(), self._b_term.data_ptr(), None, None, float(self.gamma), 1.0,
+        last_v = None
+        if self.bootstrap_value:
+            with torch.no_grad():
+                last_v = self.critic(self._next_obs).reshape(-1).contiguous()
+        _capi.check(L.navppo_rtg_scan(self._b_rew.data_ptr(), self._b_term.data_ptr(), None,
+                                      None if last_v is None else last_v.data_ptr(), float(self.gamma), 1.0,
                                       self._b_rtg.data_ptr(), H, N, sp))
         st = env.stats()
         it = dict(successes=int(st.successes), collisions=int(st.collisions), timeouts=int(st.timeouts), ep_times=[],

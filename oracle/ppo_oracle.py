@@ -101,14 +101,14 @@ def compute_rtgs(batch_rews, gamma):
     return np.asarray(out, dtype=np.float32)
 
 
-def rtg_scan(rew, term, gamma):
+def rtg_scan(rew, term, gamma, last_value=None):
     """The same recurrence on the vectorised [H, N] layout: `term[t, n]` marks the last step
     of an episode (done | arrive | timeout, ppo.py:552-553); the end of the horizon is a
     boundary too (the trailing partial episode is appended as it is, ppo.py:601)."""
     rew = np.asarray(rew, dtype=np.float64)
     H = rew.shape[0]
     out = np.zeros_like(rew)
-    acc = np.zeros(rew.shape[1:], dtype=np.float64)
+    acc = np.zeros(rew.shape[1:], dtype=np.float64) if last_value is None else np.asarray(last_value, dtype=np.float64).copy()
     for t in range(H - 1, -1, -1):
         acc = np.where(np.asarray(term[t]).astype(bool), 0.0, acc)
         acc = rew[t] + gamma * acc

@@ -69,6 +69,9 @@ def test_rtg_scan_matches_reference_and_oracle():
     out = torch.empty_like(rd)
     _capi.check(_capi.lib().navppo_rtg_scan(rd.data_ptr(), td_.data_ptr(), None, None, 0.99, 1.0, out.data_ptr(), H, N, _sp()))
     np.testing.assert_allclose(out.cpu().numpy(), po.rtg_scan(r, t, 0.99), rtol=1e-6, atol=1e-5)
+    # bootstrapped reward-to-go (PPO's bootstrap_value option)
+    _capi.check(_capi.lib().navppo_rtg_scan(rd.data_ptr(), td_.data_ptr(), None, lvd.data_ptr(), 0.99, 1.0, out.data_ptr(), H, N, _sp()))
+    np.testing.assert_allclose(out.cpu().numpy(), po.rtg_scan(r, t, 0.99, last_value=lv), rtol=1e-6, atol=1e-5)
     _capi.check(_capi.lib().navppo_rtg_scan(rd.data_ptr(), td_.data_ptr(), vd.data_ptr(), lvd.data_ptr(), 0.99, 0.95,
                                             out.data_ptr(), H, N, _sp()))
     np.testing.assert_allclose(out.cpu().numpy(), po.gae_scan(r, t, v, lv, 0.99, 0.95), rtol=1e-5, atol=1e-4)

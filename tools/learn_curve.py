@@ -20,12 +20,14 @@ h = int(sys.argv[3]) if len(sys.argv) > 3 else 128
 epochs = int(sys.argv[4]) if len(sys.argv) > 4 else 50
 prec = {"fp32": _capi.PREC_FP32, "bf16x3": _capi.PREC_BF16X3, "bf16": _capi.PREC_BF16}[sys.argv[5] if len(sys.argv) > 5 else "bf16x3"]
 map_name = sys.argv[6] if len(sys.argv) > 6 else "stage_1"
+cont = len(sys.argv) > 7 and sys.argv[7] == "continue"   # keep episodes across rollouts + bootstrap the tail
 env = VecEnv(n, map=map_name, device=0, seed=0, max_episode_steps=500)
 rows = []
 with tempfile.TemporaryDirectory() as tmp:
     agent = PPO(NetActor, NetCritic, env, 16, 2, timesteps_per_batch=n * h, max_timesteps_per_episode=500,
                 n_updates_per_iteration=epochs, gamma=0.99, lr=3e-4, clip=0.2, seed=0, output_dir=tmp, method_name="curve",
-                verbose=False, precision=prec, log_episodes=False, save_freq=10 ** 9)
+                verbose=False, precision=prec, log_episodes=False, save_freq=10 ** 9, continue_episodes=cont,
+                bootstrap_value=cont)
     t_so_far = 0
     t0 = time.time()
     for it in range(iters):
