@@ -11,14 +11,20 @@
 //   PPO.rollout's episode protocol (auto-reset)       (ppo.py:549-593)
 //   Env.reset + goal sampling                         (:312-382)
 //
+// Execution model: G lanes (1..32, a power of two chosen from N and the map) cooperate on one
+// agent; a launch runs `nsteps` consecutive steps with the agent state in registers (agents
+// never interact, so no grid-wide synchronisation exists) and writes every step's observation,
+// reward and flags - into the same [N, .] arrays, or into the time-major [H, N, .] rollout
+// buffers.  See navsim_step_kernel below and DESIGN.md section 4.1.
+//
 // Data layout in HBM: structure-of-arrays, one array per state field, agent index fastest,
-// so a warp's 32 agents read/write one contiguous 128/256-byte run per field.  Pose, goal
-// and past_distance are fp64 because the reference computes in Python floats and quantises
-// (see navsim_math.h); the outputs the policy consumes (obs, reward) are fp32 as ppo.py:616
-// casts them.  The obstacle set (beam table + wall segments, a few hundred bytes to a few
-// KB) is staged into shared memory once per CTA with one TMA bulk copy (cp.async.bulk +
-// mbarrier) and read as warp-wide broadcasts.  The observation tile is transposed through
-// shared memory so the [N,16] fp32 rows leave as full 128-bit coalesced stores.
+// so a warp's agents read/write one contiguous run per field.  Pose, goal and past_distance
+// are fp64 because the reference computes in Python floats and quantises (see navsim_math.h);
+// the outputs the policy consumes (obs, reward) are fp32 as ppo.py:616 casts them.  The
+// obstacle set (wall segments, beam table, spawn-pose scan: a few hundred bytes to a few KB)
+// is staged into shared memory once per CTA with one TMA bulk copy (cp.async.bulk + mbarrier),
+// waited on only where the first ray is cast, and read as warp-wide broadcasts.  Observation
+// rows are assembled in shared memory and leave as 128-bit stores, one warp's agents at a time.
 //
 // Compile with -fmad=false: the physics must round exactly like the host build of
 // navsim_math.h that drives the reference Env in the oracle.
