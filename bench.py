@@ -389,6 +389,8 @@ def main():
             e3 = VecEnv(n_c, map=mp, device=local, seed=0, num_beams=beams)
             e3.reset()
             ob = e3.rollout_scripted(H, 0)
+            for _ in range(3):                      # let the robots leave the common spawn pose
+                e3.rollout_scripted(H, 0, out=ob)
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
