@@ -464,3 +464,56 @@ def test_step_and_policy_calls_are_cuda_graph_capturable():
     for x, y in zip(b1, b2):
         assert torch.equal(x, y)
     assert b1[3].sum() + b1[4].sum() + b1[5].sum() > 0      # episodes ended (cap 3): auto-reset ran inside the graph
+
+
+@pytest.mark.parametrize("beams,n,lanes", [(1, 33, 0), (2, 31, 16), (3, 1, 0), (11, 257, 4), (37, 65, 0)])
+def test_odd_beam_counts_and_ragged_batches(beams, n, lanes):
+    """Edge shapes: 1 / 2 / 3 beams (lidar features repeat beams, idx_i = int(i * L / 10)), 11 and 37
+    beams (first counts of the padded and the warp-per-agent variants), batch sizes that do not fill a
+    warp or a CTA."""
+    cfg = _capi.default_cfg(n)
+    cfg.num_beams, cfg.seed, cfg.max_episode_steps, cfg.lanes_per_agent = beams, 31, 15, lanes
+    seg = maps.get_map("stage_2")
+    env = _vec_from_cfg(cfg, seg)
+    sim = binding.OracleSim(cfg, seg)
+    np.testing.assert_allclose(env.reset().cpu().numpy(), sim.reset(), atol=OBS_ATOL, rtol=0)
+    for t in range(40):
+        act = binding.scripted_actions(5, 0, t, n)
+        act[:, 0] = np.maximum(act[:, 0], 0.8)
+        o_ref, r_ref, d_ref, a_ref, tr_ref = sim.step(act)
+        obs, rew, done, arrive = env.step(torch.from_numpy(act).cuda())
+        np.testing.assert_array_equal(done.cpu().numpy(), d_ref, err_msg=f"done t={t}")
+        np.testing.assert_array_equal(arrive.cpu().numpy(), a_ref)
+        np.testing.assert_array_equal(env.trunc.cpu().numpy(), tr_ref)
+        np.testing.assert_allclose(obs.cpu().numpy(), o_ref, atol=OBS_ATOL, rtol=0, err_msg=f"obs t={t}")
+        np.testing.assert_allclose(rew.cpu().numpy(), r_ref, atol=REW_ATOL, rtol=0)
+    np.testing.assert_array_equal(env.get_state(_capi.F_X), sim.arr["x"])
+    out = env.rollout_scripted(1, action_seed=3)          # a one-step fused launch
+    o_ref, *_ = sim.step(binding.scripted_actions(3, 0, 0, n))
+    np.testing.assert_allclose(out["obs"][0].cpu().numpy(), o_ref, atol=OBS_ATOL, rtol=0)
+
+
+def test_open_world_single_wall_and_oversized_map():
+    """One free-standing two-sided wall (no closed boxes): beams see it from both sides; robots
+    that drive away never collide.  A map that cannot fit in shared memory is refused."""
+    n = 200
+    cfg = _capi.default_cfg(n)
+    cfg.seed, cfg.max_episode_steps = 2, 30
+    wall = np.array([[1.0, -2.0, 1.0, 2.0]])
+    env = VecEnv(n, map=wall, cfg=cfg, closed_boxes=False)
+    sim = binding.OracleSim(cfg, wall, closed_boxes=False)
+    np.testing.assert_allclose(env.reset().cpu().numpy(), sim.reset(), atol=OBS_ATOL, rtol=0)
+    hits = 0
+    for t in range(60):
+        act = binding.scripted_actions(9, 0, t, n)
+        act[: n // 2, 0] = 1.0; act[: n // 2, 1] = 0.0        # half the robots drive straight at the wall
+        o_ref, r_ref, d_ref, a_ref, tr_ref = sim.step(act)
+        obs, rew, done, arrive = env.step(torch.from_numpy(act).cuda())
+        np.testing.assert_array_equal(done.cpu().numpy(), d_ref, err_msg=f"t={t}")
+        np.testing.assert_allclose(obs.cpu().numpy(), o_ref, atol=OBS_ATOL, rtol=0, err_msg=f"t={t}")
+        hits += int(d_ref.sum())
+    assert hits > 0
+    np.testing.assert_array_equal(env.scan().cpu().numpy(), sim.scan())
+    big = maps.synthetic_map(8000, seed=1, extent=60.0)     # 32,000 walls = 1 MB of wall records
+    with pytest.raises(_capi.NavError):
+        VecEnv(16, map=big)
