@@ -158,10 +158,29 @@ def _floats(text):
     return [float(t) for t in re.split(r"\s+", text.strip()) if t]
 
 
-def compile_sdf(path: str, model: str | None = None, z_plane: float = LIDAR_Z):
+def polygon_segments(cx: float, cy: float, radius: float, sides: int = 16) -> np.ndarray:
+    """Counter-clockwise regular polygon circumscribing a circle (an upright cylinder cut by the
+    LiDAR plane): `sides` wall segments, closed, so it can share a map with box obstacles."""
+    r = radius / math.cos(math.pi / sides)          # the circle touches every edge from inside
+    pts = [(cx + r * math.cos(2 * math.pi * k / sides), cy + r * math.sin(2 * math.pi * k / sides)) for k in range(sides)]
+    return np.asarray([(*pts[k], *pts[(k + 1) % sides]) for k in range(sides)], dtype=np.float64)
+
+
+def compile_sdf_segments(path: str, model: str | None = None, z_plane: float = LIDAR_Z, cylinder_sides: int = 16) -> np.ndarray:
+    """SDF world/model -> wall segments of every box AND cylinder collision crossing `z_plane`
+    (cylinders as circumscribed `cylinder_sides`-gons).  Mesh collisions are not handled."""
+    segs = [boxes_to_segments(compile_sdf(path, model, z_plane))]
+    for cx, cy, radius in compile_sdf(path, model, z_plane, want="cylinder"):
+        segs.append(polygon_segments(cx, cy, radius, cylinder_sides))
+    segs = [s for s in segs if len(s)]
+    return np.concatenate(segs) if segs else np.zeros((0, 4))
+
+
+def compile_sdf(path: str, model: str | None = None, z_plane: float = LIDAR_Z, want: str = "box"):
     """SDF world/model -> list of (cx, cy, sx, sy, yaw) for every box *collision* whose
-    z-extent contains `z_plane`.  Handles model pose + link pose + collision pose with
-    yaw-only rotations (all walls in the reference's worlds are upright boxes)."""
+    z-extent contains `z_plane` (want="cylinder": list of (cx, cy, radius) for upright
+    cylinders).  Handles model pose + link pose + collision pose with yaw-only rotations (all
+    walls in the reference's worlds are upright boxes)."""
     root = ET.parse(path).getroot()
     out = []
     for mdl in root.iter("model"):
@@ -174,9 +193,17 @@ def compile_sdf(path: str, model: str | None = None, z_plane: float = LIDAR_Z):
             lp = _floats(lpose.text) if lpose is not None else [0.0] * 6
             for col in link.findall("collision"):
                 box = col.find("geometry/box/size")
-                if box is None:
-                    continue
-                sx, sy, sz = _floats(box.text)
+                cyl = col.find("geometry/cylinder")
+                if want == "cylinder":
+                    if cyl is None:
+                        continue
+                    rad = float(cyl.find("radius").text)
+                    sx = sy = 2.0 * rad
+                    sz = float(cyl.find("length").text)
+                else:
+                    if box is None:
+                        continue
+                    sx, sy, sz = _floats(box.text)
                 cpose = col.find("pose")
                 cp = _floats(cpose.text) if cpose is not None else [0.0] * 6
                 # compose planar transforms model * link * collision
@@ -190,7 +217,7 @@ def compile_sdf(path: str, model: str | None = None, z_plane: float = LIDAR_Z):
                     continue
                 if sx >= 50 or sy >= 50:  # ground plane
                     continue
-                out.append((x, y, sx, sy, yaw))
+                out.append((x, y, sx / 2.0) if want == "cylinder" else (x, y, sx, sy, yaw))
         if model is not None:
             break
     return out
