@@ -162,18 +162,23 @@ __device__ __forceinline__ void stage_map(float* s_map, const float* g_map, uint
   }
 }
 
-// every thread waits for phase 0 of the barrier (called after the state loads are in flight)
+// Wait for phase 0 of the barrier.  Only the first warp polls it (a polling loop costs issue
+// slots; bar.sync does not); the CTA barrier then publishes the map to everyone.  Must be
+// called by all threads of the CTA.
 __device__ __forceinline__ void wait_map(uint64_t* bar) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_MAP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
-      "@p bra DONE_MAP;\n"
-      "bra WAIT_MAP;\n"
-      "DONE_MAP:\n"
-      "}\n" ::"r"(smem_u32(bar))
-      : "memory");
+  if (threadIdx.x < 32) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_MAP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra DONE_MAP;\n"
+        "bra WAIT_MAP;\n"
+        "DONE_MAP:\n"
+        "}\n" ::"r"(smem_u32(bar))
+        : "memory");
+  }
+  __syncthreads();
 }
 
 // ----------------------------------------------------------------------------------------
