@@ -16,7 +16,7 @@
 // Operands are BF16 in shared memory in the dual-use row-block tile format of tc_common.cuh
 // (every activation / weight tile is stored ONCE and read K-major by the products that
 // contract over features / hidden units and MN-major by those that contract over samples);
-// accumulators are fp32 in TMEM (400 of 512 columns).  Arithmetic modes: PASSES = 1 plain
+// accumulators are fp32 in TMEM (480 of 512 columns; the weight-gradient accumulators are double buffered).  Arithmetic modes: PASSES = 1 plain
 // bf16 x bf16; PASSES = 3 split operands x = hi + lo (two bf16 tiles) and hi*hi + lo*hi +
 // hi*lo, about 16 mantissa bits (5e-6 relative in the self-test) at 3 MMAs per step.
 // Elementwise work between the products (bias, LeakyReLU and its derivative, heads, losses)
@@ -103,7 +103,10 @@ constexpr uint32_t OFF_MISC = OFF_RED + 4 * 128 * 4;        // barriers, tmem ba
 constexpr uint32_t TC_SMEM_BYTES = OFF_MISC + 64;           // 227,392 B of the 232,448 B a CTA may have
 
 // TMEM columns
-constexpr uint32_t TM_Z = 0, TM_GH = 128, TM_DWA = 256, TM_DWB = 304, TM_U = 336, TM_GX = 368, TM_COLS = 512;
+// the weight-gradient accumulators are double buffered (chunk c -> buffer c & 1) so that chunk c - 1 can be
+// flushed while the tensor pipe works on chunk c
+constexpr uint32_t TM_Z = 0, TM_GH = 128, TM_DWA = 256, TM_DWB = 304, TM_U = 336, TM_GX = 368, TM_DW2 = 144,
+                   TM_COLS = 512;   // second buffer: TM_DWA + 144 = 400, TM_DWB + 144 = 448 .. 480
 
 struct TcGradArgs {
   GradArgs g;
@@ -433,18 +436,18 @@ __global__ void __launch_bounds__(256, 1) mlp_grad_tc_kernel(TcGradArgs ta) {
           float* ga = grow + o_wa + j * IN;
           for (int c0 = 0; c0 < IN; c0 += 16) {
             float v[16];
-            tc::tmem_ld16(trow + TM_DWA + c0, v);
+            tc::tmem_ld16(trow + TM_DWA + (c & 1) * TM_DW2 + c0, v);
 #pragma unroll
             for (int i = 0; i < 4; ++i) red_add4(ga + c0 + 4 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           }
           float v[16];
-          tc::tmem_ld16(trow + TM_DWA + 32, v);       // column 32 = sum over samples of g_z = bias gradient
+          tc::tmem_ld16(trow + TM_DWA + (c & 1) * TM_DW2 + 32, v);       // column 32 = sum over samples of g_z = bias gradient
           red_add1(grow + o_ba + j, v[0]);
         } else {
           float* gb = grow + o_wb + j * IN;            // kernel layout: fc2 transposed
           for (int c0 = 0; c0 < IN; c0 += 16) {
             float v[16];
-            tc::tmem_ld16(trow + TM_DWB + c0, v);
+            tc::tmem_ld16(trow + TM_DWB + (c & 1) * TM_DW2 + c0, v);
 #pragma unroll
             for (int i = 0; i < 4; ++i) red_add4(gb + c0 + 4 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           }
@@ -467,7 +470,6 @@ __global__ void __launch_bounds__(256, 1) mlp_grad_tc_kernel(TcGradArgs ta) {
           load_wb(blk, c + 1);                      // GH(c) done: the fc2 buffer is free
           load_wa(blk, c + 1);                      // ring slot (c+1)&1 was last read by Z / GX of c-1
         }
-        if (c > 0) flush_dw(c - 1);
         {  // H = lrelu(z), GZ = GH * lrelu'(z), z = Z + ba
           const float* sBa = sBias + blk * HID + c * CHUNK;
 #pragma unroll 1
@@ -498,10 +500,10 @@ __global__ void __launch_bounds__(256, 1) mlp_grad_tc_kernel(TcGradArgs ta) {
                                CHUNK / 16, c > 0);
           }
           // dWa = GZ^T [X | 1] : both operands MN-major (rows = K = samples)
-          issue_gemm<PASSES>(tmem + TM_DWA, aGZ, aGZ + SH_PART, 128, ROWG, 256, 1, aX, aX + SX_PART, 128, ROWG, 256, 1, XCOLS,
+          issue_gemm<PASSES>(tmem + TM_DWA + (c & 1) * TM_DW2, aGZ, aGZ + SH_PART, 128, ROWG, 256, 1, aX, aX + SX_PART, 128, ROWG, 256, 1, XCOLS,
                              128 / 16, false);
           // dWbT = H^T GU
-          issue_gemm<PASSES>(tmem + TM_DWB, aH, aH + SH_PART, 128, ROWG, 256, 1, aGU, aGU + SGU_PART, 128, ROWG, 256, 1, IN,
+          issue_gemm<PASSES>(tmem + TM_DWB + (c & 1) * TM_DW2, aH, aH + SH_PART, 128, ROWG, 256, 1, aGU, aGU + SGU_PART, 128, ROWG, 256, 1, IN,
                              128 / 16, false);
           if (c + 1 < NCHUNK) {                     // next chunk's phase 1 rides on the same commit
             wait_wa(c + 1);
@@ -510,6 +512,9 @@ __global__ void __launch_bounds__(256, 1) mlp_grad_tc_kernel(TcGradArgs ta) {
           }
           tc::mma_commit(mbar);
         }
+        // the previous chunk's weight gradients sit complete in the other TMEM buffer: flush them
+        // while the tensor pipe runs the MMAs just issued
+        if (c > 0) flush_dw(c - 1);
       }
       tc::mbar_wait(mbar, mphase); mphase ^= 1;     // phase 2 of the last chunk complete
       tc::fence_after_sync();
