@@ -143,6 +143,17 @@ int navsim_reset_host(navsim_t* h, const uint8_t* mask_host, float* obs_host);
 int navsim_step_host(navsim_t* h, const float* act_host, float* obs_host, float* rew_host,
                      uint8_t* done_host, uint8_t* arrive_host, uint8_t* trunc_host);
 
+/* The one-robot calling convention of the reference, Env.step(action, past_action) /
+ * Env.reset() followed by reads of env.position / env.goal_position / env.past_distance
+ * (environment_new.py:272,299-300; ppo.py:535, main.py:202), in ONE launch and one
+ * synchronisation: past_act_host[N,2] (may be NULL) replaces the simulator's own copy of the
+ * previous action before the step; pose_host[N,6] doubles (may be NULL) receives x, y, theta,
+ * goal x, goal y, past_distance after the step / reset. */
+int navsim_step_host_ex(navsim_t* h, const float* act_host, const float* past_act_host, float* obs_host,
+                        float* rew_host, uint8_t* done_host, uint8_t* arrive_host, uint8_t* trunc_host,
+                        double* pose_host);
+int navsim_reset_host_ex(navsim_t* h, const uint8_t* mask_host, float* obs_host, double* pose_host);
+
 /* Scripted-action driver used by benchmarks: `num_steps` consecutive steps in ONE launch with
  * actions a0~U[0,1], a1~U[-1,1] drawn on device (Philox, key action_seed); every step
  * overwrites the [N,.] output arrays, which end up holding the last step's results. */

@@ -94,6 +94,8 @@ struct StepIO {
   float* rew;         // [N]
   uint8_t *done, *arrive, *trunc;  // [N] each, trunc may be null
   float *ep_ret, *ep_path;         // [N] each or null: return / path length of an episode, written at its last step
+  const float* past_act;           // [N,2] or null: the caller's previous action replaces the simulator's copy
+  double* pose_out;                // [N,6] or null: x, y, theta, goal x, goal y, past_distance after the step
   long long obs_stride, vec_stride;
 };
 
@@ -439,6 +441,10 @@ __global__ void __launch_bounds__(kBlock, KB != NAVSIM_LIDAR_FEATS ? 1 : (G == 1
   float* my_obs = s_obs + slot * kObsPad;
   Agent a;
   load_agent(st, i, &a);
+  if (io.past_act) {   // Env.step(action, past_action): the caller owns the previous action (environment_new.py:272,299)
+    const float2 pv = reinterpret_cast<const float2*>(io.past_act)[i];
+    a.pa0 = pv.x; a.pa1 = pv.y;
+  }
   bool goal_dirty = false;
   uint32_t script_words[4] = {0u, 0u, 0u, 0u};   // one Philox block = the scripted actions of two steps
 
@@ -581,7 +587,13 @@ __global__ void __launch_bounds__(kBlock, KB != NAVSIM_LIDAR_FEATS ? 1 : (G == 1
     }
     __syncwarp();
   }
-  if (writer) store_agent(st, i, a, goal_dirty);
+  if (writer) {
+    store_agent(st, i, a, goal_dirty);
+    if (io.pose_out) {
+      double* po = io.pose_out + (size_t)i * 6;
+      po[0] = a.x; po[1] = a.y; po[2] = a.th; po[3] = a.gx; po[4] = a.gy; po[5] = a.past;
+    }
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats->steps, (unsigned long long)c.N * (unsigned long long)nsteps);
 }
 
@@ -610,6 +622,10 @@ __global__ void __launch_bounds__(kBlock) navsim_step_anybeam_kernel(SimConst c,
   float* my_obs = s_obs + slot * kObsPad;
   Agent a;
   load_agent(st, i, &a);
+  if (io.past_act) {
+    const float2 pv = reinterpret_cast<const float2*>(io.past_act)[i];
+    a.pa0 = pv.x; a.pa1 = pv.y;
+  }
   wait_map(bar);
   bool goal_dirty = false;
   for (int t = 0; t < nsteps; ++t) {
@@ -723,14 +739,21 @@ __global__ void __launch_bounds__(kBlock) navsim_step_anybeam_kernel(SimConst c,
           make_float4(my_obs[4 * g], my_obs[4 * g + 1], my_obs[4 * g + 2], my_obs[4 * g + 3]);
     __syncwarp();
   }
-  if (writer) store_agent(st, i, a, goal_dirty);
+  if (writer) {
+    store_agent(st, i, a, goal_dirty);
+    if (io.pose_out) {
+      double* po = io.pose_out + (size_t)i * 6;
+      po[0] = a.x; po[1] = a.y; po[2] = a.th; po[3] = a.gx; po[4] = a.gy; po[5] = a.past;
+    }
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats->steps, (unsigned long long)c.N * (unsigned long long)nsteps);
 }
 
 // Env.reset for the masked agents (thread per agent).
 __global__ void __launch_bounds__(kBlock) navsim_reset_kernel(SimConst c, SimState st, const float* __restrict__ g_map,
                                                               const uint16_t* __restrict__ rt_tab,
-                                                              const uint8_t* __restrict__ mask, float* __restrict__ obs) {
+                                                              const uint8_t* __restrict__ mask, float* __restrict__ obs,
+                                                              double* __restrict__ pose_out) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(dyn_smem);
   float* s_map = reinterpret_cast<float*>(dyn_smem + 16);
   const uint32_t map_bytes = map_bytes_of(c.B, c.S);
@@ -745,6 +768,10 @@ __global__ void __launch_bounds__(kBlock) navsim_reset_kernel(SimConst c, SimSta
   load_agent(st, i, &a);
   reset_agent(c, map_view(s_map, c.B, c.S), rt_tab, (uint64_t)(c.agent_off + i), &a, my_obs, true, 1, 0);
   store_agent(st, i, a, true);
+  if (pose_out) {
+    double* po = pose_out + (size_t)i * 6;
+    po[0] = a.x; po[1] = a.y; po[2] = a.th; po[3] = a.gx; po[4] = a.gy; po[5] = a.past;
+  }
   if (obs) {
     float4* dst = reinterpret_cast<float4*>(obs + (size_t)i * NAVSIM_OBS_DIM);
     for (int q = 0; q < 4; ++q) dst[q] = make_float4(my_obs[4 * q], my_obs[4 * q + 1], my_obs[4 * q + 2], my_obs[4 * q + 3]);
@@ -798,6 +825,10 @@ struct navsim {
   const void* pin_seen[2] = {nullptr, nullptr};  // last caller buffers of navsim_step_host (actions, obs)
   const float* pin_alias[2] = {nullptr, nullptr};
   float* h_rew_dev = nullptr;    // device alias of the pinned h_rew block (reward + flags)
+  // navsim_*_host_ex: mapped pinned blocks for the caller-owned previous action and the pose read-back
+  float *h_past = nullptr, *h_past_dev = nullptr;        // [N,2]
+  double *h_pose = nullptr, *h_pose_dev = nullptr;       // [N,6]
+  double* reset_pose_out = nullptr;                      // set around a navsim_reset_host_ex launch
 };
 
 namespace {
@@ -921,7 +952,7 @@ StepIO make_io(const float* act, float* obs, float* rew, uint8_t* done, uint8_t*
                long long obs_stride, long long vec_stride) {
   StepIO io;
   io.act = act; io.obs = obs; io.rew = rew; io.done = done; io.arrive = arrive; io.trunc = trunc;
-  io.ep_ret = nullptr; io.ep_path = nullptr;
+  io.ep_ret = nullptr; io.ep_path = nullptr; io.past_act = nullptr; io.pose_out = nullptr;
   io.obs_stride = obs_stride; io.vec_stride = vec_stride;
   return io;
 }
@@ -1041,6 +1072,13 @@ int navsim_create(navsim_t** out, const navsim_cfg* cfg) {
     if (cudaHostGetDevicePointer(&dp, h->h_rew, 0) == cudaSuccess) h->h_rew_dev = static_cast<float*>(dp);
     else cudaGetLastError();
   }
+  TRY_OR_CLEAN(cudaMallocHost(&h->h_past, N * 2 * sizeof(float)));
+  TRY_OR_CLEAN(cudaMallocHost(&h->h_pose, N * 6 * sizeof(double)));
+  {
+    void* dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, h->h_past, 0) == cudaSuccess) h->h_past_dev = static_cast<float*>(dp); else cudaGetLastError();
+    if (cudaHostGetDevicePointer(&dp, h->h_pose, 0) == cudaSuccess) h->h_pose_dev = static_cast<double*>(dp); else cudaGetLastError();
+  }
   TRY_OR_CLEAN(cudaMalloc(&h->d_act, N * 2 * sizeof(float)));
   TRY_OR_CLEAN(cudaMalloc(&h->d_obs, N * NAVSIM_OBS_DIM * sizeof(float)));
   TRY_OR_CLEAN(cudaMalloc(&h->d_rew, N * sizeof(float) + N * 3));
@@ -1061,6 +1099,8 @@ int navsim_destroy(navsim_t* h) {
   if (h->h_act) cudaFreeHost(h->h_act);
   if (h->h_obs) cudaFreeHost(h->h_obs);
   if (h->h_rew) cudaFreeHost(h->h_rew);
+  if (h->h_past) cudaFreeHost(h->h_past);
+  if (h->h_pose) cudaFreeHost(h->h_pose);
   if (h->d_act) cudaFree(h->d_act);
   if (h->d_obs) cudaFree(h->d_obs);
   if (h->d_rew) cudaFree(h->d_rew);
@@ -1157,7 +1197,7 @@ int navsim_set_map(navsim_t* h, const double* seg_host, int32_t num_segments, in
 int navsim_reset(navsim_t* h, const uint8_t* mask_dev, float* obs_dev, void* stream) {
   if (int rc = check_ready(h)) return rc;
   navsim_reset_kernel<<<aux_grid_of(h), kBlock, aux_smem_bytes(h), (cudaStream_t)stream>>>(h->c, h->st, h->d_map, h->d_rt,
-                                                                                         mask_dev, obs_dev);
+                                                                                         mask_dev, obs_dev, h->reset_pose_out);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
   return NAVSIM_OK;
@@ -1218,6 +1258,55 @@ int navsim_reset_host(navsim_t* h, const uint8_t* mask_host, float* obs_host) {
     for (size_t i = 0; i < N; ++i)
       if (mask_host[i]) memcpy(obs_host + i * NAVSIM_OBS_DIM, h->h_obs + i * NAVSIM_OBS_DIM, NAVSIM_OBS_DIM * sizeof(float));
   }
+  return NAVSIM_OK;
+}
+
+int navsim_reset_host_ex(navsim_t* h, const uint8_t* mask_host, float* obs_host, double* pose_host) {
+  if (!h) return fail(NAVSIM_EINVAL, "null handle");
+  if (pose_host && !h->h_pose_dev) return fail(NAVSIM_ECUDA, "mapped host memory is not available on this device");
+  h->reset_pose_out = pose_host ? h->h_pose_dev : nullptr;
+  const int rc = navsim_reset_host(h, mask_host, obs_host);
+  h->reset_pose_out = nullptr;
+  if (rc == NAVSIM_OK && pose_host) {
+    const size_t N = (size_t)h->c.N;
+    if (!mask_host) memcpy(pose_host, h->h_pose, N * 6 * sizeof(double));
+    else
+      for (size_t i = 0; i < N; ++i)
+        if (mask_host[i]) memcpy(pose_host + 6 * i, h->h_pose + 6 * i, 6 * sizeof(double));
+  }
+  return rc;
+}
+
+int navsim_step_host_ex(navsim_t* h, const float* act_host, const float* past_act_host, float* obs_host, float* rew_host,
+                        uint8_t* done_host, uint8_t* arrive_host, uint8_t* trunc_host, double* pose_host) {
+  if (int rc = check_ready(h)) return rc;
+  if (!act_host || !obs_host || !rew_host || !done_host || !arrive_host) return fail(NAVSIM_EINVAL, "null buffer");
+  if (!h->h_rew_dev || !h->h_past_dev || !h->h_pose_dev)
+    return fail(NAVSIM_ECUDA, "mapped host memory is not available on this device");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const size_t N = (size_t)h->c.N;
+  cudaStream_t s = h->own_stream;
+  // everything through mapped pinned blocks: one launch, one synchronisation
+  memcpy(h->h_act, act_host, N * 2 * sizeof(float));
+  if (past_act_host) memcpy(h->h_past, past_act_host, N * 2 * sizeof(float));
+  void* act_alias = nullptr;
+  CUDA_TRY(cudaHostGetDevicePointer(&act_alias, h->h_act, 0));
+  void* obs_alias = nullptr;
+  CUDA_TRY(cudaHostGetDevicePointer(&obs_alias, h->h_obs, 0));
+  float* rew_dev = h->h_rew_dev;
+  uint8_t* fl_dev = reinterpret_cast<uint8_t*>(rew_dev + N);
+  StepIO io = make_io(static_cast<const float*>(act_alias), static_cast<float*>(obs_alias), rew_dev, fl_dev, fl_dev + N,
+                      fl_dev + 2 * N, 0, 0);
+  io.past_act = past_act_host ? h->h_past_dev : nullptr;
+  io.pose_out = pose_host ? h->h_pose_dev : nullptr;
+  if (int rc = launch_step(h, io, s, false, 0, 1)) return rc;
+  CUDA_TRY(cudaStreamSynchronize(s));
+  memcpy(obs_host, h->h_obs, N * NAVSIM_OBS_DIM * sizeof(float));
+  memcpy(rew_host, h->h_rew, N * sizeof(float));
+  memcpy(done_host, h->h_flags, N);
+  memcpy(arrive_host, h->h_flags + N, N);
+  if (trunc_host) memcpy(trunc_host, h->h_flags + 2 * N, N);
+  if (pose_host) memcpy(pose_host, h->h_pose, N * 6 * sizeof(double));
   return NAVSIM_OK;
 }
 

@@ -220,31 +220,39 @@ class Env:
         self._vec = VecEnv(1, map=map, device=device, seed=seed, auto_reset=False, is_training=is_training,
                            max_episode_steps=1 << 30)
         self.threshold_arrive = 0.2 if is_training else 0.4
+        # one C call per reset / step (navsim_*_host_ex): action, caller-owned previous action in; observation,
+        # reward, flags and the pose block out
+        self._L = _capi.lib()
+        self._step_ex = self._L.navsim_step_host_ex
+        self._act, self._past = np.zeros((1, 2), np.float32), np.zeros((1, 2), np.float32)
+        self._obs, self._rew = np.zeros((1, 16), np.float32), np.zeros(1, np.float32)
+        self._done, self._arrive, self._trunc = np.zeros(1, np.uint8), np.zeros(1, np.uint8), np.zeros(1, np.uint8)
+        self._pose = np.zeros((1, 6), np.float64)
+        self._ptrs = tuple(int(x.__array_interface__["data"][0]) for x in
+                           (self._act, self._past, self._obs, self._rew, self._done, self._arrive, self._trunc, self._pose))
         self.position = SimpleNamespace(x=0.0, y=0.0, z=0.0)
         self.goal_position = SimpleNamespace(position=SimpleNamespace(x=0.0, y=0.0, z=0.01))
         self.past_distance = 0.0
 
-    def _sync_public_state(self):
-        v = self._vec
-        self.position.x = float(v.get_state(_capi.F_X)[0])
-        self.position.y = float(v.get_state(_capi.F_Y)[0])
-        self.goal_position.position.x = float(v.get_state(_capi.F_GOAL_X)[0])
-        self.goal_position.position.y = float(v.get_state(_capi.F_GOAL_Y)[0])
-        self.past_distance = float(v.get_state(_capi.F_PAST_DIST)[0])
+    def _publish(self):
+        """env.position / env.goal_position / env.past_distance (read by ppo.py:535, main.py:202) from the
+        pose block the last call returned."""
+        x, y, _th, gx, gy, past = (float(v) for v in self._pose[0])
+        self.position.x, self.position.y = x, y
+        self.goal_position.position.x, self.goal_position.position.y = gx, gy
+        self.past_distance = past
 
     def getLatestImage(self):
         return None
 
     def reset(self):
-        obs = self._vec.reset_host()[0].astype(np.float64)
-        self._sync_public_state()
-        return obs
+        _capi.check(self._L.navsim_reset_host_ex(self._vec._h, None, self._obs.ctypes.data, self._pose.ctypes.data))
+        self._publish()
+        return self._obs[0].astype(np.float64)
 
     def step(self, action, past_action):
-        v = self._vec
-        pa = np.asarray(past_action, dtype=np.float32).reshape(2)
-        v.set_state(_capi.F_PREV_A0, pa[:1])
-        v.set_state(_capi.F_PREV_A1, pa[1:])
-        obs, rew, done, arrive, _ = v.step_host(np.asarray(action, dtype=np.float32).reshape(1, 2))
-        self._sync_public_state()
-        return obs[0].astype(np.float64), float(rew[0]), bool(done[0]), bool(arrive[0])
+        self._act[0] = np.asarray(action, dtype=np.float32).reshape(2)
+        self._past[0] = np.asarray(past_action, dtype=np.float32).reshape(2)
+        _capi.check(self._step_ex(self._vec._h, *self._ptrs))
+        self._publish()
+        return self._obs[0].astype(np.float64), float(self._rew[0]), bool(self._done[0]), bool(self._arrive[0])
