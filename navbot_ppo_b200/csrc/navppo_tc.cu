@@ -288,7 +288,11 @@ __global__ void __launch_bounds__(256, 1) mlp_grad_tc_kernel(TcGradArgs ta) {
             float v[16];
             tc::tmem_ld16(trow + TM_Z + c0, v);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = lrelu_fast(v[i] + sBa[c0 + i]);
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sBa + c0 + 4 * i4);
+              v[4 * i4] = lrelu_fast(v[4 * i4] + b4.x); v[4 * i4 + 1] = lrelu_fast(v[4 * i4 + 1] + b4.y);
+              v[4 * i4 + 2] = lrelu_fast(v[4 * i4 + 2] + b4.z); v[4 * i4 + 3] = lrelu_fast(v[4 * i4 + 3] + b4.w);
+            }
             store8<PASSES>(sH, SH_PART, row, c0, v);
             store8<PASSES>(sH, SH_PART, row, c0 + 8, v + 8);
           }
@@ -478,10 +482,17 @@ __global__ void __launch_bounds__(256, 1) mlp_grad_tc_kernel(TcGradArgs ta) {
             tc::tmem_ld16(trow + TM_Z + c0, z);
             tc::tmem_ld16(trow + TM_GH + c0, g);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float zz = z[i] + sBa[c0 + i];
-              z[i] = lrelu_fast(zz);
-              g[i] = g[i] * dlrelu(zz);
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sBa + c0 + 4 * i4);   // one broadcast load per 4 biases
+              const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int i = 4 * i4 + k;
+                const float zz = z[i] + bb[k];
+                const float sl = zz > 0.f ? 1.f : LEAK;       // LeakyReLU slope: h = zz * slope, g_z = g_h * slope
+                z[i] = zz * sl;
+                g[i] = g[i] * sl;
+              }
             }
             store8<PASSES>(sH, SH_PART, row, c0, z);
             store8<PASSES>(sH, SH_PART, row, c0 + 8, z + 8);
