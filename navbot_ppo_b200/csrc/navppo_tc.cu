@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(256, 1) mlp_grad_tc_kernel(TcGradArgs ta) {
         }
         {  // H = lrelu(Z + ba): this warp's 32 rows x 64 columns
           const float* sBa = sBias + blk * HID + c * CHUNK;
-#pragma unroll 1
+#pragma unroll
           for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 16) {
             float v[16];
             tc::tmem_ld16(trow + TM_Z + c0, v);
@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(256, 1) mlp_grad_tc_kernel(TcGradArgs ta) {
         }
         {  // H = lrelu(z), GZ = GH * lrelu'(z), z = Z + ba
           const float* sBa = sBias + blk * HID + c * CHUNK;
-#pragma unroll 1
+#pragma unroll
           for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 16) {
             float z[16], g[16];
             tc::tmem_ld16(trow + TM_Z + c0, z);
