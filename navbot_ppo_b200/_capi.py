@@ -125,6 +125,7 @@ NAVPPO_SYMBOLS = {
     "navppo_adam": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "navppo_tc_selftest": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "navppo_tc_selftest_bf16": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "navppo_tc_profile": (ctypes.c_int, [_vp]),
     "navppo_update": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _f64, _i32, _vp, _vp, _vp, _vp]),
 }
 

@@ -28,6 +28,7 @@ UNITS = [
     ("navsim_kernels.cu", ["-fmad=false"]),
     ("navppo_kernels.cu", []),
     ("navppo_tc.cu", []),
+    ("navppo_tcws.cu", []),
 ]
 
 

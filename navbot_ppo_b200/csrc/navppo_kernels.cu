@@ -22,6 +22,7 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <cstdlib>
 #include <new>
 #include <string>
 
@@ -34,6 +35,10 @@
 int navppo_tc_grad_launch(const ppo::GradArgs& a, int rows, int passes, float* wprep, cudaStream_t s);
 size_t navppo_tc_prep_bytes();
 int navppo_tc_init();
+// warp-specialised version of the same kernel (navppo_tcws.cu), the default
+int navppo_tcws_grad_launch(const ppo::GradArgs& a, int rows, int passes, float* wprep, cudaStream_t s);
+size_t navppo_tcws_prep_bytes();
+int navppo_tcws_init();
 
 namespace {
 
@@ -748,6 +753,7 @@ struct navppo {
   double* adv_stats = nullptr;  // [3]
   float* grad_ws = nullptr;   // [NAVPPO_FLAT] used by navppo_update
   float* wprep = nullptr;     // tensor-core path: pre-split, pre-tiled weights
+  bool tc_single_role = false;  // NAVPPO_TC_KERNEL=single: the first (single-role) tcgen05 kernel, kept as a cross-check
   int sm_count = 148;
   int64_t launches = 0;
 };
@@ -820,8 +826,11 @@ int navppo_create(navppo_t** out, const navppo_cfg* cfg) {
   if (e == cudaSuccess) e = cudaMalloc(&h->adv_stats, 3 * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&h->grad_ws, (size_t)NAVPPO_FLAT * sizeof(float));
   if (e == cudaSuccess && cfg->precision != NAVPPO_FP32) {
-    e = cudaMalloc(&h->wprep, navppo_tc_prep_bytes());
-    if (e == cudaSuccess && navppo_tc_init() != NAVSIM_OK) {
+    const char* which = getenv("NAVPPO_TC_KERNEL");
+    h->tc_single_role = which && std::string(which) == "single";
+    const size_t wb = navppo_tc_prep_bytes() > navppo_tcws_prep_bytes() ? navppo_tc_prep_bytes() : navppo_tcws_prep_bytes();
+    e = cudaMalloc(&h->wprep, wb);
+    if (e == cudaSuccess && (navppo_tc_init() != NAVSIM_OK || navppo_tcws_init() != NAVSIM_OK)) {
       navppo_destroy(h);
       return NAVSIM_ECUDA;   // nav_last_error already set
     }
@@ -935,7 +944,10 @@ int navppo_grad(navppo_t* h, const float* params, const float* obs, const float*
     // two networks split the SMs
     const int per_net = h->sm_count / 2 > 0 ? h->sm_count / 2 : 1;
     rows = tiles < per_net ? tiles : per_net;
-    if (int rc = navppo_tc_grad_launch(a, rows, h->cfg.precision == NAVPPO_BF16X3 ? 3 : 1, h->wprep, s)) return rc;
+    const int passes = h->cfg.precision == NAVPPO_BF16X3 ? 3 : 1;
+    if (int rc = h->tc_single_role ? navppo_tc_grad_launch(a, rows, passes, h->wprep, s)
+                                   : navppo_tcws_grad_launch(a, rows, passes, h->wprep, s))
+      return rc;
     h->launches++;
   }
   grad_reduce_kernel<<<(NAVPPO_FLAT + 255) / 256, 256, 0, s>>>(h->gpart, h->mpart, rows, a.inv_n, grad, metrics);
