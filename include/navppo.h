@@ -157,11 +157,13 @@ int navppo_tc_selftest(const float* A, const float* B, float* D, int32_t N, int3
 int navppo_tc_selftest_bf16(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t a_mode, int32_t b_mode,
                             int32_t passes, void* stream);
 
-/* Diagnostic: while `device_counters32` (32 x int64 on the device) is non-NULL, split-BF16 gradient
- * passes run an instrumented build of the tcgen05 kernel whose CTA (0, 0) writes per-role cycle
- * counters there (epilogue warp 0: [0..7], epilogue warp 4: [8..15], MMA thread: [16..23], flush
- * warp: [24..31]; categories in tools/tc_ws_profile.py).  NULL switches it off.  Process-wide. */
-int navppo_tc_profile(long long* device_counters32);
+/* Diagnostic: while `device_counters` (32 + 4 * 512 int64 on the device) is non-NULL, split-BF16
+ * gradient passes run an instrumented build of the tcgen05 kernel whose CTA (0, 0) writes per-role
+ * cycle counters there (epilogue warp 0: [0..7], epilogue warp 4: [8..15], MMA thread: [16..23], flush
+ * warp: [24..31]) followed by an event trace of its 41st tile, 512 slots per role (slot 0 = start
+ * clock, slot 511 = count, entries = category << 56 | clock; categories in tools/tc_ws_profile.py).
+ * NULL switches it off.  Process-wide. */
+int navppo_tc_profile(long long* device_counters);
 
 #ifdef __cplusplus
 }

@@ -95,7 +95,9 @@ constexpr int NWSLOT = 3;
 constexpr uint32_t OFF_W = OFF_SGZ + 2 * SH_PART;           // 168 KB
 constexpr uint32_t OFF_BIAS = OFF_W + NWSLOT * WSLOT;       // 216 KB: fc1 biases of both blocks, 2 x 512 floats
 constexpr uint32_t OFF_RED = OFF_BIAS + 2 * HID * 4;        // head / bias-b gradient partials [4 warps][128] floats
-constexpr uint32_t OFF_BAR = OFF_RED + 4 * 128 * 4;         // mbarriers, tmem base
+constexpr uint32_t OFF_PAR = OFF_RED + 4 * 128 * 4;         // fc2 biases and head weights, 128 floats
+constexpr int P_B1B = 0, P_B2B = OBS, P_HEAD = OBS + X1;    // offsets inside that block
+constexpr uint32_t OFF_BAR = OFF_PAR + 128 * 4;             // mbarriers, tmem base
 constexpr uint32_t WS_SMEM_BYTES = OFF_BAR + 256;           // 227,584 B of the 232,448 B a CTA may have
 
 // mbarrier indices
@@ -127,6 +129,7 @@ struct WsGradArgs {
       const long long t__ = clock64();          \
       pc[i] += t__ - plast;                     \
       plast = t__;                              \
+      if (tbuf && tn < 500) tbuf[tn++] = ((long long)(i) << 56) | (t__ & 0x00FFFFFFFFFFFFFFLL); \
     }                                           \
   } while (0)
 
@@ -183,6 +186,26 @@ __device__ __forceinline__ void gemm(uint32_t tmem_d, const Opnd& A, const Opnd&
   }
   __syncwarp();
 }
+// D (+)= A B over the 64 hidden units of a half-chunk with A in tensor memory, as the epilogue warps leave
+// it: per 32 hidden units [16 packed hi columns | 16 packed lo columns], 8 packed columns per instruction
+template <int PASSES>
+__device__ __forceinline__ void gemm_ts(uint32_t tmem_d, uint32_t tmem_a, const Opnd& B, uint32_t idesc, bool accumulate) {
+  if (elect_one()) {
+    uint32_t acc = accumulate ? 1u : 0u;
+    const uint32_t b0 = B.start | (B.lbo << 16);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const uint32_t ah = tmem_a + 32 * (kk >> 1) + 8 * (kk & 1);
+      const uint64_t bh = words_desc(b0 + kk * B.step, B.sbo);
+      if (PASSES == 3) {  // small terms first
+        tc::mma_bf16_ts(tmem_d, ah + 16, bh, idesc, acc); acc = 1u;
+        tc::mma_bf16_ts(tmem_d, ah, words_desc(b0 + kk * B.step + B.part, B.sbo), idesc, acc);
+      }
+      tc::mma_bf16_ts(tmem_d, ah, bh, idesc, acc); acc = 1u;
+    }
+  }
+  __syncwarp();
+}
 // tcgen05.commit by the lane that issues the MMAs
 __device__ __forceinline__ void commit(uint64_t* bar) {
   if (elect_one()) tc::mma_commit(bar);
@@ -216,6 +239,32 @@ __device__ __forceinline__ void red_add1(float* addr, float a) {
 }
 __device__ __forceinline__ float lrelu_fast(float x) { return fmaxf(x, LEAK * x); }
 
+// Sums over the 32 lanes of a warp of V per-lane values at once: every round hands half of the values to
+// the partner lane (the pairs and their order are those of the xor butterfly 16, 8, 4, 2, 1, so each
+// total is the same sequence of additions), and lane l ends up with the total of value l * V / 32.
+template <int V>
+__device__ __forceinline__ float colsum(float* v, int lane) {
+  int n = V;
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    if (n > 1) {
+      n >>= 1;
+      const bool up = (lane & m) != 0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (i < n) {
+          const float send = up ? v[i] : v[i + n];
+          const float keep = up ? v[i + n] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+      }
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], m);
+    }
+  }
+  return v[0];
+}
+
 // pass order inside a tile: forward block 1, forward block 2, backward block 2, backward block 1
 __device__ __forceinline__ int pass_block(int pass) { return (pass == 1 || pass == 2) ? 1 : 0; }
 
@@ -223,6 +272,16 @@ template <int PASSES, bool PROF>
 __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs ta) {
   long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long plast = PROF ? clock64() : 0;
+  long long* tbuf = nullptr;   // PROF: event trace of one tile (the 41st of CTA (0, 0)), 512 slots per role after the counters
+  int tn = 0;
+  constexpr int TRACE_TILE = 40;
+#define TRACE_BEGIN(role, designated)                                                                          \
+  if (PROF) {                                                                                                  \
+    tbuf = (blockIdx.x == 0 && blockIdx.y == 0 && (designated) && tile == TRACE_TILE * (int)gridDim.x)        \
+               ? ta.prof + 32 + (role) * 512 : nullptr;                                                        \
+    if (tbuf) { tn = 1; tbuf[0] = clock64(); }                                                                 \
+  }
+#define TRACE_END() if (PROF && tbuf) { tbuf[511] = tn; tbuf = nullptr; }
   const GradArgs& a = ta.g;
   unsigned char* smem = ws_smem;
   unsigned char* sX = smem + OFF_SX;
@@ -231,6 +290,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
   unsigned char* sGZ = smem + OFF_SGZ;
   float* sBias = reinterpret_cast<float*>(smem + OFF_BIAS);
   float* sRed = reinterpret_cast<float*>(smem + OFF_RED);
+  float* sPar = reinterpret_cast<float*>(smem + OFF_PAR);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + B_COUNT * 8);
 
@@ -253,6 +313,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
   for (int i = tid; i < NET_ROW; i += WS_THREADS) grow[i] = 0.f;
   __threadfence();   // the zeros are in L2 before any red.add of this CTA
   for (int i = tid; i < 2 * HID; i += WS_THREADS) sBias[i] = p[(i < HID ? O_B1A : O_B2A - HID) + i];
+  if (tid < OBS) sPar[P_B1B + tid] = p[O_B1B + tid];
+  else if (tid < OBS + X1) sPar[tid] = p[O_B2B + tid - OBS];
+  else if (tid < OBS + X1 + (net == 0 ? ACTOR_HEAD : CRITIC_HEAD)) sPar[tid] = p[O_HEAD + tid - OBS - X1];
   if (tid < 128) {   // constant part of the X tile: columns 32..47 = (1, 0, 0, ...) in every row
     float ones[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, zeros[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     store8<3>(sX, SX_PART, tid, 32, ones);
@@ -274,35 +337,58 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
     uint32_t pz = 0, ph = 0x3, pacc = 0;               // parity bits per ring slot (hfree starts "free")
     double macc[4] = {0.0, 0.0, 0.0, 0.0};
 
-    // publish: this thread's tile stores are visible to the tensor core, then one arrive per warp
-    auto publish = [&](uint64_t* bar) {
-      tc::fence_smem_to_async();
+    // one arrive per warp once every lane's TMEM accesses (and, with SMEM, tile stores) are ordered
+    auto publish = [&](uint64_t* bar, bool wrote_smem) {
+      if (wrote_smem) tc::fence_smem_to_async();
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar);
     };
+    // 32 rows x 4 packed words (8 bf16 columns) -> one 16-byte granule per row of a 128-row tile
+    auto st_granule = [&](unsigned char* tile, int col0, const uint32_t* w) {
+      *reinterpret_cast<uint4*>(tile + (uint32_t)(col0 >> 3) * ROWG + (uint32_t)row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    };
+
+    float x1[X1];
+    auto load_x0 = [&](int tile) {                     // this row's observation (zeros past the end of the batch)
+      const int sj = tile * 128 + row;
+      if (tile < ntiles && sj < a.T) {
+        const float4* o = reinterpret_cast<const float4*>(a.obs + (size_t)sj * OBS);
+#pragma unroll
+        for (int k4 = 0; k4 < OBS / 4; ++k4) {
+          const float4 t = o[k4];
+          x1[4 * k4] = t.x; x1[4 * k4 + 1] = t.y; x1[4 * k4 + 2] = t.z; x1[4 * k4 + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < OBS; ++k) x1[k] = 0.f;
+      }
+    };
+    if (owner) load_x0(blockIdx.x);
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      TRACE_END();
+      TRACE_BEGIN(warp >> 2, lane == 0 && (warp == 0 || warp == 4));
       const int si = tile * 128 + row;
       const bool valid = owner && si < a.T;
-      float x1[X1], u2[X1], gsk[OBS];
+      float u2[X1], gsk[OBS];
       uint32_t u1pos = 0;                              // bit k: u1[k] > 0
-      // ------------------------------------------------------------------ load x0, publish it
+      float2 av = make_float2(0.f, 0.f);
+      float s_lpo = 0.f, s_adv = 0.f, s_rtg = 0.f;
+      // ------------------------------------------------------------------ publish x0; fetch the row's scalars early
       if (owner) {
-        if (valid) {
-          const float4* o = reinterpret_cast<const float4*>(a.obs + (size_t)si * OBS);
-#pragma unroll
-          for (int k4 = 0; k4 < OBS / 4; ++k4) {
-            const float4 t = o[k4];
-            x1[4 * k4] = t.x; x1[4 * k4 + 1] = t.y; x1[4 * k4 + 2] = t.z; x1[4 * k4 + 3] = t.w;
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < OBS; ++k) x1[k] = 0.f;
-        }
         store8<PASSES>(sX, SX_PART, row, 0, x1);
         store8<PASSES>(sX, SX_PART, row, 8, x1 + 8);
-        publish(bars + B_XREADY);
+        publish(bars + B_XREADY, true);
+        if (valid) {
+          if (net == 0) {
+            av = reinterpret_cast<const float2*>(a.act)[si];
+            s_lpo = a.logp_old[si];
+            s_adv = a.adv[si];
+          } else {
+            s_rtg = a.rtg[si];
+          }
+        }
       }
 
 #pragma unroll 1
@@ -317,56 +403,80 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
           tc::mbar_wait(bars + B_ZFULL + s, (pz >> s) & 1); pz ^= 1u << s;    // Z (and GH) of half-chunk h are in TMEM
           tc::fence_after_sync();
           PT(0);
-          tc::mbar_wait(bars + B_HFREE + s, (ph >> s) & 1); ph ^= 1u << s;    // the tile columns are no longer read
-          PT(1);
           const float* sBa = sBias + blk * HID + h * HC + ch * 32;
           const uint32_t tz = trow + TM_ZG + s * 128 + ch * 32;
           const int tcol = s * 64 + ch * 32;                                   // column inside the 128-column tiles
           if (fwd) {
+            // H = lrelu(Z + ba), written back over the columns this warp just read as the A operand of
+            // U += H Wb^T: [hi: 16 packed columns | lo: 16 packed columns]
+            float v[32];
+            tc::tmem_ld16_nowait(tz, v);
+            tc::tmem_ld16_nowait(tz + 16, v + 16);
+            tc::tmem_ld_wait();
+            uint32_t hi[16], lo[16];
 #pragma unroll
-            for (int c0 = 0; c0 < 32; c0 += 16) {   // H = lrelu(Z + ba)
-              float v[16];
-              tc::tmem_ld16(tz + c0, v);
-#pragma unroll
-              for (int i4 = 0; i4 < 4; ++i4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(sBa + c0 + 4 * i4);
-                v[4 * i4] = lrelu_fast(v[4 * i4] + b4.x); v[4 * i4 + 1] = lrelu_fast(v[4 * i4 + 1] + b4.y);
-                v[4 * i4 + 2] = lrelu_fast(v[4 * i4 + 2] + b4.z); v[4 * i4 + 3] = lrelu_fast(v[4 * i4 + 3] + b4.w);
-              }
-              store8<PASSES>(sH, SH_PART, row, tcol + c0, v);
-              store8<PASSES>(sH, SH_PART, row, tcol + c0 + 8, v + 8);
+            for (int i4 = 0; i4 < 8; ++i4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sBa + 4 * i4);
+              const float h0 = lrelu_fast(v[4 * i4] + b4.x), h1 = lrelu_fast(v[4 * i4 + 1] + b4.y);
+              const float h2 = lrelu_fast(v[4 * i4 + 2] + b4.z), h3 = lrelu_fast(v[4 * i4 + 3] + b4.w);
+              tc::split_bf16x2(h0, h1, &hi[2 * i4], &lo[2 * i4]);
+              tc::split_bf16x2(h2, h3, &hi[2 * i4 + 1], &lo[2 * i4 + 1]);
             }
+            tc::tmem_st16(tz, hi);
+            if (PASSES == 3) tc::tmem_st16(tz + 16, lo);
+            tc::tmem_st_wait();
+            publish(bars + B_EFULL + s, false);
           } else {
+            // H = lrelu(z), GZ = GH * lrelu'(z), z = Z + ba
+            float z[32], g[32];
+            tc::tmem_ld16_nowait(tz, z);
+            tc::tmem_ld16_nowait(tz + 16, z + 16);
+            tc::tmem_ld16_nowait(tz + 64, g);
+            tc::tmem_ld16_nowait(tz + 80, g + 16);
+            tc::tmem_ld_wait();
+            uint32_t hh[16], hl[16], gh[16], gl[16];
 #pragma unroll
-            for (int c0 = 0; c0 < 32; c0 += 16) {   // H = lrelu(z), GZ = GH * lrelu'(z), z = Z + ba
-              float z[16], g[16];
-              tc::tmem_ld16(tz + c0, z);
-              tc::tmem_ld16(tz + 64 + c0, g);
+            for (int i4 = 0; i4 < 8; ++i4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sBa + 4 * i4);   // one broadcast load per 4 biases
+              const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-              for (int i4 = 0; i4 < 4; ++i4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(sBa + c0 + 4 * i4);
-                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const int i = 4 * i4 + k;
-                  const float zz = z[i] + bb[k];
-                  const float sl = zz > 0.f ? 1.f : LEAK;       // LeakyReLU slope: h = zz * slope, g_z = g_h * slope
-                  z[i] = zz * sl;
-                  g[i] = g[i] * sl;
-                }
+              for (int k = 0; k < 4; ++k) {
+                const int i = 4 * i4 + k;
+                const float zz = z[i] + bb[k];
+                const float sl = zz > 0.f ? 1.f : LEAK;       // LeakyReLU slope: h = zz * slope, g_z = g_h * slope
+                z[i] = zz * sl;
+                g[i] = g[i] * sl;
               }
-              store8<PASSES>(sH, SH_PART, row, tcol + c0, z);
-              store8<PASSES>(sH, SH_PART, row, tcol + c0 + 8, z + 8);
-              store8<PASSES>(sGZ, SH_PART, row, tcol + c0, g);
-              store8<PASSES>(sGZ, SH_PART, row, tcol + c0 + 8, g + 8);
+              tc::split_bf16x2(z[4 * i4], z[4 * i4 + 1], &hh[2 * i4], &hl[2 * i4]);
+              tc::split_bf16x2(z[4 * i4 + 2], z[4 * i4 + 3], &hh[2 * i4 + 1], &hl[2 * i4 + 1]);
+              tc::split_bf16x2(g[4 * i4], g[4 * i4 + 1], &gh[2 * i4], &gl[2 * i4]);
+              tc::split_bf16x2(g[4 * i4 + 2], g[4 * i4 + 3], &gh[2 * i4 + 1], &gl[2 * i4 + 1]);
             }
+            if (blk) {   // GZ is also the A operand (in tensor memory, over the GH columns) of GX += GZ Wa
+              tc::tmem_st16(tz + 64, gh);
+              if (PASSES == 3) tc::tmem_st16(tz + 80, gl);
+            }
+            PT(3);
+            tc::mbar_wait(bars + B_HFREE + s, (ph >> s) & 1); ph ^= 1u << s;    // the tile columns are no longer read
+            PT(1);
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+              st_granule(sH, tcol + 8 * c8, hh + 4 * c8);
+              st_granule(sGZ, tcol + 8 * c8, gh + 4 * c8);
+              if (PASSES == 3) {
+                st_granule(sH + SH_PART, tcol + 8 * c8, hl + 4 * c8);
+                st_granule(sGZ + SH_PART, tcol + 8 * c8, gl + 4 * c8);
+              }
+            }
+            if (blk) tc::tmem_st_wait();
+            publish(bars + B_EFULL + s, true);
           }
-          publish(bars + B_EFULL + s);
           PT(fwd ? 2 : 3);
         }
 
         // -------------------------------------------------------------- between the passes: row owners only
         if (!owner) continue;
+        if (pass == 3) load_x0(tile + gridDim.x);       // the next tile's observation row flies behind the wait
         tc::mbar_wait(bars + B_ACC, pacc); pacc ^= 1;   // every product of this pass has completed
         tc::fence_after_sync();
         PT(4);
@@ -376,39 +486,38 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
           tc::tmem_ld16(trow + TM_U, acc);
 #pragma unroll
           for (int k = 0; k < OBS; ++k) {
-            const float u = x1[k] + acc[k] + p[O_B1B + k];
+            const float u = x1[k] + acc[k] + sPar[P_B1B + k];
             if (u > 0.f) u1pos |= 1u << k;
             x1[OBS + k] = lrelu(u);
           }
           store8<PASSES>(sX, SX_PART, row, 16, x1 + 16);
           store8<PASSES>(sX, SX_PART, row, 24, x1 + 24);
-          publish(bars + B_XREADY);
+          publish(bars + B_XREADY, true);
         } else if (pass == 1) {
           {
-            float acc[16];
-            tc::tmem_ld16(trow + TM_U, acc);
+            float acc[32];
+            tc::tmem_ld16_nowait(trow + TM_U, acc);
+            tc::tmem_ld16_nowait(trow + TM_U + 16, acc + 16);
+            tc::tmem_ld_wait();
 #pragma unroll
-            for (int k = 0; k < 16; ++k) u2[k] = x1[k] + acc[k] + p[O_B2B + k];
-            tc::tmem_ld16(trow + TM_U + 16, acc);
-#pragma unroll
-            for (int k = 0; k < 16; ++k) u2[16 + k] = x1[16 + k] + acc[k] + p[O_B2B + 16 + k];
+            for (int k = 0; k < X1; ++k) u2[k] = x1[k] + acc[k] + sPar[P_B2B + k];
           }
           // ================================================================ heads, losses, dL/du2
           float go1 = 0.f, go2 = 0.f;
           float y2[X1], gu2[X1];
 #pragma unroll
           for (int k = 0; k < X1; ++k) y2[k] = lrelu(u2[k]);
+          const float* hw = sPar + P_HEAD;
           if (net == 0) {
-            float o1 = p[O_HEAD + X1], o2 = p[O_HEAD + 2 * X1 + 1];
+            float o1 = hw[X1], o2 = hw[2 * X1 + 1];
 #pragma unroll
-            for (int k = 0; k < X1; ++k) { o1 = fmaf(p[O_HEAD + k], y2[k], o1); o2 = fmaf(p[O_HEAD + X1 + 1 + k], y2[k], o2); }
+            for (int k = 0; k < X1; ++k) { o1 = fmaf(hw[k], y2[k], o1); o2 = fmaf(hw[X1 + 1 + k], y2[k], o2); }
             const float m0 = sigmoidf_(o1), m1 = tanhf(o2);
             if (valid) {
-              const float2 av = reinterpret_cast<const float2*>(a.act)[si];
               const float lp = gauss_logp(av.x, av.y, m0, m1, a.var);
-              const float lr = lp - a.logp_old[si];
+              const float lr = lp - s_lpo;
               const float ratio = expf(lr);                                          // ppo.py:316
-              const float A = a.adv[si];
+              const float A = s_adv;
               const float s1 = ratio * A;                                            // ppo.py:319
               const float s2 = fminf(fmaxf(ratio, 1.f - a.clip), 1.f + a.clip) * A;  // ppo.py:320
               macc[0] += (double)(-fminf(s1, s2));                                   // ppo.py:342
@@ -420,51 +529,49 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
               go2 = gm1 * (1.f - m1 * m1);
             }
           } else {
-            float v = p[O_HEAD + X1];
+            float v = hw[X1];
 #pragma unroll
-            for (int k = 0; k < X1; ++k) v = fmaf(p[O_HEAD + k], y2[k], v);
+            for (int k = 0; k < X1; ++k) v = fmaf(hw[k], y2[k], v);
             if (valid) {
-              const float d = v - a.rtg[si];
+              const float d = v - s_rtg;
               macc[1] += (double)(d * d);                                            // ppo.py:343
               go1 = 2.f * d * a.inv_n;
             }
           }
 #pragma unroll
           for (int k = 0; k < X1; ++k) {
-            const float gy = (net == 0) ? fmaf(p[O_HEAD + k], go1, p[O_HEAD + X1 + 1 + k] * go2) : p[O_HEAD + k] * go1;
+            const float gy = (net == 0) ? fmaf(hw[k], go1, hw[X1 + 1 + k] * go2) : hw[k] * go1;
             gu2[k] = gy * dlrelu(u2[k]);
           }
 #pragma unroll
           for (int k = 0; k < X1; k += 8) store8<PASSES>(sGU, SGU_PART, row, k, gu2 + k);
+          publish(bars + B_XREADY, true);               // GU is published: the tensor pipe starts the backward pass
 #pragma unroll
           for (int k = 0; k < OBS; ++k) gsk[k] = gu2[OBS + k];   // the skip-connection share of dL/dx1
-          // per-warp partial sums over the 32 samples: head weights / biases, then the fc2 bias of block 2
+          // per-warp sums over the 32 samples (lane k ends up with column k): head weights / biases, then
+          // the fc2 bias of block 2
           const int nh = (net == 0) ? 2 : 1;
           for (int hd = 0; hd < nh; ++hd) {
             const float g = hd ? go2 : go1;
             float bsum = g;
             for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+            float t[X1];
 #pragma unroll
-            for (int k = 0; k < X1; ++k) {
-              float t = g * y2[k];
-              for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-              if (lane == 0) sRed[warp * 128 + hd * (X1 + 1) + k] = t;
-            }
+            for (int k = 0; k < X1; ++k) t[k] = g * y2[k];
+            const float cs = colsum<X1>(t, lane);
+            sRed[warp * 128 + hd * (X1 + 1) + lane] = cs;
             if (lane == 0) sRed[warp * 128 + hd * (X1 + 1) + X1] = bsum;
           }
-#pragma unroll
-          for (int k = 0; k < X1; ++k) {
-            float t = gu2[k];
-            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            if (lane == 0) sRed[warp * 128 + 72 + k] = t;
+          {
+            const float cs = colsum<X1>(gu2, lane);
+            sRed[warp * 128 + 72 + lane] = cs;
           }
-          publish(bars + B_XREADY);                     // GU is published; the tensor pipe starts the backward pass
           named_sync(1, 128);
           {
             const int nhead = (net == 0) ? ACTOR_HEAD : CRITIC_HEAD;
-            if (tid < nhead) grow[O_HEAD + tid] += ((sRed[tid] + sRed[128 + tid]) + sRed[256 + tid]) + sRed[384 + tid];
+            if (tid < nhead) red_add1(grow + O_HEAD + tid, ((sRed[tid] + sRed[128 + tid]) + sRed[256 + tid]) + sRed[384 + tid]);
             if (tid >= 72 && tid < 72 + X1)
-              grow[O_B2B + tid - 72] += ((sRed[tid] + sRed[128 + tid]) + sRed[256 + tid]) + sRed[384 + tid];
+              red_add1(grow + O_B2B + tid - 72, ((sRed[tid] + sRed[128 + tid]) + sRed[256 + tid]) + sRed[384 + tid]);
           }
         } else if (pass == 2) {
           // dL/dx1 = g_u2 (skip connection) + GX; dL/du1 = dL/dy1 * lrelu'(u1); publish GU1 for block 1
@@ -474,16 +581,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
           for (int k = 0; k < OBS; ++k) gu1[k] = (gsk[k] + acc[k]) * (((u1pos >> k) & 1u) ? 1.f : LEAK);
           store8<PASSES>(sGU, SGU_PART, row, 0, gu1);
           store8<PASSES>(sGU, SGU_PART, row, 8, gu1 + 8);
-#pragma unroll
-          for (int k = 0; k < OBS; ++k) {
-            float t = gu1[k];
-            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            if (lane == 0) sRed[warp * 128 + 104 + k] = t;
-          }
-          publish(bars + B_XREADY);
+          publish(bars + B_XREADY, true);
+          const float cs = colsum<OBS>(gu1, lane);      // lanes 2k and 2k + 1 hold column k
+          if (!(lane & 1)) sRed[warp * 128 + 104 + (lane >> 1)] = cs;
           named_sync(1, 128);
           if (tid >= 104 && tid < 104 + OBS)
-            grow[O_B1B + tid - 104] += ((sRed[tid] + sRed[128 + tid]) + sRed[256 + tid]) + sRed[384 + tid];
+            red_add1(grow + O_B1B + tid - 104, ((sRed[tid] + sRed[128 + tid]) + sRed[256 + tid]) + sRed[384 + tid]);
         }
         // pass == 3: the tile's last product has completed; X / GU may be overwritten
       }
@@ -505,6 +608,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t pdw = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      TRACE_END();
+      TRACE_BEGIN(3, lane == 0 && warp == W_FLUSH0);
 #pragma unroll 1
       for (int blk = 1; blk >= 0; --blk) {
         const int IN = blk ? X1 : OBS;
@@ -578,6 +683,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
       auto next_slot = [](int s) { return s == NWSLOT - 1 ? 0 : s + 1; };
 
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        TRACE_END();
+        TRACE_BEGIN(2, lane == 0);
 #pragma unroll 1
         for (int pass = 0; pass < 4; ++pass) {
           const int blk = pass_block(pass);
@@ -606,6 +713,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
               if (blk) gemm<PASSES, 2>(tmem + TM_ZG + s * 128 + 64, GUk, Wbm, id_gh, false);
               else gemm<PASSES, 1>(tmem + TM_ZG + s * 128 + 64, GUk, Wbm, id_gh, false);
             }
+            PT(5);
             commit(bars + B_ZFULL + s);
             if (!fwd && !blk) commit(bars + B_WFREE + wslot_p1);   // backward block 1 has no GX: last reader
             wslot_p1 = next_slot(wslot_p1);
@@ -614,17 +722,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
           auto issue_p2 = [&](int h) {
             const int s = h & 1;
             const uint32_t w = aW + wslot_p2 * WSLOT;
-            const uint32_t koff = s * 8 * RG;             // the half-chunk's columns inside the 128-column tiles
-            if (fwd) {
-              const Opnd Hk{(aH >> 4) + koff, SH_PART >> 4, RG, 8, 2 * RG};
+            if (fwd) {   // A = H (tensor memory, over the Z columns), B = Wb (rows = output features, K-major)
               const Opnd Wbk{(w + 2 * wp) >> 4, wp >> 4, (uint32_t)IN, 8, 2u * IN};
-              gemm<PASSES, 4>(tmem + TM_U, Hk, Wbk, id_u, h > 0);
-              commit(bars + B_HFREE + s);
-            } else {
-              const Opnd GZk{(aGZ >> 4) + koff, SH_PART >> 4, RG, 8, 2 * RG};
+              gemm_ts<PASSES>(tmem + TM_U, tmem + TM_ZG + s * 128, Wbk, id_u, h > 0);
+            } else {     // A = GZ (tensor memory, over the GH columns), B = Wa read MN-major (rows = K = hidden units)
               const Opnd Wam{w >> 4, wp >> 4, 8, HC, 16};
-              gemm<PASSES, 4>(tmem + TM_GX, GZk, Wam, id_gx, h > 0);
+              gemm_ts<PASSES>(tmem + TM_GX, tmem + TM_ZG + s * 128 + 64, Wam, id_gx, h > 0);
             }
+            PT(6);
             commit(bars + B_WFREE + wslot_p2);
           };
           // weight gradients of the chunk whose two half-chunks sit complete in the H / GZ tiles
@@ -636,6 +741,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
             // dWa = GZ^T [X | 1], dWbT = H^T GU : both operands MN-major (rows = K = samples)
             gemm<PASSES, 8>(tmem + TM_DWA, GZm, Xm, id_dwa, false);
             gemm<PASSES, 8>(tmem + TM_DWB, Hm, GUm, id_dwb, false);
+            PT(7);
             commit(bars + B_DWFULL);
             commit(bars + B_HFREE + 0);
             commit(bars + B_HFREE + 1);
@@ -664,10 +770,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
                 wslot_p2 = next_slot(wslot_p2);
                 if (h + 2 < NHC) issue_p1(h + 2);
               } else {
+                if (blk) issue_p2(h);                    // before Z / GH of h + 2 overwrite the slot GZ sits in
+                wslot_p2 = next_slot(wslot_p2);
                 if (h + 2 < NHC) issue_p1(h + 2);
                 issue_dw();
-                if (blk) issue_p2(h);
-                wslot_p2 = next_slot(wslot_p2);
               }
             }
           }
@@ -701,7 +807,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
 // ---- internal entry points used by navppo_kernels.cu -----------------------------------
 size_t navppo_tcws_prep_bytes() { return (size_t)2 * WS_NET_BLOB; }
 
-static long long* g_prof = nullptr;   // navppo_tc_profile: per-role cycle counters of CTA (0, 0), 32 values
+static long long* g_prof = nullptr;   // navppo_tc_profile: per-role cycle counters + one-tile event trace of CTA (0, 0)
 
 int navppo_tcws_init() {
   NAV_CUDA_TRY(cudaFuncSetAttribute(mlp_grad_ws_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES));
@@ -722,7 +828,7 @@ int navppo_tcws_grad_launch(const ppo::GradArgs& a, int rows, int passes, float*
   return NAVSIM_OK;
 }
 
-extern "C" int navppo_tc_profile(long long* device_counters32) {
-  g_prof = device_counters32;
+extern "C" int navppo_tc_profile(long long* device_counters) {
+  g_prof = device_counters;
   return NAVSIM_OK;
 }

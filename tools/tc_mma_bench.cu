@@ -25,7 +25,7 @@ struct Args {
   const float* B;   // [N, K]
   float* D;         // [M, N]
   long long* cyc;   // [2]: cycles, stress stores issued
-  int M, N, K, a_src, b_mode, reps, stress, d_lane, issuers;
+  int M, N, K, a_src, b_mode, reps, stress, d_lane, issuers, stress_kind;
 };
 
 extern __shared__ __align__(128) unsigned char smem[];
@@ -172,18 +172,45 @@ __global__ void __launch_bounds__(384) bench_kernel(Args p) {
     if (lane == 0)
     if (atomicAdd((int*)&stop_flag, 1) + 1 == p.issuers) stop_flag = 1000;
   } else if (warp >= 4 && warp < 4 + p.stress) {
-    // stream 16-byte stores (one 512-byte row per warp instruction) until the MMAs are done
+    // keep one SM resource busy until the MMAs are done: 0 = 16-byte shared-memory stores (one 512-byte row per
+    // warp instruction), 1 = FP32 multiplies + bf16x2 conversions, 2 = tcgen05.ld of 16 columns, 3 = 16-byte
+    // shared-memory loads
     long long n = 0;
     uint4 v = make_uint4(tid, tid, tid, tid);
     unsigned char* base = sS + (warp - 4) * 8192 + lane * 16;
+    float f0 = 1.0f + tid * 1e-3f, f1 = 0.5f, f2 = 0.25f, f3 = 2.f;
+    uint32_t sink = 0;
     while (stop_flag < 1000) {
+      if (p.stress_kind == 0) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tc::smem_u32(base + i * 512)), "r"(v.x), "r"(v.y), "r"(v.z),
-                     "r"(v.w)
-                     : "memory");
+        for (int i = 0; i < 16; ++i)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tc::smem_u32(base + i * 512)), "r"(v.x), "r"(v.y), "r"(v.z),
+                       "r"(v.w)
+                       : "memory");
+      } else if (p.stress_kind == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          f0 = f0 * 1.0001f; f1 = f1 * 0.9999f; f2 = f2 * 1.0002f; f3 = f3 * 0.9998f;
+          uint32_t a_, b_;
+          asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(a_) : "f"(f0), "f"(f1));
+          asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(b_) : "f"(f2), "f"(f3));
+          sink ^= a_ + b_;
+        }
+      } else if (p.stress_kind == 2) {
+        float t[16];
+        tc::tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + 384 + (warp >> 2) * 16, t);
+        sink ^= __float_as_uint(t[0]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          uint4 r;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(tc::smem_u32(base + i * 512)));
+          sink ^= r.x;
+        }
+      }
       n += 16;
     }
+    if (sink == 0x12345678u) p.D[0] = f0 + f1 + f2 + f3;
     if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.cyc + 1), (unsigned long long)n);
   }
   __syncthreads();
@@ -229,7 +256,7 @@ int main(int argc, char** argv) {
   cudaMalloc(&dC, 32);
   const size_t sm = 32768 + 65536 + 65536;
   cudaFuncSetAttribute(bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  struct Case { int M, N, K, a_src, b_mode, stress, d_lane, issuers = 1; };
+  struct Case { int M, N, K, a_src, b_mode, stress, d_lane, issuers = 1, stress_kind = 0; };
   std::vector<Case> cases;
   const int Ns128[] = {16, 32, 48, 64, 96, 128, 256};
   for (int a_src = 0; a_src < 3; ++a_src)
@@ -257,6 +284,13 @@ int main(int argc, char** argv) {
     for (int a_src : {0, 2})
       for (int N : {16, 32, 48, 64}) cases.push_back({128, N, 128, a_src, 0, 0, 0, is});
   for (int is : {2, 4}) cases.push_back({128, 48, 128, 1, 1, 0, 0, is});
+  // what slows the MMA stream down: ALU / conversion work, TMEM loads or shared-memory loads in 8 other warps?
+  for (int kind : {1, 2, 3})
+    for (int st : {8}) {
+      cases.push_back({128, 64, 32, 0, 0, st, 0, 1, kind});     // Z-like: SS, N = 64
+      cases.push_back({128, 32, 128, 2, 0, st, 0, 1, kind});    // U / GX-like: TS, N = 32
+      cases.push_back({128, 48, 128, 1, 1, st, 0, 1, kind});    // dW-like
+    }
   if (only == -2) { printf("%d\n", (int)cases.size()); return 0; }
   int idx = -1;
   for (const Case& c : cases) {
@@ -269,7 +303,7 @@ int main(int argc, char** argv) {
     cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
     cudaMemset(dD, 0, 128 * 256 * 4);
     cudaMemset(dC, 0, 32);
-    Args p{dA, dB, dD, dC, c.M, c.N, c.K, c.a_src, c.b_mode, reps, c.stress, c.d_lane, c.issuers};
+    Args p{dA, dB, dD, dC, c.M, c.N, c.K, c.a_src, c.b_mode, reps, c.stress, c.d_lane, c.issuers, c.stress_kind};
     bench_kernel<<<1, 384, sm>>>(p);   // warm (instruction cache)
     cudaMemset(dC, 0, 32);
     bench_kernel<<<1, 384, sm>>>(p);
@@ -286,8 +320,8 @@ int main(int argc, char** argv) {
         err = fmax(err, fabs(s - D[m * c.N + n]));
       }
     const double nm = (double)reps * (c.K / 16);
-    printf("%4d %4d %4d %6d %6d %6d %6d | %10.1f %10.1f %12.3f %10.2e %s issuers=%d other=%.1f\n", c.M, c.N, c.K, c.a_src, c.b_mode, c.stress,
-           c.d_lane, cyc[0] / nm, cyc[2] / nm, (double)cyc[1] * 1.0 / cyc[0], err, err < 1e-3 ? "ok" : "WRONG", c.issuers, cyc[3] / nm);
+    printf("%4d %4d %4d %6d %6d %6d %6d | %10.1f %10.1f %12.3f %10.2e %s issuers=%d other=%.1f kind=%d\n", c.M, c.N, c.K, c.a_src, c.b_mode, c.stress,
+           c.d_lane, cyc[0] / nm, cyc[2] / nm, (double)cyc[1] * 1.0 / cyc[0], err, err < 1e-3 ? "ok" : "WRONG", c.issuers, cyc[3] / nm, c.stress_kind);
     fflush(stdout);
   }
   return 0;

@@ -17,12 +17,13 @@ from tools.tc_ws_check import handle  # noqa: E402
 DEV = "cuda:0"
 EPI = ["wait Z/GH in TMEM", "wait tile columns free", "epilogue forward", "epilogue backward", "wait pass complete",
        "row-owner work", "-", "-"]
-MMA = ["wait X/GU published", "wait epilogue of half-chunk", "wait weights", "wait dW flushed", "issue", "-", "-", "-"]
+MMA = ["wait X/GU published", "wait epilogue of half-chunk", "wait weights", "wait dW flushed", "commits / other",
+       "issue Z / GH", "issue U / GX", "issue dW"]
 FL = ["wait dW complete", "flush", "-", "-", "-", "-", "-", "-"]
 
 
 def main():
-    T = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+    T = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 1 << 20
     g = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "ppo_learn_b.npz"))
     rng = np.random.RandomState(0)
     idx = rng.randint(0, len(g["obs"]), T)
@@ -39,7 +40,7 @@ def main():
     h = handle(_capi.PREC_BF16X3, max(T, 1024), False)
     grad = torch.zeros(_capi.PPO_FLAT, device=DEV)
     met = torch.zeros(8, dtype=torch.float64, device=DEV)
-    prof = torch.zeros(32, dtype=torch.int64, device=DEV)
+    prof = torch.zeros(32 + 4 * 512, dtype=torch.int64, device=DEV)
 
     def run():
         rc = L.navppo_grad(h, flat.data_ptr(), o.data_ptr(), a_.data_ptr(), l_.data_ptr(), ad.data_ptr(), rt.data_ptr(), T, T,
@@ -63,6 +64,27 @@ def main():
         for i, lab in enumerate(labels):
             if lab != "-":
                 print(f"      {lab:30s} {pc[base + i] / per_cta:9.0f}  ({100.0 * pc[base + i] / max(tot, 1):5.1f} %)")
+
+
+    # event trace of one tile: every mark is "the segment that just ended was of this category"
+    if "--trace" in sys.argv:
+        names = {0: ("E0", EPI), 1: ("E4", EPI), 2: ("MMA", MMA), 3: ("FL", FL)}
+        ev = []
+        t0 = min(int(pc[32 + r * 512]) for r in range(4) if pc[32 + r * 512 + 511] > 0)
+        for r in range(4):
+            base = 32 + r * 512
+            n = int(pc[base + 511])
+            prev = int(pc[base]) & ((1 << 56) - 1)
+            for k in range(1, n):
+                v = int(pc[base + k])
+                cat, t = (v >> 56) & 0xFF, v & ((1 << 56) - 1)
+                ev.append((prev - t0, t - t0, names[r][0], names[r][1][cat]))
+                prev = t
+        ev.sort()
+        print("trace of one tile: start end dur role segment")
+        for a_, b_, r, c in ev:
+            if b_ - a_ >= int(os.environ.get("TRACE_MIN", "150")):
+                print(f"  {a_:7d} {b_:7d} {b_ - a_:6d}  {r:4s} {c}")
 
 
 if __name__ == "__main__":
