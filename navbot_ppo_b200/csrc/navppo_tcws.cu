@@ -4,23 +4,29 @@
 //
 // Same arithmetic as mlp_grad_tc_kernel (one epoch body — forward, losses, backward — of one network
 // per CTA row over tiles of 128 samples, ppo.py:305-397, net_actor.py:16-53), restructured so that the
-// tensor pipe and the CUDA cores work at the same time:
+// tensor pipe and the CUDA cores work at the same time and so that as few operands as possible
+// travel through shared memory (operand fetch from shared memory, 128 B/clk, is what bounds these
+// skinny products: profiles/r02a_tcgen05_issue_rate.txt):
 //
-//   warps 0-7   epilogue: TMEM -> bias / LeakyReLU / derivative -> bf16 hi|lo split -> operand tiles in
-//               shared memory; warps 0-3 also own one sample row each (block outputs, heads, losses)
-//   warps 8-11  weight-gradient flush: TMEM (lane = hidden unit) -> red.global.add into the CTA's
-//               partial-gradient row
-//   warp 12     the ONE thread that issues every tcgen05.mma
-//   warp 13     the ONE thread that streams pre-tiled weight half-chunks through a 3-slot TMA ring
+//   warps 0-7   epilogue: TMEM -> bias / LeakyReLU / derivative -> bf16 hi|lo split -> written back IN
+//               PLACE into tensor memory as the A operand of the next products; warps 0-3 also own one
+//               sample row each (block outputs, heads, losses)
+//   warps 8-11  weight-gradient flush: TMEM (lane = hidden unit) -> the CTA's partial-gradient row
+//   warp 12     issues every tcgen05.mma (converged warp, one elected lane)
+//   warp 13     one thread streams pre-tiled weights through TMA rings
 //
-// The hidden layer is walked in half-chunks of 64 units.  Z / GH accumulators live in a 2-slot TMEM
-// ring, so while the epilogue warps turn half-chunk h into operand tiles, the tensor pipe already
-// computes Z / GH of half-chunk h + 1 and the U / GX products of half-chunk h - 1.  The weight-gradient
-// products (M = 128 hidden units of a whole chunk, K = 128 samples) read the complete H / GZ tiles and
-// are the one phase that cannot overlap the epilogue of the next chunk (the tiles are single
-// buffered: 128 KB of the 227 KB); their accumulators are flushed by the flush warps under the next
-// chunk's epilogue.  All hand-offs are mbarriers (tcgen05.commit on the tensor side, one elected
-// arrive per warp on the CUDA-core side); there is no CTA-wide barrier inside the tile loop.
+// Forward (per block, half-chunks of 64 hidden units, 2-slot TMEM ring):
+//     Z = X Wa^T  [128 samples x 64]  (operands in shared memory)
+//     H = lrelu(Z + ba) -> packed over Z;   U += H Wb^T  (A = H in tensor memory)
+// Backward (per block, chunks of 128 hidden units x halves of 64 samples, TRANSPOSED: lane = hidden unit):
+//     Z^T = Wa X^T, GH^T = Wb^T GU^T  [128 hidden x 64 samples]
+//     H^T = lrelu(.), GZ^T = GH^T * lrelu'(.) -> packed over Z^T / GH^T
+//     dWa += GZ^T [X | 1],  dWb^T += H^T GU   (A in tensor memory, K = the 64 samples; double-buffered
+//                                              accumulators, flushed per chunk under the next chunk)
+//     GX += GZ Wa  (block 2 only; A = the GZ^T tile the epilogue also leaves in shared memory)
+// Only X, GU, the weights and (block 2) GZ^T ever sit in shared memory.  All hand-offs are mbarriers
+// (tcgen05.commit on the tensor side, one elected arrive per warp on the CUDA-core side); there is no
+// CTA-wide barrier inside the tile loop.
 //
 // Every product is issued in the same k-order and pass order as the first kernel, every reduction
 // keeps its order, so the two kernels return bit-identical gradients (tests/test_ppo_tc_gpu.py).
@@ -50,10 +56,20 @@ constexpr int HC = 64;                                    // hidden units per ha
 constexpr int NHC = HID / HC;                             // 8
 __host__ __device__ constexpr uint32_t wpart(int IN) { return (uint32_t)(HC * IN * 2); }
 __host__ __device__ constexpr uint32_t wblob(int IN) { return 4u * wpart(IN); }
-constexpr uint32_t WS_NET_BLOB = NHC * (wblob(OBS) + wblob(X1));   // 196,608 B
+constexpr uint32_t WS_FWD_BLOB = NHC * (wblob(OBS) + wblob(X1));   // 196,608 B
 __host__ __device__ constexpr uint32_t wblob_off(int block2, int h) {
   return block2 ? NHC * wblob(OBS) + (uint32_t)h * wblob(X1) : (uint32_t)h * wblob(OBS);
 }
+// ... followed by 4 chunk blobs (128 hidden units) of block 1 then 4 of block 2 for the backward pass,
+//   [Wa hi | Wa lo | Wb hi | Wb lo], Wa tile: rows = hidden unit (128), Wb tile: rows = output feature (IN)
+constexpr int CH = 128;
+constexpr int NCH = HID / CH;                              // 4
+__host__ __device__ constexpr uint32_t cpart(int IN) { return (uint32_t)(CH * IN * 2); }
+__host__ __device__ constexpr uint32_t cblob(int IN) { return 4u * cpart(IN); }
+__host__ __device__ constexpr uint32_t cblob_off(int block2, int c) {
+  return WS_FWD_BLOB + (block2 ? NCH * cblob(OBS) + (uint32_t)c * cblob(X1) : (uint32_t)c * cblob(OBS));
+}
+constexpr uint32_t WS_NET_BLOB = WS_FWD_BLOB + NCH * (cblob(OBS) + cblob(X1));   // 393,216 B
 
 __global__ void ws_prep_weights_kernel(const float* __restrict__ params, unsigned char* __restrict__ wprep) {
   const int net = blockIdx.y;
@@ -75,6 +91,15 @@ __global__ void ws_prep_weights_kernel(const float* __restrict__ params, unsigne
     tc::split_bf16(p[(block2 ? O_W2B : O_W1B) + i * HID + j], &hi, &lo);
     *reinterpret_cast<uint16_t*>(blob + 2 * wp + tc::rb16_off(IN, i, jl)) = hi;
     *reinterpret_cast<uint16_t*>(blob + 3 * wp + tc::rb16_off(IN, i, jl)) = lo;
+    // the same two weights in the chunk blobs of the backward pass
+    const int c = j / CH, jc = j % CH;
+    unsigned char* cb = out + cblob_off(block2, c);
+    const uint32_t cp = cpart(IN);
+    *reinterpret_cast<uint16_t*>(cb + 2 * cp + tc::rb16_off(IN, i, jc)) = hi;
+    *reinterpret_cast<uint16_t*>(cb + 3 * cp + tc::rb16_off(IN, i, jc)) = lo;
+    tc::split_bf16(p[(block2 ? O_W2A : O_W1A) + j * IN + i], &hi, &lo);
+    *reinterpret_cast<uint16_t*>(cb + tc::rb16_off(CH, jc, i)) = hi;
+    *reinterpret_cast<uint16_t*>(cb + cp + tc::rb16_off(CH, jc, i)) = lo;
   }
 }
 
@@ -85,29 +110,31 @@ constexpr int XCOLS = 48;                                   // x0 | y1 | 1 0 0 .
 constexpr uint32_t ROWG = 128 * 16;                         // bytes of one 8-column group of a 128-row tile
 constexpr uint32_t SX_PART = (XCOLS / 8) * ROWG;            // 12 KB
 constexpr uint32_t SGU_PART = (X1 / 8) * ROWG;              // 8 KB
-constexpr uint32_t SH_PART = (128 / 8) * ROWG;              // 32 KB: 128 hidden columns = one chunk
+constexpr uint32_t SGZ_PART = (128 / 8) * ROWG;             // 32 KB: GZ^T of one chunk, 128 hidden rows x 128 samples
 constexpr uint32_t OFF_SX = 0;
 constexpr uint32_t OFF_SGU = OFF_SX + 2 * SX_PART;          // 24 KB
-constexpr uint32_t OFF_SH = OFF_SGU + 2 * SGU_PART;         // 40 KB
-constexpr uint32_t OFF_SGZ = OFF_SH + 2 * SH_PART;          // 104 KB
-constexpr uint32_t WSLOT = wblob(X1);                       // 16 KB: one weight half-chunk
+constexpr uint32_t OFF_SGZT = OFF_SGU + 2 * SGU_PART;       // 40 KB
+constexpr uint32_t WSLOT = wblob(X1);                       // 16 KB: one forward weight half-chunk
 constexpr int NWSLOT = 3;
-constexpr uint32_t OFF_W = OFF_SGZ + 2 * SH_PART;           // 168 KB
-constexpr uint32_t OFF_BIAS = OFF_W + NWSLOT * WSLOT;       // 216 KB: fc1 biases of both blocks, 2 x 512 floats
+constexpr uint32_t OFF_WF = OFF_SGZT + 2 * SGZ_PART;        // 104 KB: forward ring
+constexpr uint32_t CSLOT = cblob(X1);                       // 32 KB: one backward weight chunk
+constexpr int NCSLOT = 2;
+constexpr uint32_t OFF_WB = OFF_WF + NWSLOT * WSLOT;        // 152 KB: backward ring
+constexpr uint32_t OFF_BIAS = OFF_WB + NCSLOT * CSLOT;      // 216 KB: fc1 biases of both blocks, 2 x 512 floats
 constexpr uint32_t OFF_RED = OFF_BIAS + 2 * HID * 4;        // head / bias-b gradient partials [4 warps][128] floats
 constexpr uint32_t OFF_PAR = OFF_RED + 4 * 128 * 4;         // fc2 biases and head weights, 128 floats
 constexpr int P_B1B = 0, P_B2B = OBS, P_HEAD = OBS + X1;    // offsets inside that block
 constexpr uint32_t OFF_BAR = OFF_PAR + 128 * 4;             // mbarriers, tmem base
-constexpr uint32_t WS_SMEM_BYTES = OFF_BAR + 256;           // 227,584 B of the 232,448 B a CTA may have
+constexpr uint32_t WS_SMEM_BYTES = OFF_BAR + 256;           // 228,096 B of the 232,448 B a CTA may have
 
 // mbarrier indices
-enum { B_ZFULL = 0, B_EFULL = 2, B_HFREE = 4, B_WFULL = 6, B_WFREE = 9, B_DWFULL = 12, B_DWFREE = 13, B_ACC = 14,
-       B_XREADY = 15, B_COUNT = 16 };
+enum { B_ZFULL = 0, B_EFULL = 2, B_WFULL = 4, B_WFREE = 7, B_CFULL = 10, B_CFREE = 12, B_DWFULL = 14, B_DWFREE = 16,
+       B_GZFREE = 18, B_ACC = 19, B_XREADY = 20, B_COUNT = 21 };
 
-// TMEM columns: Z / GH ring of two 64-column slots, weight-gradient accumulators, U and GX
-constexpr uint32_t TM_ZG = 0;        // slot s: Z at s * 128, GH at s * 128 + 64
-constexpr uint32_t TM_DWA = 256;     // 48 columns
-constexpr uint32_t TM_DWB = 352;     // 32 columns
+// TMEM columns: ring of two 128-column slots (forward: Z in the first 64; backward: Z^T | GH^T), two
+// weight-gradient accumulator buffers (dWa 48 | dWb 32 columns each), U and GX
+constexpr uint32_t TM_ZG = 0;
+constexpr uint32_t TM_DW = 256;      // buffer b at + 80 b: dWa at + 0, dWb at + 48
 constexpr uint32_t TM_U = 416;       // 32 columns
 constexpr uint32_t TM_GX = 448;      // 32 columns
 constexpr uint32_t TM_COLS = 512;
@@ -168,8 +195,10 @@ __device__ __forceinline__ uint64_t words_desc(uint32_t lo, uint32_t sbo) {
   return ((uint64_t)(sbo | 0x4000u) << 32) | (uint64_t)lo;
 }
 
-// D (+)= A B over KSTEPS instructions (16 k each); executed by a converged warp, issued by one lane
-template <int PASSES, int KSTEPS>
+// D (+)= A B over KSTEPS instructions (16 k each); executed by a converged warp, issued by one lane.
+// SWAP issues the two small terms of the split product in the other order: a transposed product
+// (A = weights, B = activations) then adds (activation lo x weight hi) first, like the product it mirrors.
+template <int PASSES, int KSTEPS, bool SWAP = false>
 __device__ __forceinline__ void gemm(uint32_t tmem_d, const Opnd& A, const Opnd& B, uint32_t idesc, bool accumulate) {
   if (elect_one()) {
     uint32_t acc = accumulate ? 1u : 0u;
@@ -178,16 +207,22 @@ __device__ __forceinline__ void gemm(uint32_t tmem_d, const Opnd& A, const Opnd&
     for (int kk = 0; kk < KSTEPS; ++kk) {
       const uint64_t ah = words_desc(a0 + kk * A.step, A.sbo), bh = words_desc(b0 + kk * B.step, B.sbo);
       if (PASSES == 3) {  // small terms first
-        tc::mma_bf16(tmem_d, words_desc(a0 + kk * A.step + A.part, A.sbo), bh, idesc, acc); acc = 1u;
-        tc::mma_bf16(tmem_d, ah, words_desc(b0 + kk * B.step + B.part, B.sbo), idesc, acc);
+        const uint64_t al = words_desc(a0 + kk * A.step + A.part, A.sbo), bl = words_desc(b0 + kk * B.step + B.part, B.sbo);
+        if (SWAP) {
+          tc::mma_bf16(tmem_d, ah, bl, idesc, acc); acc = 1u;
+          tc::mma_bf16(tmem_d, al, bh, idesc, acc);
+        } else {
+          tc::mma_bf16(tmem_d, al, bh, idesc, acc); acc = 1u;
+          tc::mma_bf16(tmem_d, ah, bl, idesc, acc);
+        }
       }
       tc::mma_bf16(tmem_d, ah, bh, idesc, acc); acc = 1u;
     }
   }
   __syncwarp();
 }
-// D (+)= A B over the 64 hidden units of a half-chunk with A in tensor memory, as the epilogue warps leave
-// it: per 32 hidden units [16 packed hi columns | 16 packed lo columns], 8 packed columns per instruction
+// D (+)= A B over K = 64 with A in tensor memory, as the epilogue warps leave it: per 32 k [16 packed hi
+// columns | 16 packed lo columns], 8 packed columns per instruction
 template <int PASSES>
 __device__ __forceinline__ void gemm_ts(uint32_t tmem_d, uint32_t tmem_a, const Opnd& B, uint32_t idesc, bool accumulate) {
   if (elect_one()) {
@@ -286,8 +321,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
   unsigned char* smem = ws_smem;
   unsigned char* sX = smem + OFF_SX;
   unsigned char* sGU = smem + OFF_SGU;
-  unsigned char* sH = smem + OFF_SH;
-  unsigned char* sGZ = smem + OFF_SGZ;
+  unsigned char* sGZT = smem + OFF_SGZT;
   float* sBias = reinterpret_cast<float*>(smem + OFF_BIAS);
   float* sRed = reinterpret_cast<float*>(smem + OFF_RED);
   float* sPar = reinterpret_cast<float*>(smem + OFF_PAR);
@@ -302,10 +336,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
   const int ntiles = (a.T + 127) / 128;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(bars + B_ZFULL + i, 1); tc::mbar_init(bars + B_EFULL + i, 8); tc::mbar_init(bars + B_HFREE + i, 1); }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(bars + B_ZFULL + i, 1); tc::mbar_init(bars + B_EFULL + i, 8);
+      tc::mbar_init(bars + B_CFULL + i, 1); tc::mbar_init(bars + B_CFREE + i, 1);
+      tc::mbar_init(bars + B_DWFULL + i, 1); tc::mbar_init(bars + B_DWFREE + i, 4);
+    }
     for (int i = 0; i < NWSLOT; ++i) { tc::mbar_init(bars + B_WFULL + i, 1); tc::mbar_init(bars + B_WFREE + i, 1); }
-    tc::mbar_init(bars + B_DWFULL, 1);
-    tc::mbar_init(bars + B_DWFREE, 4);
+    tc::mbar_init(bars + B_GZFREE, 1);
     tc::mbar_init(bars + B_ACC, 1);
     tc::mbar_init(bars + B_XREADY, 4);
   }
@@ -334,7 +371,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
     const int row = q * 32 + lane;                     // sample row
     const bool owner = ch == 0;                        // threads 0..127 own one sample row each
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
-    uint32_t pz = 0, ph = 0x3, pacc = 0;               // parity bits per ring slot (hfree starts "free")
+    uint32_t pz = 0, pgz = 1, pacc = 0;                // parity bits (per ring slot); the GZ^T tile starts free
     double macc[4] = {0.0, 0.0, 0.0, 0.0};
 
     // one arrive per warp once every lane's TMEM accesses (and, with SMEM, tile stores) are ordered
@@ -344,7 +381,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
       __syncwarp();
       if (lane == 0) mbar_arrive(bar);
     };
-    // 32 rows x 4 packed words (8 bf16 columns) -> one 16-byte granule per row of a 128-row tile
+    // 4 packed words (8 bf16 columns) of this thread's row -> one 16-byte granule of a 128-row tile
     auto st_granule = [&](unsigned char* tile, int col0, const uint32_t* w) {
       *reinterpret_cast<uint4*>(tile + (uint32_t)(col0 >> 3) * ROWG + (uint32_t)row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
     };
@@ -403,12 +440,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
           tc::mbar_wait(bars + B_ZFULL + s, (pz >> s) & 1); pz ^= 1u << s;    // Z (and GH) of half-chunk h are in TMEM
           tc::fence_after_sync();
           PT(0);
-          const float* sBa = sBias + blk * HID + h * HC + ch * 32;
           const uint32_t tz = trow + TM_ZG + s * 128 + ch * 32;
-          const int tcol = s * 64 + ch * 32;                                   // column inside the 128-column tiles
           if (fwd) {
-            // H = lrelu(Z + ba), written back over the columns this warp just read as the A operand of
-            // U += H Wb^T: [hi: 16 packed columns | lo: 16 packed columns]
+            // half-chunk h of 64 hidden units; lane = sample row.  H = lrelu(Z + ba), written back over the
+            // columns this warp just read as the A operand of U += H Wb^T: [hi: 16 packed columns | lo: 16]
+            const float* sBa = sBias + blk * HID + h * HC + ch * 32;
             float v[32];
             tc::tmem_ld16_nowait(tz, v);
             tc::tmem_ld16_nowait(tz + 16, v + 16);
@@ -427,7 +463,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
             tc::tmem_st_wait();
             publish(bars + B_EFULL + s, false);
           } else {
-            // H = lrelu(z), GZ = GH * lrelu'(z), z = Z + ba
+            // unit h = (chunk c of 128 hidden units, half sh of 64 samples), TRANSPOSED: lane = hidden unit, columns
+            // = samples.  H^T = lrelu(z), GZ^T = GH^T * lrelu'(z), z = Z^T + ba, written back over Z^T / GH^T as the
+            // A operands of the weight-gradient products; block 2 also leaves GZ^T in shared memory for GX.
+            const int c = h >> 1, sh = h & 1;
+            const float ba = sBias[blk * HID + c * CH + row];
             float z[32], g[32];
             tc::tmem_ld16_nowait(tz, z);
             tc::tmem_ld16_nowait(tz + 16, z + 16);
@@ -436,40 +476,39 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
             tc::tmem_ld_wait();
             uint32_t hh[16], hl[16], gh[16], gl[16];
 #pragma unroll
-            for (int i4 = 0; i4 < 8; ++i4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(sBa + 4 * i4);   // one broadcast load per 4 biases
-              const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+            for (int i2 = 0; i2 < 16; ++i2) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int i = 4 * i4 + k;
-                const float zz = z[i] + bb[k];
+              for (int k = 0; k < 2; ++k) {
+                const int i = 2 * i2 + k;
+                const float zz = z[i] + ba;
                 const float sl = zz > 0.f ? 1.f : LEAK;       // LeakyReLU slope: h = zz * slope, g_z = g_h * slope
                 z[i] = zz * sl;
                 g[i] = g[i] * sl;
               }
-              tc::split_bf16x2(z[4 * i4], z[4 * i4 + 1], &hh[2 * i4], &hl[2 * i4]);
-              tc::split_bf16x2(z[4 * i4 + 2], z[4 * i4 + 3], &hh[2 * i4 + 1], &hl[2 * i4 + 1]);
-              tc::split_bf16x2(g[4 * i4], g[4 * i4 + 1], &gh[2 * i4], &gl[2 * i4]);
-              tc::split_bf16x2(g[4 * i4 + 2], g[4 * i4 + 3], &gh[2 * i4 + 1], &gl[2 * i4 + 1]);
+              tc::split_bf16x2(z[2 * i2], z[2 * i2 + 1], &hh[i2], &hl[i2]);
+              tc::split_bf16x2(g[2 * i2], g[2 * i2 + 1], &gh[i2], &gl[i2]);
             }
-            if (blk) {   // GZ is also the A operand (in tensor memory, over the GH columns) of GX += GZ Wa
-              tc::tmem_st16(tz + 64, gh);
-              if (PASSES == 3) tc::tmem_st16(tz + 80, gl);
+            tc::tmem_st16(tz, hh);
+            tc::tmem_st16(tz + 64, gh);
+            if (PASSES == 3) {
+              tc::tmem_st16(tz + 16, hl);
+              tc::tmem_st16(tz + 80, gl);
             }
             PT(3);
-            tc::mbar_wait(bars + B_HFREE + s, (ph >> s) & 1); ph ^= 1u << s;    // the tile columns are no longer read
-            PT(1);
+            if (blk) {
+              if (sh == 0) {   // GX of the previous chunk has finished reading the tile
+                tc::mbar_wait(bars + B_GZFREE, pgz); pgz ^= 1;
+              }
+              PT(1);
+              const int scol = sh * 64 + ch * 32;              // sample column inside the [128 hidden x 128 samples] tile
 #pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) {
-              st_granule(sH, tcol + 8 * c8, hh + 4 * c8);
-              st_granule(sGZ, tcol + 8 * c8, gh + 4 * c8);
-              if (PASSES == 3) {
-                st_granule(sH + SH_PART, tcol + 8 * c8, hl + 4 * c8);
-                st_granule(sGZ + SH_PART, tcol + 8 * c8, gl + 4 * c8);
+              for (int c8 = 0; c8 < 4; ++c8) {
+                st_granule(sGZT, scol + 8 * c8, gh + 4 * c8);
+                if (PASSES == 3) st_granule(sGZT + SGZ_PART, scol + 8 * c8, gl + 4 * c8);
               }
             }
-            if (blk) tc::tmem_st_wait();
-            publish(bars + B_EFULL + s, true);
+            tc::tmem_st_wait();
+            publish(bars + B_EFULL + s, blk != 0);
           }
           PT(fwd ? 2 : 3);
         }
@@ -594,9 +633,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
     PT(5);
     if (PROF && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 0 || warp == 4))
       for (int i = 0; i < 8; ++i) ta.prof[(warp ? 8 : 0) + i] = pc[i];
-    // per-CTA metric partials of the row owners (every product has completed: the H tile is free)
+    // per-CTA metric partials of the row owners (every product has completed: the GZ^T tile is free)
     if (owner) {
-      double* red = reinterpret_cast<double*>(sH);
+      double* red = reinterpret_cast<double*>(sGZT);
 #pragma unroll
       for (int k = 0; k < 4; ++k) red[k * 128 + tid] = macc[k];
     }
@@ -606,7 +645,22 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
     const int q = warp - W_FLUSH0;
     const int jrow = q * 32 + lane;                    // hidden unit inside the chunk = TMEM lane
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
-    uint32_t pdw = 0;
+    uint32_t pdw = 0;                                  // parity bit per accumulator buffer
+    // old + new of 16 consecutive floats of this thread's gradient row.  Every address of the CTA's row has ONE
+    // writer (this thread, tile after tile), so a plain load-add-store is the same sequence of IEEE additions as
+    // an atomic; it keeps the load/store unit 3-4x less busy than red.global (which is served lane by lane and
+    // holds up the epilogue warps' shared-memory stores meanwhile), and nobody waits for its latency here.
+    auto accum16 = [&](float* dst, uint32_t taddr) {
+      float4 o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = __ldcg(reinterpret_cast<const float4*>(dst) + i);
+      float v[16];
+      tc::tmem_ld16(taddr, v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        __stcg(reinterpret_cast<float4*>(dst) + i,
+               make_float4(o[i].x + v[4 * i], o[i].y + v[4 * i + 1], o[i].z + v[4 * i + 2], o[i].w + v[4 * i + 3]));
+    };
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       TRACE_END();
       TRACE_BEGIN(3, lane == 0 && warp == W_FLUSH0);
@@ -615,34 +669,27 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
         const int IN = blk ? X1 : OBS;
         const int o_wa = blk ? O_W2A : O_W1A, o_ba = blk ? O_B2A : O_B1A, o_wb = blk ? O_W2B : O_W1B;
 #pragma unroll 1
-        for (int c = 0; c < NHC / 2; ++c) {
+        for (int c = 0; c < NCH; ++c) {
+          const int b = c & 1;
           PT(1);
-          tc::mbar_wait(bars + B_DWFULL, pdw); pdw ^= 1;
+          tc::mbar_wait(bars + B_DWFULL + b, (pdw >> b) & 1); pdw ^= 1u << b;
           tc::fence_after_sync();
           PT(0);
-          const int j = c * 128 + jrow;
+          const uint32_t td = trow + TM_DW + b * 80;
+          const int j = c * CH + jrow;
           float* ga = grow + o_wa + j * IN;
           float* gb = grow + o_wb + j * IN;            // kernel layout: fc2 transposed
-          for (int c0 = 0; c0 < IN; c0 += 16) {
-            float v[16];
-            tc::tmem_ld16(trow + TM_DWA + c0, v);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) red_add4(ga + c0 + 4 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          }
+          const float bias_old = __ldcg(grow + o_ba + j);
+          for (int c0 = 0; c0 < IN; c0 += 16) accum16(ga + c0, td + c0);
           {
             float v[16];
-            tc::tmem_ld16(trow + TM_DWA + 32, v);      // column 32 = sum over samples of g_z = bias gradient
-            red_add1(grow + o_ba + j, v[0]);
+            tc::tmem_ld16(td + 32, v);                 // column 32 = sum over samples of g_z = bias gradient
+            __stcg(grow + o_ba + j, bias_old + v[0]);
           }
-          for (int c0 = 0; c0 < IN; c0 += 16) {
-            float v[16];
-            tc::tmem_ld16(trow + TM_DWB + c0, v);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) red_add4(gb + c0 + 4 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          }
+          for (int c0 = 0; c0 < IN; c0 += 16) accum16(gb + c0, td + 48 + c0);
           tc::fence_before_sync();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bars + B_DWFREE);
+          if (lane == 0) mbar_arrive(bars + B_DWFREE + b);
         }
       }
     }
@@ -653,33 +700,42 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
     reg_dec<88>();
     if (warp == W_TMA && lane == 0) {
       // ==================================================================== weight producer
-      uint32_t pfree = 0x7;                           // all three slots start free
+      uint32_t pfree = 0x7, pcfree = 0x3;             // every ring slot starts free
       int slot = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
 #pragma unroll 1
         for (int pass = 0; pass < 4; ++pass) {
           const int blk = pass_block(pass);
-          const uint32_t bytes = wblob(blk ? X1 : OBS);
+          if (pass < 2) {      // forward: half-chunk blobs through the 3-slot ring
+            const uint32_t bytes = wblob(blk ? X1 : OBS);
 #pragma unroll 1
-          for (int h = 0; h < NHC; ++h) {
-            tc::mbar_wait(bars + B_WFREE + slot, (pfree >> slot) & 1); pfree ^= 1u << slot;
-            tma_load(smem + OFF_W + slot * WSLOT, wblob_g + wblob_off(blk, h), bytes, bars + B_WFULL + slot);
-            slot = slot == NWSLOT - 1 ? 0 : slot + 1;
+            for (int h = 0; h < NHC; ++h) {
+              tc::mbar_wait(bars + B_WFREE + slot, (pfree >> slot) & 1); pfree ^= 1u << slot;
+              tma_load(smem + OFF_WF + slot * WSLOT, wblob_g + wblob_off(blk, h), bytes, bars + B_WFULL + slot);
+              slot = slot == NWSLOT - 1 ? 0 : slot + 1;
+            }
+          } else {             // backward: chunk blobs through the 2-slot ring
+            const uint32_t bytes = cblob(blk ? X1 : OBS);
+#pragma unroll 1
+            for (int c = 0; c < NCH; ++c) {
+              const int b = c & 1;
+              tc::mbar_wait(bars + B_CFREE + b, (pcfree >> b) & 1); pcfree ^= 1u << b;
+              tma_load(smem + OFF_WB + b * CSLOT, wblob_g + cblob_off(blk, c), bytes, bars + B_CFULL + b);
+            }
           }
         }
       }
     } else if (warp == W_MMA) {
       // ==================================================================== the MMA-issuing warp (converged; one elected lane issues)
-      const uint32_t aX = tc::smem_u32(sX), aGU = tc::smem_u32(sGU), aH = tc::smem_u32(sH), aGZ = tc::smem_u32(sGZ),
-                     aW = tc::smem_u32(smem + OFF_W);
-      // activation tiles: K-major (rows = samples are the M index) and MN-major (rows = samples are K)
+      const uint32_t aX = tc::smem_u32(sX), aGU = tc::smem_u32(sGU), aGZT = tc::smem_u32(sGZT),
+                     aWF = tc::smem_u32(smem + OFF_WF), aWB = tc::smem_u32(smem + OFF_WB);
+      // activation tiles: K-major (rows = samples are the M / N index) and MN-major (rows = samples are K)
       constexpr uint32_t RG = ROWG >> 4;
-      const Opnd Xk{aX >> 4, SX_PART >> 4, RG, 8, 2 * RG}, Xm{aX >> 4, SX_PART >> 4, 8, RG, 16};
-      const Opnd GUk{aGU >> 4, SGU_PART >> 4, RG, 8, 2 * RG}, GUm{aGU >> 4, SGU_PART >> 4, 8, RG, 16};
-      const Opnd Hm{aH >> 4, SH_PART >> 4, 8, RG, 16}, GZm{aGZ >> 4, SH_PART >> 4, 8, RG, 16};
-      uint32_t pe = 0, pw = 0, pdfree = 1, px = 0;
-      int wslot_p1 = 0;       // ring slot of the next half-chunk whose Z / GH is to be issued
-      int wslot_p2 = 0;       // ring slot of the next half-chunk whose U / GX is to be issued
+      const Opnd Xk{aX >> 4, SX_PART >> 4, RG, 8, 2 * RG};
+      const Opnd GZTm{aGZT >> 4, SGZ_PART >> 4, 8, RG, 16};   // GZ^T tile read as A = GZ: rows = K = hidden units
+      uint32_t pe = 0, pw = 0, pc_full = 0, pdfree = 0x3, px = 0;
+      int wslot_p1 = 0;       // forward ring slot of the next half-chunk whose Z is to be issued
+      int wslot_p2 = 0;       // forward ring slot of the next half-chunk whose U is to be issued
       auto next_slot = [](int s) { return s == NWSLOT - 1 ? 0 : s + 1; };
 
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -688,93 +744,116 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
 #pragma unroll 1
         for (int pass = 0; pass < 4; ++pass) {
           const int blk = pass_block(pass);
-          const bool fwd = pass < 2;
           const int IN = blk ? X1 : OBS;
-          const uint32_t wp = wpart(IN);
-          const uint32_t id_z = tc::make_idesc_bf16(128, HC, 0, 0), id_gh = tc::make_idesc_bf16(128, HC, 0, 1);
-          const uint32_t id_u = tc::make_idesc_bf16(128, IN, 0, 0), id_gx = tc::make_idesc_bf16(128, IN, 0, 1);
-          const uint32_t id_dwa = tc::make_idesc_bf16(128, XCOLS, 1, 1), id_dwb = tc::make_idesc_bf16(128, IN, 1, 1);
-
-          // Z (and GH) of half-chunk h into ring slot h & 1
-          auto issue_p1 = [&](int h) {
-            const int s = h & 1;
-            PT(4);
-            tc::mbar_wait(bars + B_WFULL + wslot_p1, (pw >> wslot_p1) & 1); pw ^= 1u << wslot_p1;
-            tc::fence_after_sync();
-            PT(2);
-            const uint32_t w = aW + wslot_p1 * WSLOT;
-            // Z = X Wa^T : A = X (K-major), B = Wa (rows = hidden units, K-major), K = IN
-            const Opnd Wk{w >> 4, wp >> 4, HC, 8, 2 * HC};
-            if (blk) gemm<PASSES, 2>(tmem + TM_ZG + s * 128, Xk, Wk, id_z, false);
-            else gemm<PASSES, 1>(tmem + TM_ZG + s * 128, Xk, Wk, id_z, false);
-            if (!fwd) {
-              // GH = GU Wb : A = GU (K-major), B = Wb read MN-major (rows = K = output features, R = IN)
-              const Opnd Wbm{(w + 2 * wp) >> 4, wp >> 4, 8, (uint32_t)IN, 16};
-              if (blk) gemm<PASSES, 2>(tmem + TM_ZG + s * 128 + 64, GUk, Wbm, id_gh, false);
-              else gemm<PASSES, 1>(tmem + TM_ZG + s * 128 + 64, GUk, Wbm, id_gh, false);
-            }
-            PT(5);
-            commit(bars + B_ZFULL + s);
-            if (!fwd && !blk) commit(bars + B_WFREE + wslot_p1);   // backward block 1 has no GX: last reader
-            wslot_p1 = next_slot(wslot_p1);
-          };
-          // U += H Wb^T (forward) or GX += GZ Wa (backward block 2) over the 64 hidden units of half-chunk h
-          auto issue_p2 = [&](int h) {
-            const int s = h & 1;
-            const uint32_t w = aW + wslot_p2 * WSLOT;
-            if (fwd) {   // A = H (tensor memory, over the Z columns), B = Wb (rows = output features, K-major)
-              const Opnd Wbk{(w + 2 * wp) >> 4, wp >> 4, (uint32_t)IN, 8, 2u * IN};
-              gemm_ts<PASSES>(tmem + TM_U, tmem + TM_ZG + s * 128, Wbk, id_u, h > 0);
-            } else {     // A = GZ (tensor memory, over the GH columns), B = Wa read MN-major (rows = K = hidden units)
-              const Opnd Wam{w >> 4, wp >> 4, 8, HC, 16};
-              gemm_ts<PASSES>(tmem + TM_GX, tmem + TM_ZG + s * 128 + 64, Wam, id_gx, h > 0);
-            }
-            PT(6);
-            commit(bars + B_WFREE + wslot_p2);
-          };
-          // weight gradients of the chunk whose two half-chunks sit complete in the H / GZ tiles
-          auto issue_dw = [&]() {
-            PT(4);
-            tc::mbar_wait(bars + B_DWFREE, pdfree); pdfree ^= 1;   // the previous chunk's accumulators were flushed
-            tc::fence_after_sync();
-            PT(3);
-            // dWa = GZ^T [X | 1], dWbT = H^T GU : both operands MN-major (rows = K = samples)
-            gemm<PASSES, 8>(tmem + TM_DWA, GZm, Xm, id_dwa, false);
-            gemm<PASSES, 8>(tmem + TM_DWB, Hm, GUm, id_dwb, false);
-            PT(7);
-            commit(bars + B_DWFULL);
-            commit(bars + B_HFREE + 0);
-            commit(bars + B_HFREE + 1);
-          };
-
           PT(4);
           tc::mbar_wait(bars + B_XREADY, px); px ^= 1;    // the pass's input tile (X or GU) is published
           tc::fence_after_sync();
           PT(0);
-          issue_p1(0);
-          issue_p1(1);
+          if (pass < 2) {
+            // ============================================================== forward: half-chunks of 64 hidden units
+            const uint32_t wp = wpart(IN);
+            const uint32_t id_z = tc::make_idesc_bf16(128, HC, 0, 0), id_u = tc::make_idesc_bf16(128, IN, 0, 0);
+            // Z of half-chunk h into ring slot h & 1: A = X (K-major), B = Wa (rows = hidden units, K-major), K = IN
+            auto issue_z = [&](int h) {
+              const int s = h & 1;
+              PT(4);
+              tc::mbar_wait(bars + B_WFULL + wslot_p1, (pw >> wslot_p1) & 1); pw ^= 1u << wslot_p1;
+              tc::fence_after_sync();
+              PT(2);
+              const uint32_t w = aWF + wslot_p1 * WSLOT;
+              const Opnd Wk{w >> 4, wp >> 4, HC, 8, 2 * HC};
+              if (blk) gemm<PASSES, 2>(tmem + TM_ZG + s * 128, Xk, Wk, id_z, false);
+              else gemm<PASSES, 1>(tmem + TM_ZG + s * 128, Xk, Wk, id_z, false);
+              PT(5);
+              commit(bars + B_ZFULL + s);
+              wslot_p1 = next_slot(wslot_p1);
+            };
+            issue_z(0);
+            issue_z(1);
 #pragma unroll 1
-          for (int h = 0; h < NHC; ++h) {
-            const int s = h & 1;
-            PT(4);
-            tc::mbar_wait(bars + B_EFULL + s, (pe >> s) & 1); pe ^= 1u << s;   // operand tiles of half-chunk h are written
-            tc::fence_after_sync();
-            PT(1);
-            if (fwd) {
-              issue_p2(h);
-              wslot_p2 = next_slot(wslot_p2);
-              if (h + 2 < NHC) issue_p1(h + 2);
-            } else {
-              if (s == 0) {
-                if (blk) issue_p2(h);
+            for (int h = 0; h < NHC; ++h) {
+              const int s = h & 1;
+              PT(4);
+              tc::mbar_wait(bars + B_EFULL + s, (pe >> s) & 1); pe ^= 1u << s;   // H of half-chunk h sits packed in the slot
+              tc::fence_after_sync();
+              PT(1);
+              {   // U += H Wb^T: A = H (tensor memory), B = Wb (rows = output features, K-major)
+                const uint32_t w = aWF + wslot_p2 * WSLOT;
+                const Opnd Wbk{(w + 2 * wp) >> 4, wp >> 4, (uint32_t)IN, 8, 2u * IN};
+                gemm_ts<PASSES>(tmem + TM_U, tmem + TM_ZG + s * 128, Wbk, id_u, h > 0);
+                PT(6);
+                commit(bars + B_WFREE + wslot_p2);
                 wslot_p2 = next_slot(wslot_p2);
-                if (h + 2 < NHC) issue_p1(h + 2);
-              } else {
-                if (blk) issue_p2(h);                    // before Z / GH of h + 2 overwrite the slot GZ sits in
-                wslot_p2 = next_slot(wslot_p2);
-                if (h + 2 < NHC) issue_p1(h + 2);
-                issue_dw();
               }
+              if (h + 2 < NHC) issue_z(h + 2);
+            }
+          } else {
+            // ============================================================== backward: chunks of 128 hidden units x halves
+            // of 64 samples, transposed (D lanes = hidden units)
+            const uint32_t cp = cpart(IN);
+            const uint32_t id_zt = tc::make_idesc_bf16(128, 64, 0, 0), id_ght = tc::make_idesc_bf16(128, 64, 1, 0);
+            const uint32_t id_dwa = tc::make_idesc_bf16(128, XCOLS, 0, 1), id_dwb = tc::make_idesc_bf16(128, IN, 0, 1);
+            const uint32_t id_gx = tc::make_idesc_bf16(128, IN, 1, 1);
+            // Z^T = Wa X^T and GH^T = Wb^T GU^T of unit u = (chunk u / 2, sample half u % 2) into ring slot u & 1
+            auto issue_zt = [&](int u) {
+              const int c = u >> 1, sh = u & 1, b = c & 1;
+              if (sh == 0) {
+                PT(4);
+                tc::mbar_wait(bars + B_CFULL + b, (pc_full >> b) & 1); pc_full ^= 1u << b;
+                tc::fence_after_sync();
+                PT(2);
+              }
+              const uint32_t w = aWB + b * CSLOT;
+              const Opnd Wa_k{w >> 4, cp >> 4, CH, 8, 2 * CH};                                // rows = hidden units = M
+              const Opnd Wb_m{(w + 2 * cp) >> 4, cp >> 4, 8, (uint32_t)IN, 16};               // rows = K = output features
+              const Opnd Xs{(aX >> 4) + 64 * sh, SX_PART >> 4, RG, 8, 2 * RG};                // the 64 sample rows = N
+              const Opnd GUs{(aGU >> 4) + 64 * sh, SGU_PART >> 4, RG, 8, 2 * RG};
+              const uint32_t d = tmem + TM_ZG + sh * 128;
+              if (blk) {
+                gemm<PASSES, 2, true>(d, Wa_k, Xs, id_zt, false);
+                gemm<PASSES, 2, true>(d + 64, Wb_m, GUs, id_ght, false);
+              } else {
+                gemm<PASSES, 1, true>(d, Wa_k, Xs, id_zt, false);
+                gemm<PASSES, 1, true>(d + 64, Wb_m, GUs, id_ght, false);
+              }
+              PT(5);
+              commit(bars + B_ZFULL + sh);
+              if (!blk && sh == 1) commit(bars + B_CFREE + b);    // backward block 1 has no GX: last reader of the chunk
+            };
+            issue_zt(0);
+            issue_zt(1);
+#pragma unroll 1
+            for (int u = 0; u < 2 * NCH; ++u) {
+              const int c = u >> 1, sh = u & 1, b = c & 1;
+              PT(4);
+              tc::mbar_wait(bars + B_EFULL + sh, (pe >> sh) & 1); pe ^= 1u << sh;   // H^T / GZ^T of unit u sit packed in the slot
+              tc::fence_after_sync();
+              PT(1);
+              if (sh == 1 && blk) {   // GX += GZ Wa over the chunk's 128 hidden units: both operands MN-major (rows = K).
+                // First: the next chunk's epilogue waits for the GZ^T tile
+                const uint32_t w = aWB + b * CSLOT;
+                const Opnd Wa_m{w >> 4, cp >> 4, 8, CH, 16};
+                gemm<PASSES, 8>(tmem + TM_GX, GZTm, Wa_m, id_gx, c > 0);
+                PT(6);
+                commit(bars + B_GZFREE);
+                commit(bars + B_CFREE + b);
+              }
+              if (sh == 0) {
+                PT(4);
+                tc::mbar_wait(bars + B_DWFREE + b, (pdfree >> b) & 1); pdfree ^= 1u << b;   // accumulator buffer b was flushed
+                tc::fence_after_sync();
+                PT(3);
+              }
+              {   // dWa += GZ^T [X | 1], dWbT += H^T GU over the unit's 64 samples: A in tensor memory, B MN-major
+                const Opnd Xs{(aX >> 4) + 64 * sh, SX_PART >> 4, 8, RG, 16};
+                const Opnd GUs{(aGU >> 4) + 64 * sh, SGU_PART >> 4, 8, RG, 16};
+                const uint32_t slot = tmem + TM_ZG + sh * 128, d = tmem + TM_DW + b * 80;
+                gemm_ts<PASSES>(d, slot + 64, Xs, id_dwa, sh > 0);
+                gemm_ts<PASSES>(d + 48, slot, GUs, id_dwb, sh > 0);
+                PT(7);
+                if (sh == 1) commit(bars + B_DWFULL + b);
+              }
+              if (u + 2 < 2 * NCH) issue_zt(u + 2);
             }
           }
           commit(bars + B_ACC);                   // everything issued so far: U / GX / the tile is complete
@@ -790,7 +869,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
   tc::fence_before_sync();
   __syncthreads();
   if (tid < 4) {
-    const double* red = reinterpret_cast<const double*>(sH);
+    const double* red = reinterpret_cast<const double*>(sGZT);
     double t = 0.0;
     for (int m = 0; m < 128; ++m) t += red[tid * 128 + m];
     a.mpart[((size_t)net * gridDim.x + blockIdx.x) * 4 + tid] = t;

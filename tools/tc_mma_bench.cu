@@ -134,7 +134,41 @@ __global__ void __launch_bounds__(384) bench_kernel(Args p) {
     // back to back in the instruction stream
     __syncwarp();
     const long long t0 = clock64();
-    if (elect_one()) {
+    if (p.stress_kind >= 10) {
+      // kernel-like burst pattern (numerics not checked): per rep 24 TS MMAs (N = 48 / 32) + commit, 24 SS MMAs
+      // (N = 32) + 2 commits, 12 SS MMAs (N = 64) + commit; 10 = as described, 11 = no commits, 12 = wait after
+      // every commit, 13 = commits by re-electing for each one like the library's commit()
+      const uint32_t id48 = tc::make_idesc_bf16(128, 48, 0, 1), id32 = tc::make_idesc_bf16(128, 32, 0, 0),
+                     id64 = tc::make_idesc_bf16(128, 64, 0, 0);
+      const uint64_t a_k = tc::make_desc(a0, 128 * 16, 128), b_k = tc::make_desc(b0, 64 * 16, 128), b_m = tc::make_desc(b0, 128, 128 * 16);
+      uint32_t ph1 = 0;
+      for (int rep = 0; rep < p.reps; ++rep) {
+        if (elect_one()) {
+#pragma unroll
+          for (int i = 0; i < 12; ++i) mma_ts(tmem + 128, tmem + TM_A + (i & 3) * 8, b_m + (i & 3) * 16, id48, i > 0);
+#pragma unroll
+          for (int i = 0; i < 12; ++i) mma_ts(tmem + 192, tmem + TM_A + (i & 3) * 8, b_m + (i & 3) * 16, id32, i > 0);
+          if (p.stress_kind == 10 || p.stress_kind == 12) tc::mma_commit(&bars[1]);
+        }
+        __syncwarp();
+        if (p.stress_kind == 13) { if (elect_one()) tc::mma_commit(&bars[1]); __syncwarp(); }
+        if (elect_one()) {
+#pragma unroll
+          for (int i = 0; i < 24; ++i) tc::mma_bf16(tmem + 224, a_k + (i & 7) * 256, b_k + (i & 7) * 128, id32, i > 0);
+          if (p.stress_kind == 10 || p.stress_kind == 12) { tc::mma_commit(&bars[2]); tc::mma_commit(&bars[3]); }
+        }
+        __syncwarp();
+        if (p.stress_kind == 13) { if (elect_one()) tc::mma_commit(&bars[2]); __syncwarp(); if (elect_one()) tc::mma_commit(&bars[3]); __syncwarp(); }
+        if (p.stress_kind == 12) { tc::mbar_wait(&bars[2], ph1); ph1 ^= 1; }
+        if (elect_one()) {
+#pragma unroll
+          for (int i = 0; i < 12; ++i) tc::mma_bf16(tmem, a_k + (i & 1) * 256, b_k + (i & 1) * 128, id64, (i & 1));
+          if (p.stress_kind == 10 || p.stress_kind == 12) tc::mma_commit(&bars[1]);
+        }
+        __syncwarp();
+        if (p.stress_kind == 13) { if (elect_one()) tc::mma_commit(&bars[1]); __syncwarp(); }
+      }
+    } else if (elect_one()) {
       if (ks == 8) {
         if (p.a_src == 2) {
           for (int rep = 0; rep < p.reps; ++rep) {
@@ -200,6 +234,27 @@ __global__ void __launch_bounds__(384) bench_kernel(Args p) {
         float t[16];
         tc::tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + 384 + (warp >> 2) * 16, t);
         sink ^= __float_as_uint(t[0]);
+      } else if (p.stress_kind == 4) {   // tcgen05.st of 16 columns
+        uint32_t r[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = tid + i;
+        tc::tmem_st16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + 384 + (warp >> 2) * 16, r);
+        tc::tmem_st_wait();
+      } else if (p.stress_kind == 5) {   // an epilogue-like mix: tcgen05.ld x2, 32 multiplies, 16 conversions, tcgen05.st x2
+        float t[32];
+        const uint32_t ta_ = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 384 + (warp >> 2) * 32;
+        tc::tmem_ld16_nowait(ta_, t);
+        tc::tmem_ld16_nowait(ta_ + 16, t + 16);
+        tc::tmem_ld_wait();
+        uint32_t r[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float a_ = t[2 * i] * f0, b_ = t[2 * i + 1] * f1;
+          asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r[i]) : "f"(a_), "f"(b_));
+        }
+        tc::tmem_st16(ta_, r);
+        tc::tmem_st16(ta_ + 16, r);
+        tc::tmem_st_wait();
       } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -285,12 +340,13 @@ int main(int argc, char** argv) {
       for (int N : {16, 32, 48, 64}) cases.push_back({128, N, 128, a_src, 0, 0, 0, is});
   for (int is : {2, 4}) cases.push_back({128, 48, 128, 1, 1, 0, 0, is});
   // what slows the MMA stream down: ALU / conversion work, TMEM loads or shared-memory loads in 8 other warps?
-  for (int kind : {1, 2, 3})
+  for (int kind : {1, 2, 3, 4, 5})
     for (int st : {8}) {
       cases.push_back({128, 64, 32, 0, 0, st, 0, 1, kind});     // Z-like: SS, N = 64
       cases.push_back({128, 32, 128, 2, 0, st, 0, 1, kind});    // U / GX-like: TS, N = 32
       cases.push_back({128, 48, 128, 1, 1, st, 0, 1, kind});    // dW-like
     }
+  for (int pat : {10, 11, 12, 13}) cases.push_back({128, 64, 128, 2, 0, 0, 0, 1, pat});
   if (only == -2) { printf("%d\n", (int)cases.size()); return 0; }
   int idx = -1;
   for (const Case& c : cases) {
