@@ -11,7 +11,8 @@
 //   warps 0-7   epilogue: TMEM -> bias / LeakyReLU / derivative -> bf16 hi|lo split -> written back IN
 //               PLACE into tensor memory as the A operand of the next products; warps 0-3 also own one
 //               sample row each (block outputs, heads, losses)
-//   warps 8-11  weight-gradient flush: TMEM (lane = hidden unit) -> the CTA's partial-gradient row
+//   warps 8-11  weight-gradient flush: TMEM (lane = hidden unit) -> red.global.add into the CTA's
+//               partial-gradient row
 //   warp 12     issues every tcgen05.mma (converged warp, one elected lane)
 //   warp 13     one thread streams pre-tiled weights through TMA rings
 //
@@ -646,20 +647,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
     const int jrow = q * 32 + lane;                    // hidden unit inside the chunk = TMEM lane
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t pdw = 0;                                  // parity bit per accumulator buffer
-    // old + new of 16 consecutive floats of this thread's gradient row.  Every address of the CTA's row has ONE
-    // writer (this thread, tile after tile), so a plain load-add-store is the same sequence of IEEE additions as
-    // an atomic; it keeps the load/store unit 3-4x less busy than red.global (which is served lane by lane and
-    // holds up the epilogue warps' shared-memory stores meanwhile), and nobody waits for its latency here.
+    // fire-and-forget accumulation into the CTA's own partial-gradient row: the L2 does the fp32 add, so the
+    // thread never waits for the old value (every address has ONE writer, in tile order -> the sum is the same
+    // sequence of IEEE additions as a load-add-store; a load-add-store flush was tried and is slower: its five
+    // dependent round trips per chunk take 5.5 k cycles against 2 k for the reds; pausing between the reds to leave
+    // the load/store unit to the epilogue warps changes nothing)
     auto accum16 = [&](float* dst, uint32_t taddr) {
-      float4 o[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) o[i] = __ldcg(reinterpret_cast<const float4*>(dst) + i);
       float v[16];
       tc::tmem_ld16(taddr, v);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        __stcg(reinterpret_cast<float4*>(dst) + i,
-               make_float4(o[i].x + v[4 * i], o[i].y + v[4 * i + 1], o[i].z + v[4 * i + 2], o[i].w + v[4 * i + 3]));
+      for (int i = 0; i < 4; ++i) red_add4(dst + 4 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     };
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       TRACE_END();
@@ -679,12 +676,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
           const int j = c * CH + jrow;
           float* ga = grow + o_wa + j * IN;
           float* gb = grow + o_wb + j * IN;            // kernel layout: fc2 transposed
-          const float bias_old = __ldcg(grow + o_ba + j);
           for (int c0 = 0; c0 < IN; c0 += 16) accum16(ga + c0, td + c0);
           {
             float v[16];
             tc::tmem_ld16(td + 32, v);                 // column 32 = sum over samples of g_z = bias gradient
-            __stcg(grow + o_ba + j, bias_old + v[0]);
+            red_add1(grow + o_ba + j, v[0]);
           }
           for (int c0 = 0; c0 < IN; c0 += 16) accum16(gb + c0, td + 48 + c0);
           tc::fence_before_sync();

@@ -123,3 +123,46 @@ def test_learn_on_vecenv_in_bf16_mode(tmp_path):
     assert torch.isfinite(agent.flat).all() and not torch.equal(before, agent.flat)
     s = agent.logger["summary"]
     assert np.isfinite(list(s.values())).all()
+
+
+def _raw_handle(prec, max_samples, single_role):
+    """A navppo handle outside the cache; `single_role` picks the first tcgen05 kernel (navppo_tc.cu)."""
+    import ctypes
+    import os
+    if single_role:
+        os.environ["NAVPPO_TC_KERNEL"] = "single"
+    try:
+        cfg = _capi.default_ppo_cfg()
+        cfg.device = 0
+        cfg.max_samples = int(max_samples)
+        cfg.precision = int(prec)
+        h = ctypes.c_void_p()
+        _capi.check(_capi.lib().navppo_create(ctypes.byref(h), ctypes.byref(cfg)))
+    finally:
+        os.environ.pop("NAVPPO_TC_KERNEL", None)
+    return h
+
+
+@pytest.mark.parametrize("prec", [_capi.PREC_BF16X3, _capi.PREC_BF16])
+@pytest.mark.parametrize("T", [1, 127, 128, 129, 5000, 74 * 128 * 3 + 17])
+def test_warp_specialised_kernel_is_bit_identical_to_the_single_role_kernel(T, prec):
+    """The warp-specialised kernel (transposed backward pass, operands in tensor memory, mbarrier
+    pipeline) issues every product in the first kernel's k-order and pass order: same bits, for
+    ragged sizes from one sample to several tiles per CTA."""
+    g = golden("ppo_learn_b")
+    rng = np.random.RandomState(T)
+    idx = rng.randint(0, len(g["obs"]), T)
+    obs = (g["obs"][idx] + rng.normal(scale=0.01, size=(T, 16))).astype(np.float32)
+    act, lp, rtg = g["acts"][idx], (g["logp"][idx] + rng.normal(scale=0.1, size=T)).astype(np.float32), g["rtgs"][idx]
+    adv = rng.normal(size=T).astype(np.float32)
+    flat = _flat_from(g["actor_after"], g["critic_after"])
+    o, a_, l_, ad, rt = _t(obs), _t(act), _t(lp), _t(adv), _t(rtg)
+    out = []
+    for single in (True, False):
+        h = _raw_handle(prec, max(T, 1024), single)
+        grad, met = _grad(h, flat, o, a_, l_, ad, rt, T, float(g["var"]))
+        out.append((grad.clone(), met.copy()))
+        _capi.lib().navppo_destroy(h)
+    assert torch.equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1])
+    assert float(out[1][0].abs().max()) > 0
