@@ -32,6 +32,11 @@ import numpy as np  # noqa: E402
 #   write: pose 24 + past_dist 8 + prev_action 8 + ep stats 12 + steps 4 + obs 64 + rew 4 + flags 3     = 127
 BYTES_PER_ENV_STEP = 84 + 127
 BYTES_PER_ENV_STEP_SCRIPTED = BYTES_PER_ENV_STEP - 8  # actions drawn in-kernel, not read
+# SURVEY.md 8(d), the contract figure: fp32 SoA 44 B read + 106 B written = 150 B (174 B with the pose kept in
+# fp64, which is what this simulator stores); the 203 B above adds what the kernel also moves per step (episode
+# return / path length / last move, draw counter, timeout flag, goal as fp64).  All three are reported.
+BYTES_SURVEY = 150
+BYTES_SURVEY_FP64_POSE = 174
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full`
 # capture of the same kernel and shape (profiles/README.md names the file); keyed by (N, H)
 NCU_TRAFFIC_BYTES_PER_LAUNCH = {(8192, 128): 739072 + 17440768}   # profiles/r01p_step_8192_fused_ncu.csv
@@ -99,23 +104,42 @@ class ClockSampler:
                 "reasons": reasons}
 
 
-def cpu_port_throughput(n_agents: int, seconds: float, threads: int):
-    """The C oracle (oracle/navsim_oracle.c) stepping the same stage_1 workload on host cores."""
-    from navbot_ppo_b200 import _capi, maps
-    from oracle import binding
-    cfg = _capi.default_cfg(n_agents)
-    cfg.seed = 0
-    sim = binding.OracleSim(cfg, maps.get_map("stage_1"), nthreads=threads)
-    sim.reset()
-    acts = [binding.scripted_actions(0, 0, t, n_agents) for t in range(16)]
-    for t in range(4):
-        sim.step(acts[t])
-    t0 = time.perf_counter()
-    steps = 0
-    while time.perf_counter() - t0 < seconds:
-        sim.step(acts[steps % 16])
-        steps += 1
-    dt = time.perf_counter() - t0
+def workload_string(n_per_gpu: int, horizon: int) -> str:
+    """config.workload, identical in both arms."""
+    return (f"stage_1 map, {n_per_gpu} agents/GPU, 10-beam LiDAR, 16-D obs / 2-D action, {horizon} env steps per bench "
+            f"step, scripted Philox actions, auto-reset episodes (cap 500)")
+
+
+class CpuPort:
+    """The C restatement of the reference path (oracle/navsim_oracle.c) on host threads: test
+    infrastructure, used here only as the reported CPU baseline / reference arm.  Nothing of the product
+    package is imported on this path (the stage_1 geometry and the reference constants are restated in
+    oracle/)."""
+
+    def __init__(self, n_agents: int, threads: int):
+        from oracle import binding
+        self.n, self.threads = n_agents, threads
+        cfg = binding.default_cfg(n_agents)
+        cfg.seed = 0
+        self.sim = binding.OracleSim(cfg, binding.stage_1_segments(), nthreads=threads)
+        self.sim.reset()
+        self.step0 = 0
+
+    def run(self, nsteps: int) -> float:
+        """nsteps consecutive Env.step calls for every agent (scripted actions, in C); seconds taken."""
+        t0 = time.perf_counter()
+        self.sim.run_scripted(nsteps, action_seed=0, step0=self.step0)
+        self.step0 += nsteps
+        return time.perf_counter() - t0
+
+
+def cpu_port_throughput(n_agents: int, seconds: float, threads: int, chunk: int = 32):
+    port = CpuPort(n_agents, threads)
+    port.run(4)
+    steps, dt = 0, 0.0
+    while dt < seconds:
+        dt += port.run(chunk)
+        steps += chunk
     return n_agents * steps / dt, steps, dt
 
 
@@ -166,32 +190,32 @@ def training_bench(args, torch, dist, dev, rank, world, barrier):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the CPU port of the same path with every host core.  (The
-    reference itself is Python over ROS/Gazebo and cannot travel to this box; the oracle
-    port is its restatement, pinned to it by tests/golden.)"""
+    """--impl reference: the CPU restatement of the same path with every host core, on the SAME workload as
+    the GPU arm (one bench step = H consecutive Env.step calls for all agents of the job).  (The reference
+    itself is Python over ROS/Gazebo and cannot travel to this box; the oracle port is its restatement,
+    pinned to it by tests/golden.)"""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n = args.agents
-    per_step = []
-    tot_steps = 0
-    for i in range(args.warmup + args.steps):
-        v, nsteps, dt = cpu_port_throughput(n, args.ref_seconds, threads)
-        if i >= args.warmup:
-            per_step.append((v, nsteps, dt))
-            tot_steps += nsteps
-    env_steps = sum(n * s for _, s, _ in per_step)
-    secs = sum(d for _, _, d in per_step)
-    value = env_steps / secs
+    n_total = args.agents * max(1, args.gpus)
+    port = CpuPort(n_total, threads)
+    H = args.horizon
+    for _ in range(max(args.warmup, 1)):
+        port.run(H)
+    secs = 0.0
+    for _ in range(args.steps):
+        secs += port.run(H)
+    value = n_total * H * args.steps / secs
     line = {
         "impl": "reference", "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"stage_1 map, {n} agents, 10-beam LiDAR, 16-D obs / 2-D action, scripted actions",
-                   "agents": n},
+        "config": {"workload": workload_string(args.agents, H), "agents_per_gpu": args.agents, "horizon": H,
+                   "agents_total": n_total},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.ref_seconds:.0f} s of Env.step per bench step over {n} agents, "
-                                   f"C port (oracle/navsim_oracle.c), {threads} pthreads"},
+                         "sample": f"{args.steps} bench steps of {H} Env.step calls over {n_total} agents "
+                                   f"({n_total * H * args.steps} env-steps, {secs:.2f} s), C port "
+                                   f"(oracle/navsim_oracle.c), {threads} pooled pthreads, no Python between steps"},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -290,6 +314,21 @@ def main():
     b_ev.record()
     torch.cuda.synchronize()
     single_launch_us = a_ev.elapsed_time(b_ev) * 1e3 / H
+    # ---- and with the actions in a device tensor, one Env.step launch per step: what a policy-driven caller
+    # ---- (PPO.rollout) pays for the simulator
+    act_dev = torch.rand((N, 2), device=dev)
+    env.step(act_dev)
+    barrier()
+    a_ev.record()
+    for _ in range(H):
+        env.step(act_dev)
+    b_ev.record()
+    torch.cuda.synchronize()
+    policy_step_us = a_ev.elapsed_time(b_ev) * 1e3 / H
+    t = torch.tensor([policy_step_us], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    value_policy_step = world * N / (float(t.item()) * 1e-6)
 
     # ---- end to end through the host-buffer entry point (navsim_step_host) ----------------
     He = H
@@ -333,10 +372,16 @@ def main():
 
     # ---- roofline of the step kernel: live CUDA-event duration per launch -----------------
     per_launch_s = (ms_total * 1e-3) / K
-    achieved = BYTES_PER_ENV_STEP_SCRIPTED * N * H / per_launch_s / 1e9
     fused_bytes = (64 + 4 + 3) + (BYTES_PER_ENV_STEP_SCRIPTED - 71) / H   # outputs every step, state once per launch
+    def by_def(nbytes):
+        a_ = nbytes * N * H / per_launch_s / 1e9
+        return {"bytes_per_env_step": nbytes, "achieved": a_, "frac": a_ / peak_gbs}
+    achieved = BYTES_SURVEY * N * H / per_launch_s / 1e9        # the contract figure: SURVEY.md 8(d), 150 B / env-step
     roofline = {"kernel": "navsim_step_kernel", "bound": "hbm", "achieved": achieved, "peak": peak_gbs,
                 "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get((N, H)),
+                "definition": "SURVEY.md 8(d): 150 B per env-step (44 B read + 106 B written, fp32 SoA)",
+                "by_definition": {"survey_150B": by_def(BYTES_SURVEY), "survey_fp64_pose_174B": by_def(BYTES_SURVEY_FP64_POSE),
+                                  "kernel_state_203B": by_def(BYTES_PER_ENV_STEP_SCRIPTED)},
                 "peak_source": peak_src, "bytes_per_env_step": BYTES_PER_ENV_STEP_SCRIPTED,
                 "env_steps_per_launch": N * H, "us_per_launch": per_launch_s * 1e6, "us_per_env_step_batch": per_launch_s * 1e6 / H,
                 "lanes_per_agent": env.lanes_per_agent,
@@ -421,12 +466,13 @@ def main():
         "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"stage_1 map, {N} agents/GPU, 10-beam LiDAR, 16-D obs / 2-D action, "
-                               f"{H} env steps per bench step, scripted Philox actions, auto-reset episodes (cap 500)",
-                   "agents_per_gpu": N, "horizon": H, "launches_per_bench_step": 1,
+        "config": {"workload": workload_string(N, H), "agents_per_gpu": N, "horizon": H, "launches_per_bench_step": 1,
                    "l2": "flushed between timed steps (256 MiB write, untimed)",
                    "parallelism": f"agents sharded x{world}, no data-path collective"},
         "clocks": clocks,
+        "value_policy_step": {"value": value_policy_step, "unit": "env-steps/s", "us_per_launch": policy_step_us,
+                              "note": "actions from a device tensor, ONE navsim_step launch per env step (no fusion over "
+                                      "steps): the simulator's share of a policy-driven rollout"},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N * 8 * H,
                 "d2h_bytes_per_step": N * (64 + 4 + 3) * H,
                 "api": "navsim_step_host via VecEnv.step_host: host actions in, host obs/reward/flags out, every env step; "

@@ -114,6 +114,16 @@ int navppo_rollout(navppo_t* h, navsim_t* sim, const float* params, int32_t H, d
                    int64_t agent_id_offset, uint32_t draw0, float* obs, float* next_obs, float* act, float* logp, float* rew,
                    uint8_t* done, uint8_t* arrive, uint8_t* trunc, float* ep_return, float* ep_path, void* stream);
 
+/* The same loop with two extras for replaying it as a captured CUDA graph and for device-side episode
+ * bookkeeping: ep_len[H,N] (may be NULL) receives, at the step that ends an episode, its length in steps
+ * (batch_lens, ppo.py:583); dyn_dev (may be NULL) points to two device words {float bits of the variance,
+ * increment of the noise counter} that the sampling epilogue reads at run time INSTEAD of `var` and in
+ * addition to `draw0`, so one captured launch sequence serves every rollout. */
+int navppo_rollout_ex(navppo_t* h, navsim_t* sim, const float* params, int32_t H, double var, uint64_t seed,
+                      int64_t agent_id_offset, uint32_t draw0, float* obs, float* next_obs, float* act, float* logp,
+                      float* rew, uint8_t* done, uint8_t* arrive, uint8_t* trunc, float* ep_return, float* ep_path,
+                      int32_t* ep_len, const uint32_t* dyn_dev, void* stream);
+
 /* Advantage, ppo.py:277,284, in two halves so a multi-GPU run can all-reduce the three
  * doubles in between: stats[0..2] += (sum, sum of squares, count) of A = rtg - v over T rows;
  * then adv = (A - mean) / (unbiased std + 1e-10). */

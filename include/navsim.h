@@ -135,6 +135,7 @@ typedef struct navsim_step_out {
   uint8_t* trunc;      /* [N] or NULL */
   float* ep_return;    /* [N] or NULL */
   float* ep_path;      /* [N] or NULL */
+  int32_t* ep_len;     /* [N] or NULL: the episode's length in steps (batch_lens, ppo.py:583), same rule */
 } navsim_step_out;
 int navsim_step_ex(navsim_t* h, const float* act_dev, const navsim_step_out* out, void* stream);
 

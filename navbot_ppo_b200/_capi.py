@@ -45,7 +45,7 @@ class NavsimCfg(ctypes.Structure):
 
 
 class NavsimStepOut(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_void_p) for n in ("obs", "rew", "done", "arrive", "trunc", "ep_return", "ep_path")]
+    _fields_ = [(n, ctypes.c_void_p) for n in ("obs", "rew", "done", "arrive", "trunc", "ep_return", "ep_path", "ep_len")]
 
 
 class NavsimStats(ctypes.Structure):
@@ -119,6 +119,7 @@ NAVPPO_SYMBOLS = {
     "navppo_act": (ctypes.c_int, [_vp, _vp, _vp, _i32, _f64, _u64, _i64, _u32, _vp, _vp, _vp, _vp, _vp]),
     "navppo_evaluate": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _f64, _vp, _vp, _vp]),
     "navppo_rollout": (ctypes.c_int, [_vp, _vp, _vp, _i32, _f64, _u64, _i64, _u32] + [_vp] * 11),
+    "navppo_rollout_ex": (ctypes.c_int, [_vp, _vp, _vp, _i32, _f64, _u64, _i64, _u32] + [_vp] * 13),
     "navppo_adv_stats": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp]),
     "navppo_adv_normalize": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "navppo_grad": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _f64, _vp, _vp, _vp]),

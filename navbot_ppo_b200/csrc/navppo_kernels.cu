@@ -126,6 +126,9 @@ struct InferArgs {
   float* logp;           // [T]
   // evaluate
   const float* act_in;   // [T,2]
+  // act, optional: device words {float bits of var, draw increment} read at run time, so that a captured
+  // CUDA graph of the rollout can be replayed with a new variance / noise counter
+  const uint32_t* dyn;
 };
 
 // ----------------------------------------------------------------------------------------
@@ -340,6 +343,8 @@ __global__ void __launch_bounds__(CF_THREADS) mlp_infer_kernel(InferArgs a) {
       continue;
     }
     const float m0 = sigmoidf_(o1), m1 = tanhf(o2);  // net_actor.py:141-142
+    const float var_ = (MODE == INFER_ACT && a.dyn) ? __uint_as_float(a.dyn[0]) : a.var;
+    const uint32_t draw_ = (MODE == INFER_ACT && a.dyn) ? a.draw + a.dyn[1] : a.draw;
     if (MODE == INFER_FORWARD) {
       reinterpret_cast<float2*>(a.mu)[i] = make_float2(m0, m1);
     } else if (MODE == INFER_ACT) {
@@ -350,7 +355,7 @@ __global__ void __launch_bounds__(CF_THREADS) mlp_infer_kernel(InferArgs a) {
       } else {  // Box-Muller on two Philox words
         uint32_t r[4];
         const uint64_t agent = (uint64_t)(a.agent_off + i);
-        nv_philox4x32_10(a.draw, 2u, (uint32_t)agent, (uint32_t)(agent >> 32), (uint32_t)a.seed,
+        nv_philox4x32_10(draw_, 2u, (uint32_t)agent, (uint32_t)(agent >> 32), (uint32_t)a.seed,
                          (uint32_t)(a.seed >> 32), r);
         const float uu = ((float)(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0, 1)
         const float vv = ((float)(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
@@ -359,12 +364,12 @@ __global__ void __launch_bounds__(CF_THREADS) mlp_infer_kernel(InferArgs a) {
         sincosf(6.283185307179586f * vv, &sn, &cs);
         e0 = rad * cs; e1 = rad * sn;
       }
-      const float sd = sqrtf(a.var);
+      const float sd = sqrtf(var_);
       float a0 = fmaf(sd, e0, m0), a1 = fmaf(sd, e1, m1);       // dist.sample(), ppo.py:698-699
       a0 = fminf(fmaxf(a0, 0.f), 1.f);                          // ppo.py:701
       a1 = fminf(fmaxf(a1, -1.f), 1.f);                         // ppo.py:702
       reinterpret_cast<float2*>(a.act)[i] = make_float2(a0, a1);
-      a.logp[i] = gauss_logp(a0, a1, m0, m1, a.var);            // ppo.py:704 (at the clamped action)
+      a.logp[i] = gauss_logp(a0, a1, m0, m1, var_);             // ppo.py:704 (at the clamped action)
       if (a.mu) reinterpret_cast<float2*>(a.mu)[i] = make_float2(m0, m1);
     } else {
       const float2 av = reinterpret_cast<const float2*>(a.act_in)[i];
@@ -976,28 +981,39 @@ int navppo_adam(navppo_t* h, float* params, const float* grad, float* exp_avg, f
   return NAVSIM_OK;
 }
 
-int navppo_rollout(navppo_t* h, navsim_t* sim, const float* params, int32_t H, double var, uint64_t seed,
-                   int64_t agent_id_offset, uint32_t draw0, float* obs, float* next_obs, float* act, float* logp, float* rew,
-                   uint8_t* done, uint8_t* arrive, uint8_t* trunc, float* ep_return, float* ep_path, void* stream) {
+int navppo_rollout_ex(navppo_t* h, navsim_t* sim, const float* params, int32_t H, double var, uint64_t seed,
+                      int64_t agent_id_offset, uint32_t draw0, float* obs, float* next_obs, float* act, float* logp, float* rew,
+                      uint8_t* done, uint8_t* arrive, uint8_t* trunc, float* ep_return, float* ep_path, int32_t* ep_len,
+                      const uint32_t* dyn_dev, void* stream) {
   if (int rc = check_handle(h)) return rc;
   if (!sim || !params || !obs || !next_obs || !act || !logp || !rew || !done || !arrive || !trunc)
     return nav_fail(NAVSIM_EINVAL, "null buffer");
   if (H < 1) return nav_fail(NAVSIM_EINVAL, "H must be positive");
+  if (!(var > 0.0)) return nav_fail(NAVSIM_EINVAL, "var must be positive");
   const size_t N = (size_t)navsim_num_agents(sim);
   for (int t = 0; t < H; ++t) {
     float* o_t = obs + (size_t)t * N * OBS;
     float* o_next = (t + 1 < H) ? obs + (size_t)(t + 1) * N * OBS : next_obs;
-    if (int rc = navppo_act(h, params, o_t, (int32_t)N, var, seed, agent_id_offset, draw0 + (uint32_t)t, nullptr,
-                            act + (size_t)t * N * 2, logp + (size_t)t * N, nullptr, stream))
-      return rc;
+    InferArgs a{};
+    a.params = params; a.obs = o_t; a.T = (int)N; a.var = (float)var; a.seed = seed; a.agent_off = agent_id_offset;
+    a.draw = draw0 + (uint32_t)t; a.act = act + (size_t)t * N * 2; a.logp = logp + (size_t)t * N; a.dyn = dyn_dev;
+    if (int rc = launch_infer<INFER_ACT>(h, a, false, (cudaStream_t)stream)) return rc;
     navsim_step_out out;
     out.obs = o_next; out.rew = rew + (size_t)t * N; out.done = done + (size_t)t * N; out.arrive = arrive + (size_t)t * N;
     out.trunc = trunc + (size_t)t * N;
     out.ep_return = ep_return ? ep_return + (size_t)t * N : nullptr;
     out.ep_path = ep_path ? ep_path + (size_t)t * N : nullptr;
+    out.ep_len = ep_len ? ep_len + (size_t)t * N : nullptr;
     if (int rc = navsim_step_ex(sim, act + (size_t)t * N * 2, &out, stream)) return rc;
   }
   return NAVSIM_OK;
+}
+
+int navppo_rollout(navppo_t* h, navsim_t* sim, const float* params, int32_t H, double var, uint64_t seed,
+                   int64_t agent_id_offset, uint32_t draw0, float* obs, float* next_obs, float* act, float* logp, float* rew,
+                   uint8_t* done, uint8_t* arrive, uint8_t* trunc, float* ep_return, float* ep_path, void* stream) {
+  return navppo_rollout_ex(h, sim, params, H, var, seed, agent_id_offset, draw0, obs, next_obs, act, logp, rew, done, arrive,
+                           trunc, ep_return, ep_path, nullptr, nullptr, stream);
 }
 
 int navppo_update(navppo_t* h, float* params, float* exp_avg, float* exp_avg_sq, int32_t step0, const float* obs,

@@ -94,6 +94,7 @@ struct StepIO {
   float* rew;         // [N]
   uint8_t *done, *arrive, *trunc;  // [N] each, trunc may be null
   float *ep_ret, *ep_path;         // [N] each or null: return / path length of an episode, written at its last step
+  int32_t* ep_len;                 // [N] or null: its length in steps (ppo.py:583), written at its last step
   const float* past_act;           // [N,2] or null: the caller's previous action replaces the simulator's copy
   double* pose_out;                // [N,6] or null: x, y, theta, goal x, goal y, past_distance after the step
   long long obs_stride, vec_stride;
@@ -550,6 +551,7 @@ __global__ void __launch_bounds__(kBlock, KB != NAVSIM_LIDAR_FEATS ? 1 : (G == 1
             io.ep_ret[vo] = a.ep_ret;
             io.ep_path[vo] = a.ep_path;
           }
+          if (io.ep_len) io.ep_len[(long long)t * io.vec_stride + i] = a.steps;
           atomicAdd(&stats->episodes, 1ull);
           if (arrive) atomicAdd(&stats->successes, 1ull);            // ppo.py:558-560
           else if (done) atomicAdd(&stats->collisions, 1ull);
@@ -716,6 +718,7 @@ __global__ void __launch_bounds__(kBlock) navsim_step_anybeam_kernel(SimConst c,
             io.ep_ret[vo] = a.ep_ret;
             io.ep_path[vo] = a.ep_path;
           }
+          if (io.ep_len) io.ep_len[(long long)t * io.vec_stride + i] = a.steps;
           atomicAdd(&stats->episodes, 1ull);
           if (arrive) atomicAdd(&stats->successes, 1ull);
           else if (done) atomicAdd(&stats->collisions, 1ull);
@@ -952,7 +955,7 @@ StepIO make_io(const float* act, float* obs, float* rew, uint8_t* done, uint8_t*
                long long obs_stride, long long vec_stride) {
   StepIO io;
   io.act = act; io.obs = obs; io.rew = rew; io.done = done; io.arrive = arrive; io.trunc = trunc;
-  io.ep_ret = nullptr; io.ep_path = nullptr; io.past_act = nullptr; io.pose_out = nullptr;
+  io.ep_ret = nullptr; io.ep_path = nullptr; io.ep_len = nullptr; io.past_act = nullptr; io.pose_out = nullptr;
   io.obs_stride = obs_stride; io.vec_stride = vec_stride;
   return io;
 }
@@ -1219,6 +1222,7 @@ int navsim_step_ex(navsim_t* h, const float* act_dev, const navsim_step_out* out
   StepIO io = make_io(act_dev, out->obs, out->rew, out->done, out->arrive, out->trunc, 0, 0);
   io.ep_ret = out->ep_return;
   io.ep_path = out->ep_path;
+  io.ep_len = out->ep_len;
   return launch_step(h, io, (cudaStream_t)stream, false, 0, 1);
 }
 

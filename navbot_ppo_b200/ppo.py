@@ -74,6 +74,14 @@ class PPO:
         if self.use_vision:
             raise NotImplementedError("the camera path is outside the LiDAR hot path")
         self.vectorized = isinstance(env, VecEnv)
+        if self.vectorized and "max_timesteps_per_episode" in hyperparameters and \
+                int(self.max_timesteps_per_episode) != int(env.cfg.max_episode_steps):
+            # the episode cap lives in the simulator (ppo.py:552 is folded into the step kernel): a trainer that
+            # logs one cap while the environment applies another would silently change the episode protocol
+            raise ValueError(f"max_timesteps_per_episode={self.max_timesteps_per_episode} but the VecEnv was built with "
+                             f"max_episode_steps={int(env.cfg.max_episode_steps)}; pass the same value to both")
+        if self.vectorized:
+            self.max_timesteps_per_episode = int(env.cfg.max_episode_steps)
         dev = env.device if self.vectorized else getattr(getattr(env, "_vec", None), "device", None)
         self.device = dev if dev is not None else torch.device("cuda", torch.cuda.current_device())
 
@@ -151,9 +159,9 @@ class PPO:
         self.exp_id = "v02_simple_env_60_reward_proportion"
         self.method_name = "baseline"
         self.output_dir = None
-        # additions (not in the reference): GAE lambda (1.0 reproduces reward-to-go), GEMM arithmetic,
-        # quiet logging for benchmarks
-        self.gae_lambda = 1.0
+        # additions (not in the reference): GEMM arithmetic, quiet logging for benchmarks.  (The reference has no
+        # GAE: its advantage is reward-to-go minus V, ppo.py:277; navppo_rtg_scan's (gamma, lambda) form is reachable
+        # through the C-ABI only.)
         self.precision = _capi.PREC_FP32
         self.tensorboard = False
         self.verbose = True
@@ -161,6 +169,7 @@ class PPO:
         # bootstraps, :601): keep episodes running across rollouts / bootstrap the cut-off tail from the critic
         self.continue_episodes = False
         self.bootstrap_value = False
+        self.graph_rollout = True         # vectorised rollouts: replay the step loop as one CUDA graph
         self.log_episodes = True          # vectorised rollouts: one csv row per completed episode ...
         self.max_logged_episodes = 4096   # ... up to this many per iteration (None: all)
         for k, v in hyperparameters.items():
@@ -185,6 +194,10 @@ class PPO:
         self._b_rtg = torch.empty((H, N), dtype=torch.float32, device=d)
         self._b_epret = torch.zeros((H, N), dtype=torch.float32, device=d)    # return / path length of the episode
         self._b_eppath = torch.zeros((H, N), dtype=torch.float32, device=d)   # that ends at [t, n] (ppo.py:739-746)
+        self._b_eplen = torch.zeros((H, N), dtype=torch.int32, device=d)      # and its length in steps (ppo.py:583)
+        self._dyn = torch.zeros(2, dtype=torch.int32, device=d)               # {float bits of var, noise-counter increment}
+        self._dyn_host = torch.zeros(2, dtype=torch.int32).pin_memory()
+        self._rollout_graph = None
         self._next_obs = torch.empty((N, layout.OBS_DIM), dtype=torch.float32, device=d)
 
     def _handle_for(self, T: int):
@@ -328,12 +341,33 @@ class PPO:
             env.reset(out=self._b_obs[0])                                        # ppo.py:486
         self._rollouts_done = getattr(self, "_rollouts_done", 0) + 1
         seed = 0 if self.seed is None else int(self.seed)
-        # the step loop of ppo.py:505-549 is enqueued by the library: 2 H launches, no Python in between
-        _capi.check(L.navppo_rollout(self._h, env._h, self.flat.data_ptr(), H, self.var, seed, int(env.cfg.agent_id_offset),
-                                     self._draw, self._b_obs.data_ptr(), self._next_obs.data_ptr(), self._b_act.data_ptr(),
-                                     self._b_logp.data_ptr(), self._b_rew.data_ptr(), self._b_flags[0].data_ptr(),
-                                     self._b_flags[1].data_ptr(), self._b_flags[2].data_ptr(), self._b_epret.data_ptr(),
-                                     self._b_eppath.data_ptr(), sp))
+        # The step loop of ppo.py:505-549 is enqueued by the library (2 H launches, no Python in between) ONCE, into a
+        # CUDA graph; every rollout then replays it.  What changes between rollouts (the exploration variance and the
+        # Philox counter of the action noise) is read by the sampling epilogue from two device words.
+        self._dyn_host[0] = int(np.float32(self.var).view(np.int32))
+        self._dyn_host[1] = int(np.uint32(self._draw & 0xFFFFFFFF).view(np.int32))
+        self._dyn.copy_(self._dyn_host, non_blocking=True)
+
+        def enqueue(stream_ptr):
+            _capi.check(L.navppo_rollout_ex(self._h, env._h, self.flat.data_ptr(), H, 1.0, seed, int(env.cfg.agent_id_offset), 0,
+                                            self._b_obs.data_ptr(), self._next_obs.data_ptr(), self._b_act.data_ptr(),
+                                            self._b_logp.data_ptr(), self._b_rew.data_ptr(), self._b_flags[0].data_ptr(),
+                                            self._b_flags[1].data_ptr(), self._b_flags[2].data_ptr(), self._b_epret.data_ptr(),
+                                            self._b_eppath.data_ptr(), self._b_eplen.data_ptr(), self._dyn.data_ptr(), stream_ptr))
+
+        if not self.graph_rollout:
+            enqueue(sp)
+        else:
+            if self._rollout_graph is None:
+                g = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):
+                    with torch.cuda.graph(g, stream=side):
+                        enqueue(side.cuda_stream)
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                self._rollout_graph = g
+            self._rollout_graph.replay()
         self._draw += H
         torch.amax(self._b_flags, dim=0, out=self._b_term)                       # done | arrive | timeout, ppo.py:553
         last_v = None
@@ -347,18 +381,21 @@ class PPO:
         it = dict(successes=int(st.successes), collisions=int(st.collisions), timeouts=int(st.timeouts), ep_times=[],
                   ep_count=int(st.episodes), return_sum=float(st.return_sum), length_sum=float(st.length_sum),
                   path_sum=float(st.path_sum))
-        # completed-episode lengths (ppo.py:583); every agent starts a fresh episode at t = 0
-        term = self._b_term.cpu().numpy()
-        nn_, tt = np.nonzero(term.T)                       # sorted by agent, then time
-        if tt.size:
-            prev = np.where(np.r_[True, nn_[1:] != nn_[:-1]], -1, np.r_[0, tt[:-1]])
-            batch_lens = (tt - prev).astype(np.int64)
+        # completed-episode lengths (ppo.py:583): the simulator writes an episode's length at its last step, so the
+        # list is a device-side compaction of [H, N] at the episode-end flags; only the completed episodes' few
+        # integers cross to the host (agent-major order, like the one-robot loop playing the agents in turn)
+        term_t = self._b_term.t()
+        ends = term_t.nonzero(as_tuple=False)              # [E, 2] = (agent, step), sorted by agent then time
+        if ends.shape[0]:
+            nn_d, tt_d = ends[:, 0], ends[:, 1]
+            batch_lens = self._b_eplen[tt_d, nn_d].cpu().numpy().astype(np.int64)
         else:
+            nn_d = tt_d = None
             batch_lens = np.zeros(0, np.int64)
         self.logger["batch_lens"] = batch_lens
         self.logger["batch_rews"] = []
-        if self.log_episodes and tt.size and self.rank == 0:
-            self._log_vec_episodes(t_so_far, nn_, tt, batch_lens)
+        if self.log_episodes and batch_lens.size and self.rank == 0:
+            self._log_vec_episodes(t_so_far, nn_d, tt_d, batch_lens)
         T = H * N
         return (self._b_obs.view(T, -1), self._b_act.view(T, 2), self._b_logp.view(T), self._b_rtg.view(T), batch_lens,
                 it, None)
@@ -429,9 +466,13 @@ class PPO:
             obs, acts, logp, rtgs, lens, iter_metrics, _ = self.rollout(past_action=list(past_action), t_so_far=t_so_far)
             torch.cuda.synchronize(self.device)
             t1 = time.time()
-            steps = int(np.sum(lens))
-            if self.world > 1:
-                steps = int(navdist.all_reduce_sum_(torch.tensor([steps], dtype=torch.float64, device=self.device)).item())
+            if self.vectorized:
+                # every simulated step counts: H x N per rank.  (The reference adds up completed-episode lengths, :258,
+                # which equals the batch size on one robot because an episode is far shorter than a batch; with N
+                # robots x H steps most episodes straddle rollouts and would never be counted.)
+                steps = int(obs.shape[0]) * self.world
+            else:
+                steps = int(np.sum(lens))
             t_so_far += steps                                                    # :258
             i_so_far += 1
             self.logger.update(t_so_far=t_so_far, i_so_far=i_so_far, iter_metrics=iter_metrics)
@@ -477,15 +518,16 @@ class PPO:
         """One csv row per episode completed in this rollout, the reference's columns (ppo.py:739-746).
         Episodes are listed agent by agent; `timestep` counts completed steps the way the one-robot
         loop would if it played the agents one after another; `time` is simulated time (0.2 s per
-        step, gazebo.xacro:107) because N robots share the wall clock."""
-        flags = self._b_flags.cpu().numpy()
-        arrive = flags[1][steps, agents].astype(bool)
-        done = flags[0][steps, agents].astype(bool)
-        ret = self._b_epret.cpu().numpy()[steps, agents]
-        path = self._b_eppath.cpu().numpy()[steps, agents]
+        step, gazebo.xacro:107) because N robots share the wall clock.  `agents` / `steps` are device
+        index tensors: only the logged episodes' values are gathered and copied."""
         n = len(lengths)
         if self.max_logged_episodes is not None and n > self.max_logged_episodes:
             n = int(self.max_logged_episodes)
+        a_, s_ = agents[:n], steps[:n]
+        arrive = self._b_flags[1][s_, a_].cpu().numpy().astype(bool)
+        done = self._b_flags[0][s_, a_].cpu().numpy().astype(bool)
+        ret = self._b_epret[s_, a_].cpu().numpy()
+        path = self._b_eppath[s_, a_].cpu().numpy()
         ts = t_so_far + np.cumsum(lengths)
         with open(self.episode_csv_path, "a", newline="") as f:
             w = csv.writer(f)

@@ -37,6 +37,49 @@ class _Map(ctypes.Structure):
                 ("bc", ctypes.c_void_p), ("bs", ctypes.c_void_p)]
 
 
+class OracleCfg(ctypes.Structure):
+    """include/navsim.h `navsim_cfg`, restated so that the CPU arm of bench.py never imports the product
+    package (tests/test_oracle_env.py checks the two definitions field by field)."""
+    _fields_ = [
+        ("num_agents", ctypes.c_int32), ("num_beams", ctypes.c_int32), ("max_episode_steps", ctypes.c_int32),
+        ("auto_reset", ctypes.c_int32), ("device", ctypes.c_int32), ("n_reset_rects", ctypes.c_int32),
+        ("n_respawn_rects", ctypes.c_int32), ("lanes_per_agent", ctypes.c_int32),
+        ("seed", ctypes.c_uint64), ("agent_id_offset", ctypes.c_int64),
+        ("dt", ctypes.c_double), ("lidar_offset_x", ctypes.c_double),
+        ("lidar_min", ctypes.c_double), ("lidar_max", ctypes.c_double),
+        ("fov_min", ctypes.c_double), ("fov_max", ctypes.c_double),
+        ("collision_range", ctypes.c_double), ("arrive_threshold", ctypes.c_double),
+        ("reward_scale", ctypes.c_double), ("reward_collide", ctypes.c_double), ("reward_arrive", ctypes.c_double),
+        ("diag_norm", ctypes.c_double), ("goal_lo", ctypes.c_double), ("goal_hi", ctypes.c_double),
+        ("start_x", ctypes.c_double), ("start_y", ctypes.c_double), ("start_theta", ctypes.c_double),
+        ("reset_rects", ctypes.c_double * 32), ("respawn_rects", ctypes.c_double * 32),
+    ]
+
+
+# stage_1 = worlds/train_world1.world:85-252 (turtlebot3_stage_1.launch:8): four walls as
+# (centre x, centre y, size x, size y, yaw), yaw as printed in the world file
+STAGE_1_BOXES = [(4.0, 0.0, 8.1, 0.1, -1.5708), (0.0, -4.0, 8.10002, 0.1, 3.14159), (-4.0, 0.0, 8.1, 0.1, 1.5708),
+                 (0.0, 4.0, 8.1, 0.1, 0.0)]
+
+
+def stage_1_segments() -> np.ndarray:
+    """The four counter-clockwise edges of each stage_1 wall, float64 [16, 4]."""
+    import math
+    segs = []
+    for cx, cy, sx, sy, yaw in STAGE_1_BOXES:
+        c, s = math.cos(yaw), math.sin(yaw)
+        hx, hy = sx / 2.0, sy / 2.0
+        pts = [(cx + c * px - s * py, cy + s * px + c * py) for px, py in ((-hx, -hy), (hx, -hy), (hx, hy), (-hx, hy))]
+        segs += [(*pts[k], *pts[(k + 1) % 4]) for k in range(4)]
+    return np.asarray(segs, dtype=np.float64).reshape(-1, 4)
+
+
+def default_cfg(num_agents: int) -> OracleCfg:
+    cfg = OracleCfg()
+    lib().oracle_default_cfg(ctypes.byref(cfg), int(num_agents))
+    return cfg
+
+
 _lib = None
 
 
@@ -51,6 +94,10 @@ def lib():
         L.oracle_reset.restype = None
         L.oracle_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int]
         L.oracle_step.restype = ctypes.c_int
+        L.oracle_run_scripted.argtypes = [vp, vp, vp, u64, i32, i32, vp, vp, vp, vp, vp, vp, ctypes.c_int]
+        L.oracle_run_scripted.restype = ctypes.c_int
+        L.oracle_default_cfg.argtypes = [vp, i32]
+        L.oracle_default_cfg.restype = ctypes.c_int
         L.oracle_scripted_actions.argtypes = [u64, ctypes.c_int64, i32, i32, vp]
         L.oracle_scripted_actions.restype = None
         L.shim_beam_table.argtypes = [i32, d, d, vp, vp]
@@ -117,6 +164,18 @@ class OracleSim:
                           obs.ctypes.data, rew.ctypes.data, done.ctypes.data, arrive.ctypes.data, trunc.ctypes.data,
                           None if stats is None else ctypes.byref(stats), self.nthreads)
         return obs, rew, done, arrive, trunc
+
+    def run_scripted(self, nsteps: int, action_seed: int = 0, step0: int = 0):
+        """`nsteps` Env.step calls per agent with the benchmark's scripted actions, entirely in C
+        (liboracle.so: oracle_run_scripted); returns the last step's (obs, rew, done, arrive)."""
+        if not hasattr(self, "_run_bufs"):
+            self._run_bufs = (np.zeros((self.n, 2), np.float32), np.zeros((self.n, 16)), np.zeros(self.n),
+                              np.zeros(self.n, np.uint8), np.zeros(self.n, np.uint8))
+        act, obs, rew, done, arrive = self._run_bufs
+        lib().oracle_run_scripted(ctypes.byref(self.cfg), ctypes.byref(self.map), ctypes.byref(self.state), action_seed,
+                                  step0, nsteps, act.ctypes.data, obs.ctypes.data, rew.ctypes.data, done.ctypes.data,
+                                  arrive.ctypes.data, None, self.nthreads)
+        return obs, rew, done, arrive
 
     def scan(self):
         nb = int(self.cfg.num_beams)

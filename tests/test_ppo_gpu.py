@@ -366,3 +366,47 @@ def test_ppo_error_paths():
     assert L.navppo_grad(hh, x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), 2048, 2048,
                          0.8, x.data_ptr(), x.data_ptr(), None) == -22 and b"max_samples" in L.nav_last_error()
     assert L.navppo_act(hh, x.data_ptr(), x.data_ptr(), 4, 0.0, 0, 0, 0, None, x.data_ptr(), x.data_ptr(), None, None) == -22
+
+
+def test_graph_replayed_rollout_equals_the_launch_by_launch_rollout(tmp_path):
+    """PPO.rollout replays the 2 H launches of ppo.py:505-549 as ONE captured CUDA graph whose sampling
+    epilogue reads the variance and the noise counter from device words: every rollout buffer is
+    bit-identical to navppo_rollout enqueued launch by launch, rollout after rollout (the counter and the
+    decayed variance move), and the episode lengths the simulator writes at episode ends equal the ones
+    reconstructed from the flags."""
+    def make(graph):
+        env = VecEnv(384, map="stage_2", seed=3, max_episode_steps=25)
+        return PPO(NetActor, NetCritic, env, 16, 2, timesteps_per_batch=384 * 40, max_timesteps_per_episode=25,
+                   n_updates_per_iteration=1, output_dir=str(tmp_path / ("g" if graph else "l")), method_name="r", seed=5,
+                   verbose=False, graph_rollout=graph)
+    a, b = make(True), make(False)
+    b.flat.copy_(a.flat)
+    for it in range(3):
+        if it == 2:                      # a decayed exploration variance must reach the replayed graph
+            a._decay_cov(); b._decay_cov()
+        ra, rb = a.rollout([0, 0], 0), b.rollout([0, 0], 0)
+        torch.cuda.synchronize()
+        for x, y in zip(ra[:4], rb[:4]):
+            assert torch.equal(x, y)
+        for name in ("_b_rew", "_b_flags", "_b_epret", "_b_eppath", "_b_eplen", "_b_term", "_next_obs"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), name
+        assert np.array_equal(ra[4], rb[4]) and ra[5] == rb[5]
+        # lengths from the flags: every agent starts a fresh episode at t = 0 (ppo.py:486)
+        term = a._b_term.cpu().numpy()
+        nn_, tt = np.nonzero(term.T)
+        prev = np.where(np.r_[True, nn_[1:] != nn_[:-1]], -1, np.r_[0, tt[:-1]])
+        assert np.array_equal(ra[4], tt - prev) and len(ra[4]) == ra[5]["ep_count"] > 0
+    assert a._rollout_graph is not None and b._rollout_graph is None
+
+
+def test_vectorised_learn_counts_every_simulated_step_and_checks_the_episode_cap(tmp_path):
+    """learn() on a VecEnv advances t_so_far by H x N per iteration (episodes longer than the horizon would
+    otherwise never be counted and the loop would not terminate), and a trainer whose
+    max_timesteps_per_episode disagrees with the simulator's cap is refused."""
+    env = VecEnv(256, map="stage_1", seed=1, max_episode_steps=500)
+    agent = PPO(NetActor, NetCritic, env, 16, 2, timesteps_per_batch=256 * 8, max_timesteps_per_episode=500,
+                n_updates_per_iteration=1, output_dir=str(tmp_path), method_name="c", seed=0, verbose=False)
+    assert agent.learn(total_timesteps=256 * 8 * 2) == 256 * 8 * 2      # two iterations, no episode needs to end
+    with pytest.raises(ValueError):
+        PPO(NetActor, NetCritic, env, 16, 2, timesteps_per_batch=256 * 8, max_timesteps_per_episode=800,
+            output_dir=str(tmp_path), method_name="d", verbose=False)
