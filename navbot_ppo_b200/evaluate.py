@@ -6,8 +6,10 @@
       `<method>_eval_episodes.csv` with the reference's columns, summary on stdout.
   evaluate_vec(actor, num_episodes, ...)
       the same protocol for `num_episodes` robots at once on the GPU: episode e is robot e of a
-      VecEnv (threshold_arrive 0.4 as in environment_new.py:46-47 when is_training=False); every
-      step is one policy forward + one simulator launch for all robots still running.
+      VecEnv; every step is one policy forward + one simulator launch for all robots still running.
+      `is_training` picks the arrival threshold like environment_new.py:44-47 (0.2 / 0.4); the default is
+      True because main.py builds its Env with the module constant is_training = True (main.py:22,442) for
+      `--eval` runs too.
 
 Both return the metrics dict the reference accumulates (success / collision / timeout counts and the
 per-episode lists).
@@ -112,7 +114,7 @@ def evaluate(env, hyperparameters, actor_model, critic_model, num_episodes, verb
 
 
 def evaluate_vec(actor: NetActor, num_episodes: int, map="stage_1", device=0, seed=0, max_timesteps_per_episode=500,
-                 output_dir=None, method_name="baseline", is_training=False, agent_id_offset=0, verbose=False):
+                 output_dir=None, method_name="baseline", is_training=True, agent_id_offset=0, verbose=False):
     """`num_episodes` evaluation episodes at once: robot e of a VecEnv plays episode e with the
     deterministic policy until done | arrive | timeout (main.py:195-213)."""
     n = int(num_episodes)
