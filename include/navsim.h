@@ -68,6 +68,18 @@ typedef struct navsim_cfg {
   double start_x, start_y, start_theta; /* turtlebot3_stage_1.launch:3-5 */
   double reset_rects[NAVSIM_MAX_RECTS * 4];   /* {xlo, xhi, ylo, yhi} each */
   double respawn_rects[NAVSIM_MAX_RECTS * 4];
+  /* ---- options of the un-vendored Gazebo plugins, OFF (0) by default and outside the parity contract
+   * (SURVEY.md 8 f-4).  Either one routes Env.step through the generic warp-per-agent kernel. */
+  double lidar_noise_sigma;  /* gazebo.xacro:122-126 Gaussian range noise; the plugin's value is 0.01 */
+  double wheel_accel;        /* gazebo.xacro:67 <wheelAcceleration> applied to the wheels' rim speeds [m/s^2]
+                              * at the plugin's 30 Hz update rate (:71); 0 = cmd_vel is reached at once */
+  double wheel_separation;   /* gazebo.xacro:65 / turtlebot3_fake.cpp:44: 0.160 m (used by the ramp only) */
+  /* ---- start / goal tables of spawn_goal_sampler.py:37-72 (`--use_external_sampler`, arguments.py:41):
+   * with sampler_mode = 1 and tables given through navsim_set_sampler, Env.reset places the robot at a
+   * table start pose and the goal at a table point whose distance lies in [min, max] */
+  double sampler_min_dist, sampler_max_dist;   /* GoalSpawnSampler defaults 1.5, 6.0 */
+  int32_t sampler_mode;      /* 0 = Env.reset of environment_new.py (fixed spawn, uniform goal), 1 = tables */
+  int32_t reserved0;
 } navsim_cfg;
 
 /* Per-agent state fields for navsim_get_state / navsim_set_state (host arrays of N). */
@@ -84,7 +96,9 @@ enum navsim_field {
   NAVSIM_F_DRAWS = 9,     /* uint32, goal-sampler draws consumed */
   NAVSIM_F_EP_RETURN = 10,/* float, running episode return (ppo.py:544) */
   NAVSIM_F_EP_PATH = 11,  /* float, running path length (ppo.py:535-538) */
-  NAVSIM_F_LAST_MOVE = 12 /* float, displacement of the latest step (not yet in EP_PATH) */
+  NAVSIM_F_LAST_MOVE = 12,/* float, displacement of the latest step (not yet in EP_PATH) */
+  NAVSIM_F_WHEEL_L = 13,  /* double, left / right rim speed [m/s] (wheel_accel > 0 only; zero after a reset) */
+  NAVSIM_F_WHEEL_R = 14
 };
 
 /* Episode statistics accumulated on device (ppo.py:558-580 iteration metrics). */
@@ -110,6 +124,14 @@ int navsim_destroy(navsim_t* h);
  * for free-standing two-sided walls. */
 #define NAVSIM_MAP_CLOSED_BOXES 1
 int navsim_set_map(navsim_t* h, const double* seg_host, int32_t num_segments, int32_t flags);
+
+/* GoalSpawnSampler tables (spawn_goal_sampler.py:5-35): starts_host[n_starts, 3] = (x, y, yaw),
+ * goals_host[n_goals, 2] = (x, y), host doubles, at most NAVSIM_MAX_TABLE rows each.  Call after
+ * navsim_set_map (the LaserScan seen from every start pose is cast here, once) on a handle created with
+ * cfg.sampler_mode = 1; such a handle refuses reset / step until its tables are set. */
+#define NAVSIM_MAX_TABLE 64
+int navsim_set_sampler(navsim_t* h, const double* starts_host, int32_t n_starts, const double* goals_host,
+                       int32_t n_goals);
 
 /* Env.reset (environment_new.py:312-382) for every agent whose mask byte is non-zero
  * (mask_dev == NULL: all agents).  Writes obs[N,16] rows of the agents that were reset. */

@@ -18,12 +18,12 @@ ACT_DIM = 2
 
 # enum navsim_field
 F_X, F_Y, F_THETA, F_GOAL_X, F_GOAL_Y, F_PAST_DIST, F_PREV_A0, F_PREV_A1, F_STEPS, F_DRAWS, F_EP_RETURN, \
-    F_EP_PATH, F_LAST_MOVE = range(13)
+    F_EP_PATH, F_LAST_MOVE, F_WHEEL_L, F_WHEEL_R = range(15)
 
 FIELD_DTYPES = {
     F_X: "float64", F_Y: "float64", F_THETA: "float64", F_GOAL_X: "float64", F_GOAL_Y: "float64",
     F_PAST_DIST: "float64", F_PREV_A0: "float32", F_PREV_A1: "float32", F_STEPS: "int32", F_DRAWS: "uint32",
-    F_EP_RETURN: "float32", F_EP_PATH: "float32", F_LAST_MOVE: "float32",
+    F_EP_RETURN: "float32", F_EP_PATH: "float32", F_LAST_MOVE: "float32", F_WHEEL_L: "float64", F_WHEEL_R: "float64",
 }
 
 
@@ -41,6 +41,9 @@ class NavsimCfg(ctypes.Structure):
         ("diag_norm", ctypes.c_double), ("goal_lo", ctypes.c_double), ("goal_hi", ctypes.c_double),
         ("start_x", ctypes.c_double), ("start_y", ctypes.c_double), ("start_theta", ctypes.c_double),
         ("reset_rects", ctypes.c_double * (MAX_RECTS * 4)), ("respawn_rects", ctypes.c_double * (MAX_RECTS * 4)),
+        ("lidar_noise_sigma", ctypes.c_double), ("wheel_accel", ctypes.c_double), ("wheel_separation", ctypes.c_double),
+        ("sampler_min_dist", ctypes.c_double), ("sampler_max_dist", ctypes.c_double),
+        ("sampler_mode", ctypes.c_int32), ("reserved0", ctypes.c_int32),
     ]
 
 
@@ -73,6 +76,7 @@ NAVSIM_SYMBOLS = {
     "navsim_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.POINTER(NavsimCfg)]),
     "navsim_destroy": (ctypes.c_int, [_vp]),
     "navsim_set_map": (ctypes.c_int, [_vp, _vp, _i32, _i32]),
+    "navsim_set_sampler": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i32]),
     "navsim_reset": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "navsim_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "navsim_step_ex": (ctypes.c_int, [_vp, _vp, _vp, _vp]),

@@ -35,7 +35,9 @@
 #include <string.h>
 
 #include <new>
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/navsim.h"
 #include "nav_common.h"
@@ -76,10 +78,20 @@ struct SimConst {
   float inv_diag;
   double reset_rects[NAVSIM_MAX_RECTS * 4];
   double respawn_rects[NAVSIM_MAX_RECTS * 4];
+  // GoalSpawnSampler tables (device memory; n_starts == 0: the reference Env.reset)
+  int32_t n_starts, n_goals;
+  const double* starts;        // [n_starts, 3]
+  const double* goals;         // [n_goals, 2]
+  const float* start_scans;    // [n_starts, B] sanitised ranges seen from every start pose
+  double smin, smax;
+  // fidelity options (generic kernel only)
+  float noise_sigma;
+  double wheel_accel, wheel_sep;
 };
 
 struct SimState {
   double *x, *y, *th, *gx, *gy, *past;
+  double *vl, *vr;             // wheel rim speeds (wheel_accel > 0 only)
   float *pa0, *pa1, *ep_ret, *ep_path, *last_move;
   int32_t* steps;
   uint32_t* draws;
@@ -108,6 +120,7 @@ struct DevStats {
 
 struct Agent {
   double x, y, th, gx, gy, past;
+  int32_t start_idx;           // table row of the current start pose (table sampler), else -1
   float pa0, pa1, ep_ret, ep_path, last_move;
   int32_t steps;
   uint32_t draws;
@@ -252,8 +265,20 @@ __device__ __forceinline__ void sample_goal(const SimConst& c, const double* rec
 __device__ __forceinline__ void reset_agent(const SimConst& c, const MapView& mv, const uint16_t* __restrict__ rt_tab,
                                             uint64_t agent, Agent* a, float* obs, bool feats, int lidar_mod,
                                             int lidar_lane) {
-  a->x = c.sx; a->y = c.sy; a->th = c.sth;                       // reset_world, :325
-  sample_goal(c, c.reset_rects, c.n_reset_rects, agent, a);
+  const float* start_r = mv.start_r;
+  if (c.n_starts > 0) {
+    // spawn_goal_sampler.py:52-63: start pose and goal point from the tables, distance-filtered; the scan of
+    // every start pose was cast by navsim_set_sampler
+    int is, ig;
+    nv_sample_tables(c.seed, agent, &a->draws, c.starts, c.n_starts, c.goals, c.n_goals, c.smin, c.smax, &is, &ig);
+    a->x = c.starts[3 * is]; a->y = c.starts[3 * is + 1]; a->th = c.starts[3 * is + 2];
+    a->gx = c.goals[2 * ig]; a->gy = c.goals[2 * ig + 1];
+    a->start_idx = is;
+    start_r = c.start_scans + (size_t)is * c.B;
+  } else {
+    a->x = c.sx; a->y = c.sy; a->th = c.sth;                     // reset_world, :325
+    sample_goal(c, c.reset_rects, c.n_reset_rects, agent, a);
+  }
   const double dx = a->gx - a->x, dy = a->gy - a->y;
   a->past = sqrt(dx * dx + dy * dy);                             // :359 via :116-120
   a->pa0 = 0.f; a->pa1 = 0.f; a->steps = 0;
@@ -262,8 +287,27 @@ __device__ __forceinline__ void reset_agent(const SimConst& c, const MapView& mv
   odom_features(c, rt_tab, a->x, a->y, a->th, a->gx, a->gy, &yaw, &rel, &diff);
 #pragma unroll
   for (int i = 0; i < NAVSIM_LIDAR_FEATS; ++i)
-    if ((c.pick[i] & (lidar_mod - 1)) == lidar_lane) obs[i] = mv.start_r[c.pick[i]] * kInvRmax;   // :361-369
+    if ((c.pick[i] & (lidar_mod - 1)) == lidar_lane) obs[i] = start_r[c.pick[i]] * kInvRmax;   // :361-369
   if (feats) write_goal_feats(c, obs, 0.f, 0.f, a->past, yaw, rel, diff);                    // :372-376
+}
+
+// Goal respawn on arrival when the caller does not reset (environment_new.py:245-267): from the uniform square with
+// the wider rejection margins, or - table sampler - a table point at an admissible distance from where the robot stands
+__device__ __forceinline__ void respawn_goal(const SimConst& c, uint64_t agent, Agent* a) {
+  if (c.n_starts > 0) {
+    int ig = 0;
+    for (int attempt = 0; attempt < 101; ++attempt) {
+      int is;
+      nv_table_indices(c.seed, agent, a->draws, c.n_starts, c.n_goals, &is, &ig);
+      a->draws += 1u;
+      const double dx = a->x - c.goals[2 * ig], dy = a->y - c.goals[2 * ig + 1];
+      const double dist = sqrt(dx * dx + dy * dy);
+      if (c.smin <= dist && dist <= c.smax) break;
+    }
+    a->gx = c.goals[2 * ig]; a->gy = c.goals[2 * ig + 1];
+  } else {
+    sample_goal(c, c.respawn_rects, c.n_respawn_rects, agent, a);
+  }
 }
 
 __device__ __forceinline__ void load_agent(const SimState& st, int i, Agent* a) {
@@ -272,6 +316,7 @@ __device__ __forceinline__ void load_agent(const SimState& st, int i, Agent* a) 
   a->pa0 = st.pa0[i]; a->pa1 = st.pa1[i];
   a->ep_ret = st.ep_ret[i]; a->ep_path = st.ep_path[i]; a->last_move = st.last_move[i];
   a->steps = st.steps[i]; a->draws = st.draws[i];
+  a->start_idx = -1;
 }
 
 __device__ __forceinline__ void store_agent(const SimState& st, int i, const Agent& a, bool goal_changed) {
@@ -544,7 +589,7 @@ __global__ void __launch_bounds__(kBlock, KB != NAVSIM_LIDAR_FEATS ? 1 : (G == 1
       if (done || arrive || timeout) {                               // ppo.py:553-593
         // setReward has already respawned a goal on arrival (:245-253); rollout throws it
         // away by resetting, but the draws it consumed stay consumed
-        if (arrive) sample_goal(c, c.respawn_rects, c.n_respawn_rects, agent, &a);
+        if (arrive && c.n_starts == 0) sample_goal(c, c.respawn_rects, c.n_respawn_rects, agent, &a);
         if (writer) {
           if (io.ep_ret) {                                           // ppo.py:739-746: the episode's csv row
             const long long vo = (long long)t * io.vec_stride + i;
@@ -565,7 +610,7 @@ __global__ void __launch_bounds__(kBlock, KB != NAVSIM_LIDAR_FEATS ? 1 : (G == 1
         goal_dirty = true;
       }
     } else if (arrive) {                                             // :245-267
-      sample_goal(c, c.respawn_rects, c.n_respawn_rects, agent, &a);
+      respawn_goal(c, agent, &a);
       const double gx = a.gx - a.x, gy = a.gy - a.y;
       a.past = sqrt(gx * gx + gy * gy);
       goal_dirty = true;
@@ -630,6 +675,8 @@ __global__ void __launch_bounds__(kBlock) navsim_step_anybeam_kernel(SimConst c,
   }
   wait_map(bar);
   bool goal_dirty = false;
+  double vl = 0.0, vr = 0.0;             // wheel rim speeds (fidelity option wheel_accel)
+  if (c.wheel_accel > 0.0) { vl = st.vl[i]; vr = st.vr[i]; }
   for (int t = 0; t < nsteps; ++t) {
     __syncwarp();
     float a0, a1;
@@ -644,7 +691,10 @@ __global__ void __launch_bounds__(kBlock) navsim_step_anybeam_kernel(SimConst c,
     }
     if (a.steps > 0) a.ep_path += a.last_move;
     const double px = a.x, py = a.y;
-    nv_drive(&a.x, &a.y, &a.th, (double)a0 / 4.0, (double)a1, c.dt);
+    if (c.wheel_accel > 0.0)   // fidelity option: the plugin's 30 Hz updates = 6 sub-steps of the 5 Hz LiDAR period
+      nv_drive_ramped(&a.x, &a.y, &a.th, &vl, &vr, (double)a0 / 4.0, (double)a1, c.dt, c.wheel_accel, c.wheel_sep, 6);
+    else
+      nv_drive(&a.x, &a.y, &a.th, (double)a0 / 4.0, (double)a1, c.dt);
     {
       const double mx = a.x - px, my = a.y - py;
       a.last_move = sqrtf((float)(mx * mx + my * my));
@@ -654,6 +704,7 @@ __global__ void __launch_bounds__(kBlock) navsim_step_anybeam_kernel(SimConst c,
     const float ox = (float)(a.x + c.off_x * c_new), oy = (float)(a.y + c.off_x * s_new);
     const float ch = (float)c_new, sh = (float)s_new, rmin = (float)c.rmin, rmax = (float)c.rmax;
     float mn = NV_INF_F;
+    float nz[4] = {0.f, 0.f, 0.f, 0.f};
     int pickn = 0;
     // walls this agent can see at all (same two-phase sweep as group_sweep)
     int nvis = c.S;
@@ -680,6 +731,10 @@ __global__ void __launch_bounds__(kBlock) navsim_step_anybeam_kernel(SimConst c,
       __syncwarp();
       q = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(q)));
       float rb = nv_range_from_q(q, rmin, rmax);
+      if (c.noise_sigma > 0.f) {           // fidelity option: Gaussian range noise, then the sensor's gates again
+        if ((b & 3) == 0) nv_scan_noise4(c.seed ^ 0x6e6f697365ull, agent, a.draws, (uint32_t)a.steps, (uint32_t)(b >> 2), nz);
+        rb = nv_noisy_range(rb, nz[b & 3], c.noise_sigma, rmin, rmax);
+      }
       if (rb == NV_INF_F) rb = 3.5f;
       mn = (rb < mn) ? rb : mn;
       while (pickn < NAVSIM_LIDAR_FEATS && c.pick[pickn] == b) {
@@ -711,7 +766,7 @@ __global__ void __launch_bounds__(kBlock) navsim_step_anybeam_kernel(SimConst c,
     }
     if (c.auto_reset) {
       if (done || arrive || timeout) {
-        if (arrive) sample_goal(c, c.respawn_rects, c.n_respawn_rects, agent, &a);
+        if (arrive && c.n_starts == 0) sample_goal(c, c.respawn_rects, c.n_respawn_rects, agent, &a);
         if (writer) {
           if (io.ep_ret) {
             const long long vo = (long long)t * io.vec_stride + i;
@@ -728,10 +783,11 @@ __global__ void __launch_bounds__(kBlock) navsim_step_anybeam_kernel(SimConst c,
           atomicAdd(&stats->path_sum, (double)a.ep_path);
         }
         reset_agent(c, mv, rt_tab, agent, &a, my_obs, writer, 1, writer ? 0 : -1);
+        vl = 0.0; vr = 0.0;                                          // the plugin's Reset() zeroes the wheels
         goal_dirty = true;
       }
     } else if (arrive) {
-      sample_goal(c, c.respawn_rects, c.n_respawn_rects, agent, &a);
+      respawn_goal(c, agent, &a);
       const double gx = a.gx - a.x, gy = a.gy - a.y;
       a.past = sqrt(gx * gx + gy * gy);
       goal_dirty = true;
@@ -744,6 +800,7 @@ __global__ void __launch_bounds__(kBlock) navsim_step_anybeam_kernel(SimConst c,
   }
   if (writer) {
     store_agent(st, i, a, goal_dirty);
+    if (c.wheel_accel > 0.0) { st.vl[i] = vl; st.vr[i] = vr; }
     if (io.pose_out) {
       double* po = io.pose_out + (size_t)i * 6;
       po[0] = a.x; po[1] = a.y; po[2] = a.th; po[3] = a.gx; po[4] = a.gy; po[5] = a.past;
@@ -771,6 +828,7 @@ __global__ void __launch_bounds__(kBlock) navsim_reset_kernel(SimConst c, SimSta
   load_agent(st, i, &a);
   reset_agent(c, map_view(s_map, c.B, c.S), rt_tab, (uint64_t)(c.agent_off + i), &a, my_obs, true, 1, 0);
   store_agent(st, i, a, true);
+  if (c.wheel_accel > 0.0) { st.vl[i] = 0.0; st.vr[i] = 0.0; }   // the diff-drive plugin's Reset() zeroes the wheels
   if (pose_out) {
     double* po = pose_out + (size_t)i * 6;
     po[0] = a.x; po[1] = a.y; po[2] = a.th; po[3] = a.gx; po[4] = a.gy; po[5] = a.past;
@@ -832,12 +890,21 @@ struct navsim {
   float *h_past = nullptr, *h_past_dev = nullptr;        // [N,2]
   double *h_pose = nullptr, *h_pose_dev = nullptr;       // [N,6]
   double* reset_pose_out = nullptr;                      // set around a navsim_reset_host_ex launch
+  // GoalSpawnSampler tables (navsim_set_sampler) and the host copy of the packed map they are cast against
+  double *d_starts = nullptr, *d_goals = nullptr;
+  float* d_start_scans = nullptr;
+  std::vector<float> h_map;      // [8S + 3B] as uploaded
+  int closed = 0;
 };
 
 namespace {
 
 // variant: 0 = 10-beam register path, 1 = padded (B <= kPadBeams), 2 = any beam count (warp per agent)
-int variant_of(const navsim* h) { return h->c.B == NAVSIM_LIDAR_FEATS ? 0 : (h->c.B <= kPadBeams ? 1 : 2); }
+// (also the only kernel that implements the fidelity options: range noise, wheel-acceleration ramp)
+int variant_of(const navsim* h) {
+  if (h->c.noise_sigma > 0.f || h->c.wheel_accel > 0.0) return 2;
+  return h->c.B == NAVSIM_LIDAR_FEATS ? 0 : (h->c.B <= kPadBeams ? 1 : 2);
+}
 
 // Lanes per agent in force: the request / heuristic, raised for big maps so that the per-agent
 // visible-wall lists of a CTA (agents x S x 2 bytes) stay within ~64 KB of shared memory.
@@ -900,6 +967,26 @@ const float* host_device_alias(navsim* h, int slot, const void* p) {
 int check_ready(const navsim* h) {
   if (!h) return fail(NAVSIM_EINVAL, "null handle");
   if (!h->d_map) return fail(NAVSIM_EINVAL, "navsim_set_map has not been called");
+  if (h->cfg.sampler_mode == 1 && h->c.n_starts == 0)
+    return fail(NAVSIM_EINVAL, "sampler_mode = 1 but navsim_set_sampler has not been called");
+  return NAVSIM_OK;
+}
+
+// The per-kernel dynamic shared-memory limit is process-wide: only ever raise it, so that a handle with a
+// small map does not lower the limit an earlier handle with a big map still needs.
+int raise_smem_limit(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::vector<std::pair<const void*, int>> seen;
+  std::lock_guard<std::mutex> lock(mu);
+  for (auto& kv : seen)
+    if (kv.first == func) {
+      if (kv.second >= bytes) return NAVSIM_OK;
+      CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      kv.second = bytes;
+      return NAVSIM_OK;
+    }
+  CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  seen.emplace_back(func, bytes);
   return NAVSIM_OK;
 }
 
@@ -966,7 +1053,7 @@ extern "C" {
 
 const char* nav_last_error(void) { return g_err.c_str(); }
 
-int navsim_abi_version(void) { return 1; }
+int navsim_abi_version(void) { return 2; }
 
 int navsim_default_cfg(navsim_cfg* cfg, int32_t num_agents) {
   if (!cfg) return fail(NAVSIM_EINVAL, "cfg is null");
@@ -1001,6 +1088,12 @@ int navsim_default_cfg(navsim_cfg* cfg, int32_t num_agents) {
   memcpy(cfg->respawn_rects, respawn_r, sizeof respawn_r);
   cfg->n_reset_rects = 4;
   cfg->n_respawn_rects = 4;
+  cfg->lidar_noise_sigma = 0.0;        // gazebo.xacro:125 has 0.01; off by default (fidelity option)
+  cfg->wheel_accel = 0.0;              // gazebo.xacro:67 has 1; off by default (fidelity option)
+  cfg->wheel_separation = 0.160;       // gazebo.xacro:65, turtlebot3_fake.cpp:44
+  cfg->sampler_min_dist = 1.5;         // spawn_goal_sampler.py:38
+  cfg->sampler_max_dist = 6.0;
+  cfg->sampler_mode = 0;
   return NAVSIM_OK;
 }
 
@@ -1013,6 +1106,11 @@ int navsim_create(navsim_t** out, const navsim_cfg* cfg) {
       cfg->n_respawn_rects > NAVSIM_MAX_RECTS)
     return fail(NAVSIM_EINVAL, "too many rejection rectangles");
   if (!(cfg->goal_hi > cfg->goal_lo)) return fail(NAVSIM_EINVAL, "goal_hi must exceed goal_lo");
+  if (cfg->lidar_noise_sigma < 0.0 || cfg->wheel_accel < 0.0) return fail(NAVSIM_EINVAL, "negative fidelity option");
+  if (cfg->wheel_accel > 0.0 && !(cfg->wheel_separation > 0.0)) return fail(NAVSIM_EINVAL, "wheel_separation must be positive");
+  if (cfg->sampler_mode != 0 && cfg->sampler_mode != 1) return fail(NAVSIM_EINVAL, "sampler_mode is 0 or 1");
+  if (cfg->sampler_mode == 1 && !(cfg->sampler_max_dist >= cfg->sampler_min_dist))
+    return fail(NAVSIM_EINVAL, "sampler_max_dist must not be below sampler_min_dist");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -1035,6 +1133,9 @@ int navsim_create(navsim_t** out, const navsim_cfg* cfg) {
   memcpy(c.reset_rects, cfg->reset_rects, sizeof c.reset_rects);
   memcpy(c.respawn_rects, cfg->respawn_rects, sizeof c.respawn_rects);
   c.inv_diag = (float)(1.0 / cfg->diag_norm);
+  c.n_starts = 0; c.n_goals = 0; c.starts = nullptr; c.goals = nullptr; c.start_scans = nullptr;
+  c.smin = cfg->sampler_min_dist; c.smax = cfg->sampler_max_dist;
+  c.noise_sigma = (float)cfg->lidar_noise_sigma; c.wheel_accel = cfg->wheel_accel; c.wheel_sep = cfg->wheel_separation;
   for (int i = 0; i < NAVSIM_LIDAR_FEATS; ++i) c.pick[i] = (int)((double)(i * cfg->num_beams) / 10.0);  // :293
   c.rt_R = 0; c.rt_W = 1;
   h->lanes = pick_lanes(c.N, cfg->lanes_per_agent);
@@ -1052,15 +1153,16 @@ int navsim_create(navsim_t** out, const navsim_cfg* cfg) {
                   std::string(#expr) + ": " + cudaGetErrorString(e__));                            \
     }                                                                                              \
   } while (0)
-  TRY_OR_CLEAN(cudaMalloc(&dslab, N * 6 * sizeof(double)));
+  TRY_OR_CLEAN(cudaMalloc(&dslab, N * 8 * sizeof(double)));
   h->st.x = dslab; h->st.y = dslab + N; h->st.th = dslab + 2 * N;
   h->st.gx = dslab + 3 * N; h->st.gy = dslab + 4 * N; h->st.past = dslab + 5 * N;
+  h->st.vl = dslab + 6 * N; h->st.vr = dslab + 7 * N;
   TRY_OR_CLEAN(cudaMalloc(&fslab, N * 7 * sizeof(float)));
   h->st.pa0 = fslab; h->st.pa1 = fslab + N; h->st.ep_ret = fslab + 2 * N; h->st.ep_path = fslab + 3 * N;
   h->st.last_move = fslab + 4 * N;
   h->st.steps = reinterpret_cast<int32_t*>(fslab + 5 * N);
   h->st.draws = reinterpret_cast<uint32_t*>(fslab + 6 * N);
-  TRY_OR_CLEAN(cudaMemset(dslab, 0, N * 6 * sizeof(double)));
+  TRY_OR_CLEAN(cudaMemset(dslab, 0, N * 8 * sizeof(double)));
   TRY_OR_CLEAN(cudaMemset(fslab, 0, N * 7 * sizeof(float)));
   TRY_OR_CLEAN(cudaMalloc(&h->d_stats, sizeof(DevStats)));
   TRY_OR_CLEAN(cudaMemset(h->d_stats, 0, sizeof(DevStats)));
@@ -1098,6 +1200,9 @@ int navsim_destroy(navsim_t* h) {
   if (h->st.pa0) cudaFree(h->st.pa0);
   if (h->d_map) cudaFree(h->d_map);
   if (h->d_rt) cudaFree(h->d_rt);
+  if (h->d_starts) cudaFree(h->d_starts);
+  if (h->d_goals) cudaFree(h->d_goals);
+  if (h->d_start_scans) cudaFree(h->d_start_scans);
   if (h->d_stats) cudaFree(h->d_stats);
   if (h->h_act) cudaFreeHost(h->h_act);
   if (h->h_obs) cudaFreeHost(h->h_obs);
@@ -1158,6 +1263,8 @@ int navsim_set_map(navsim_t* h, const double* seg_host, int32_t num_segments, in
   if (h->d_map) { cudaFree(h->d_map); h->d_map = nullptr; }
   cudaError_t e = cudaMalloc(&h->d_map, bytes);
   if (e == cudaSuccess) e = cudaMemcpy(h->d_map, host, bytes, cudaMemcpyHostToDevice);
+  h->h_map.assign(host, host + bytes / sizeof(float));
+  h->closed = closed;
   delete[] host;
   if (e != cudaSuccess) return fail(NAVSIM_ECUDA, std::string("set_map: ") + cudaGetErrorString(e));
   // bearing table over every goal offset the map allows (capped; larger offsets are computed)
@@ -1188,12 +1295,50 @@ int navsim_set_map(navsim_t* h, const double* seg_host, int32_t num_segments, in
     return fail(NAVSIM_EINVAL, "map does not fit in shared memory");
   }
   const int smem = (int)step_smem_bytes(h);
-  CUDA_TRY(cudaFuncSetAttribute(step_kernel_of(h, false), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CUDA_TRY(cudaFuncSetAttribute(step_kernel_of(h, true), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CUDA_TRY(cudaFuncSetAttribute(navsim_step_anybeam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  if (int rc = raise_smem_limit((const void*)step_kernel_of(h, false), smem)) return rc;
+  if (int rc = raise_smem_limit((const void*)step_kernel_of(h, true), smem)) return rc;
+  if (int rc = raise_smem_limit((const void*)navsim_step_anybeam_kernel, smem)) return rc;
   const int aux = (int)aux_smem_bytes(h);
-  CUDA_TRY(cudaFuncSetAttribute(navsim_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, aux));
-  CUDA_TRY(cudaFuncSetAttribute(navsim_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, aux));
+  if (int rc = raise_smem_limit((const void*)navsim_reset_kernel, aux)) return rc;
+  if (int rc = raise_smem_limit((const void*)navsim_scan_kernel, aux)) return rc;
+  return NAVSIM_OK;
+}
+
+int navsim_set_sampler(navsim_t* h, const double* starts_host, int32_t n_starts, const double* goals_host, int32_t n_goals) {
+  if (!h || !starts_host || !goals_host) return fail(NAVSIM_EINVAL, "null argument");
+  if (!h->d_map) return fail(NAVSIM_EINVAL, "navsim_set_map has not been called");
+  if (h->cfg.sampler_mode != 1) return fail(NAVSIM_EINVAL, "the handle was not created with sampler_mode = 1");
+  if (n_starts < 1 || n_starts > NAVSIM_MAX_TABLE || n_goals < 1 || n_goals > NAVSIM_MAX_TABLE)
+    return fail(NAVSIM_EINVAL, "table sizes must be in 1..NAVSIM_MAX_TABLE");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  // LaserScan of every start pose, cast with the host build of the physics header against the uploaded map
+  const int B = h->c.B, S = h->S;
+  const float* seg = h->h_map.data();
+  const float *h_bc = seg + NV_SEG_FLOATS * S, *h_bs = h_bc + B;
+  std::vector<float> scans((size_t)n_starts * B);
+  for (int k = 0; k < n_starts; ++k) {
+    double sn, cs;
+    nv_sincos(starts_host[3 * k + 2], &sn, &cs);
+    const float ox = (float)(starts_host[3 * k] + h->cfg.lidar_offset_x * cs), oy = (float)(starts_host[3 * k + 1] + h->cfg.lidar_offset_x * sn);
+    for (int i = 0; i < B; ++i) {
+      float dx, dy;
+      nv_beam_dir((float)cs, (float)sn, h_bc[i], h_bs[i], &dx, &dy);
+      const float r = nv_range_from_q(nv_beam_q(ox, oy, dx, dy, seg, S, h->closed), (float)h->cfg.lidar_min, (float)h->cfg.lidar_max);
+      scans[(size_t)k * B + i] = (r == NV_INF_F) ? 3.5f : r;
+    }
+  }
+  if (h->d_starts) { cudaFree(h->d_starts); h->d_starts = nullptr; }
+  if (h->d_goals) { cudaFree(h->d_goals); h->d_goals = nullptr; }
+  if (h->d_start_scans) { cudaFree(h->d_start_scans); h->d_start_scans = nullptr; }
+  h->c.n_starts = 0;
+  CUDA_TRY(cudaMalloc(&h->d_starts, (size_t)n_starts * 3 * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->d_goals, (size_t)n_goals * 2 * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->d_start_scans, scans.size() * sizeof(float)));
+  CUDA_TRY(cudaMemcpy(h->d_starts, starts_host, (size_t)n_starts * 3 * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(h->d_goals, goals_host, (size_t)n_goals * 2 * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(h->d_start_scans, scans.data(), scans.size() * sizeof(float), cudaMemcpyHostToDevice));
+  h->c.starts = h->d_starts; h->c.goals = h->d_goals; h->c.start_scans = h->d_start_scans;
+  h->c.n_starts = n_starts; h->c.n_goals = n_goals;
   return NAVSIM_OK;
 }
 
@@ -1382,6 +1527,8 @@ static int field_ptr(navsim_t* h, int32_t field, void** p, size_t* elem) {
     case NAVSIM_F_EP_RETURN: *p = h->st.ep_ret; *elem = 4; break;
     case NAVSIM_F_EP_PATH: *p = h->st.ep_path; *elem = 4; break;
     case NAVSIM_F_LAST_MOVE: *p = h->st.last_move; *elem = 4; break;
+    case NAVSIM_F_WHEEL_L: *p = h->st.vl; *elem = 8; break;
+    case NAVSIM_F_WHEEL_R: *p = h->st.vr; *elem = 8; break;
     default: return fail(NAVSIM_EINVAL, "unknown state field");
   }
   return NAVSIM_OK;

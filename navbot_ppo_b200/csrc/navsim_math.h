@@ -29,6 +29,7 @@
 #define NV_HD static inline
 #endif
 
+#define NV_INF_F (__builtin_huge_valf())
 #define NV_PI        3.141592653589793238462643383279502884
 #define NV_TWO_PI    6.283185307179586476925286766559005768
 #define NV_RAD2DEG   0x1.ca5dc1a63c1f8p+5 /* 180.0 / pi, as CPython's math.degrees uses */
@@ -253,6 +254,78 @@ NV_HD void nv_drive(double* x, double* y, double* th, double v, double w, double
   *th = th_new;
 }
 
+// Fidelity option: the diff-drive plugin's wheel acceleration limit
+// (turtlebot3_burger.gazebo.xacro:67 <wheelAcceleration>, update rate 30 Hz :71).  The plugin's source is
+// not vendored; the model stated here is the one its parameters describe: at every plugin update (`substeps`
+// per LiDAR period) each wheel's rim speed moves toward its target by at most accel * dt_sub, and the pose is
+// integrated in the same midpoint form with the speeds of that sub-step.  vl / vr are the rim speeds in m/s
+// (state carried across steps, zero after a reset); targets from (v, w) as turtlebot3_fake.cpp:117-118.
+// accel <= 0 must not reach this function (the caller takes the plain nv_drive path).
+NV_HD void nv_drive_ramped(double* x, double* y, double* th, double* vl, double* vr, double v, double w, double dt,
+                           double accel, double wheel_sep, int substeps) {
+  const double tl = v - w * wheel_sep / 2.0, tr = v + w * wheel_sep / 2.0;
+  const double h = dt / (double)substeps, dmax = accel * h;
+  for (int k = 0; k < substeps; ++k) {
+    double dl = tl - *vl, dr = tr - *vr;
+    dl = dl > dmax ? dmax : (dl < -dmax ? -dmax : dl);
+    dr = dr > dmax ? dmax : (dr < -dmax ? -dmax : dr);
+    *vl = *vl + dl;
+    *vr = *vr + dr;
+    nv_drive(x, y, th, (*vr + *vl) / 2.0, (*vr - *vl) / wheel_sep, h);
+  }
+}
+
+// GoalSpawnSampler.sample_start_and_goal (spawn_goal_sampler.py:52-63): draw a start pose and a goal point
+// from the two tables until their distance lies in [min_dist, max_dist], at most 100 times, then take one
+// more pair unconditionally.  The reference draws rng.randint(len(table)) from numpy's Mersenne Twister;
+// here draw k of an agent is Philox block (k, 3, agent) and an index is floor(u32 * n / 2^32).
+NV_HD void nv_table_indices(uint64_t seed, uint64_t agent, uint32_t draw, int n_starts, int n_goals, int* is, int* ig) {
+  uint32_t o[4], hi, lo;
+  nv_philox4x32_10(draw, 3u, (uint32_t)agent, (uint32_t)(agent >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), o);
+  nv_mulhilo32(o[0], (uint32_t)n_starts, &hi, &lo);
+  *is = (int)hi;
+  nv_mulhilo32(o[1], (uint32_t)n_goals, &hi, &lo);
+  *ig = (int)hi;
+}
+NV_HD void nv_sample_tables(uint64_t seed, uint64_t agent, uint32_t* draws, const double* starts, int n_starts,
+                            const double* goals, int n_goals, double min_dist, double max_dist, int* is_out, int* ig_out) {
+  int is = 0, ig = 0;
+  for (int attempt = 0; attempt < 100; ++attempt) {                     // spawn_goal_sampler.py:53-54
+    nv_table_indices(seed, agent, *draws, n_starts, n_goals, &is, &ig);
+    *draws += 1u;
+    const double dx = starts[3 * is] - goals[2 * ig], dy = starts[3 * is + 1] - goals[2 * ig + 1];
+    const double dist = sqrt(dx * dx + dy * dy);                        // :57 np.linalg.norm
+    if (min_dist <= dist && dist <= max_dist) { *is_out = is; *ig_out = ig; return; }   // :58-59
+  }
+  nv_table_indices(seed, agent, *draws, n_starts, n_goals, &is, &ig);   // :60-62
+  *draws += 1u;
+  *is_out = is; *ig_out = ig;
+}
+
+// Fidelity option: Gaussian range noise of the ray sensor (turtlebot3_burger.gazebo.xacro:122-126, stddev
+// 0.01).  Four standard normals for beams 4 b4 .. 4 b4 + 3 of one scan: Philox block (b4, 4, agent) keyed by
+// the seed and mixed with the scan's identity (episode draw counter, step), Box-Muller in fp32.
+NV_HD void nv_scan_noise4(uint64_t seed, uint64_t agent, uint32_t episode_draws, uint32_t step, uint32_t b4, float n[4]) {
+  uint32_t o[4];
+  nv_philox4x32_10(b4 | (step << 8), 4u + (episode_draws << 4), (uint32_t)agent, (uint32_t)(agent >> 32),
+                   (uint32_t)seed, (uint32_t)(seed >> 32), o);
+  for (int k = 0; k < 2; ++k) {
+    const float u = ((float)(o[2 * k] >> 8) + 0.5f) * (1.0f / 16777216.0f);       // (0, 1)
+    const float v = ((float)(o[2 * k + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float r = sqrtf(-2.0f * logf(u));
+    n[2 * k] = r * cosf(6.283185307179586f * v);
+    n[2 * k + 1] = r * sinf(6.283185307179586f * v);
+  }
+}
+// the noisy range re-enters the sensor's gates (a hit pushed past max reads +inf, below min -inf)
+NV_HD float nv_noisy_range(float t, float noise, float sigma, float rmin, float rmax) {
+  if (!(t < NV_INF_F) || !(t > -NV_INF_F)) return t;   // no hit / already gated
+  const float r = t + sigma * noise;
+  if (r > rmax) return NV_INF_F;
+  if (r < rmin) return -NV_INF_F;
+  return r;
+}
+
 // ---------------------------------------------------------------------------------------
 // Row R — planar ray sensor, in fp32 like the float32 ranges a LaserScan carries (the
 // sensor's own resolution is 15 mm, gazebo.xacro:120).  The robot pose stays fp64; only
@@ -278,7 +351,6 @@ NV_HD void nv_drive(double* x, double* y, double* th, double v, double w, double
 // ---------------------------------------------------------------------------------------
 #define NV_SEG_FLOATS 8
 #define NV_SEG_EPS 1.0e-6f
-#define NV_INF_F (__builtin_huge_valf())
 #define NV_MAP_CLOSED_BOXES 1
 
 // {x0,y0,x1,y1} metres (double) -> packed fp32 record.

@@ -32,7 +32,15 @@ class VecEnv:
     def __init__(self, num_envs: int, map: str | np.ndarray = "stage_1", device: int | str | torch.device = 0,
                  seed: int = 0, max_episode_steps: int = 500, auto_reset: bool = True, is_training: bool = True,
                  num_beams: int = 10, agent_id_offset: int = 0, cfg: _capi.NavsimCfg | None = None,
-                 closed_boxes: bool = True, lanes_per_agent: int = 0):
+                 closed_boxes: bool = True, lanes_per_agent: int = 0, lidar: str | None = None,
+                 lidar_noise_sigma: float = 0.0, wheel_accel: float = 0.0, use_external_sampler: bool | str = False,
+                 sampler_min_dist: float = 1.5, sampler_max_dist: float = 6.0):
+        """Options beyond the reference Env (all off by default):
+        lidar="waffle"            the 360-beam, full-circle scan of turtlebot3_waffle.gazebo.xacro:118-125
+        lidar_noise_sigma         Gaussian range noise of the ray-sensor plugin (burger.gazebo.xacro:122-126: 0.01)
+        wheel_accel               the diff-drive plugin's wheel acceleration limit (burger.gazebo.xacro:67: 1)
+        use_external_sampler      start pose + goal from the GoalSpawnSampler tables (spawn_goal_sampler.py:37-72,
+                                  arguments.py:41): True = the table set of the map, or a world_type name"""
         self._h = ctypes.c_void_p()
         L = _capi.lib()
         dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
@@ -45,6 +53,14 @@ class VecEnv:
             cfg.max_episode_steps = max_episode_steps
             cfg.auto_reset = 1 if auto_reset else 0
             cfg.num_beams = num_beams
+            if lidar is not None:
+                if lidar != "waffle":
+                    raise ValueError("lidar presets: 'waffle' (default: the burger's 10-beam front scan)")
+                cfg.num_beams, cfg.fov_min, cfg.fov_max = 360, 0.0, 6.28319   # waffle.gazebo.xacro:118-125
+            cfg.lidar_noise_sigma = float(lidar_noise_sigma)
+            cfg.wheel_accel = float(wheel_accel)
+            cfg.sampler_mode = 1 if use_external_sampler else 0
+            cfg.sampler_min_dist, cfg.sampler_max_dist = float(sampler_min_dist), float(sampler_max_dist)
             cfg.agent_id_offset = agent_id_offset
             cfg.lanes_per_agent = lanes_per_agent   # 0: chosen from N by the library
             # environment_new.py:44-47
@@ -65,6 +81,13 @@ class VecEnv:
         self.closed_boxes = bool(closed_boxes)
         _capi.check(L.navsim_set_map(self._h, self.segments.ctypes.data, len(self.segments),
                                      _capi.MAP_CLOSED_BOXES if closed_boxes else 0))
+        self.sampler_tables = None
+        if use_external_sampler:      # (a caller-built cfg with sampler_mode = 1 sets its tables itself: set_sampler)
+            world = use_external_sampler if isinstance(use_external_sampler, str) else \
+                maps.SAMPLER_FOR_MAP.get(map if isinstance(map, str) else "", None)
+            if world is None:
+                raise ValueError("use_external_sampler=True needs a named map; pass the world_type ('small_house', 'stage1')")
+            self.set_sampler(*maps.sampler_tables(world))
         n = self.num_envs
         self.obs = torch.zeros((n, self.obs_dim), dtype=torch.float32, device=dev)
         self.rew = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -73,6 +96,13 @@ class VecEnv:
         self.trunc = torch.zeros(n, dtype=torch.uint8, device=dev)
         self._host_ptr_key, self._host_ptrs, self._host_keepalive = None, None, None
         self._step_host_fn = L.navsim_step_host
+
+    def set_sampler(self, starts, goals):
+        """GoalSpawnSampler tables: starts [n, 3] (x, y, yaw), goals [n, 2] (navsim_set_sampler)."""
+        st = np.ascontiguousarray(starts, dtype=np.float64).reshape(-1, 3)
+        go = np.ascontiguousarray(goals, dtype=np.float64).reshape(-1, 2)
+        _capi.check(_capi.lib().navsim_set_sampler(self._h, st.ctypes.data, len(st), go.ctypes.data, len(go)))
+        self.sampler_tables = (st, go)
 
     # -- lifecycle ----------------------------------------------------------------------
     def close(self):

@@ -31,10 +31,12 @@ import numpy as np
 LIDAR_Z = 0.182
 
 # robot spawn pose per map (x, y, yaw): turtlebot3_stage_1.launch:3-5; house: see the docstring
-SPAWN = {"stage_1": (0.0, 0.0, 0.0), "stage_2": (0.0, 0.0, 0.0), "house": (-3.0, 1.0, 0.0)}
+SPAWN = {"stage_1": (0.0, 0.0, 0.0), "stage_2": (0.0, 0.0, 0.0), "house": (-3.0, 1.0, 0.0),
+         "turtlebot3_world": (-2.0, -0.5, 0.0)}     # turtlebot3_world.launch:3-5
 # goal sampling square (environment_new.py:337) and whether the stage rejection rectangles
 # (:340-343) apply; the house has no such rectangles (goals are only used for the features)
-GOAL_RANGE = {"stage_1": (-3.6, 3.6, True), "stage_2": (-3.6, 3.6, True), "house": (-4.5, 4.5, False)}
+GOAL_RANGE = {"stage_1": (-3.6, 3.6, True), "stage_2": (-3.6, 3.6, True), "house": (-4.5, 4.5, False),
+              "turtlebot3_world": (-1.9, 1.9, False)}
 
 # (cx, cy, sx, sy, yaw) per collision box, yaw exactly as printed in the world file.
 _BOXES = {
@@ -112,6 +114,52 @@ _BOXES = {
 }
 
 
+# Start poses (x, y, yaw) and goal points (x, y) of the reference's GoalSpawnSampler, per world_type
+# (spawn_goal_sampler.py:5-35; data tables, reproduced as data).  `--use_external_sampler` (arguments.py:41) is
+# parsed and never read by the reference; VecEnv(use_external_sampler=...) honours it.
+SAMPLER_TABLES = {
+    "small_house": (
+        [(-3.5, 1.0, 0.0), (-3.0, 0.5, 1.57), (-2.5, 1.5, -1.57), (-3.0, 2.0, 0.0),
+         (-1.0, 0.0, 0.0), (-0.5, 0.5, 1.57), (0.0, 0.0, -1.57),
+         (2.0, 1.5, 3.14), (2.5, 0.5, -1.57), (3.0, 1.0, 0.0),
+         (1.0, -2.0, 1.57), (0.5, -2.5, 0.0), (1.5, -2.0, -1.57),
+         (-1.5, 2.5, 0.0), (-2.0, 3.0, 1.57),
+         (0.0, 1.0, 0.0), (-1.0, 1.5, 1.57), (1.0, 1.0, -1.57)],
+        [(-3.5, 0.5), (-3.0, 1.5), (-2.5, 2.0), (-3.5, 2.5), (-4.0, 1.0), (-2.0, 1.0), (-3.0, 0.0),
+         (-1.0, 0.5), (-0.5, 0.0), (0.0, 0.5), (-1.5, 0.0), (0.5, 0.0), (-1.0, -0.5),
+         (2.0, 0.5), (2.5, 1.0), (3.0, 1.5), (2.0, 2.0), (3.5, 1.0), (2.5, 0.0), (3.0, 0.5),
+         (1.0, -2.5), (0.5, -2.0), (1.5, -2.5), (1.0, -3.0), (0.0, -2.5), (1.5, -1.5),
+         (-1.5, 2.0), (-2.0, 2.5), (-1.0, 3.0), (-2.5, 2.5), (-1.5, 3.5),
+         (0.0, 1.5), (-1.0, 1.0), (1.0, 0.5), (0.5, 1.5), (-0.5, 1.0), (0.0, 2.0), (1.0, 1.5),
+         (-4.0, 3.0), (3.5, 2.0), (2.0, -3.0), (-2.0, -1.0)]),
+    "stage1": (
+        [(0.0, 0.0, 0.0), (0.5, 0.5, 0.785), (-0.5, 0.5, 2.356), (0.5, -0.5, -0.785),
+         (-0.5, -0.5, -2.356), (1.0, 0.0, 0.0), (0.0, 1.0, 1.57), (-1.0, 0.0, 3.14),
+         (0.0, -1.0, -1.57), (1.0, 1.0, 0.785)],
+        [(3.0, 3.0), (3.5, 2.5), (2.5, 3.5), (4.0, 3.0), (-3.0, 3.0), (-3.5, 2.5), (-2.5, 3.5), (-4.0, 3.0),
+         (3.0, -3.0), (3.5, -2.5), (2.5, -3.5), (4.0, -3.0), (-3.0, -3.0), (-3.5, -2.5), (-2.5, -3.5), (-4.0, -3.0),
+         (4.0, 0.0), (-4.0, 0.0), (0.0, 4.0), (0.0, -4.0), (3.0, 0.0), (-3.0, 0.0), (0.0, 3.0), (0.0, -3.0),
+         (2.0, 2.0), (-2.0, 2.0), (2.0, -2.0), (-2.0, -2.0)]),
+}
+# which table set a named map uses when the caller only says use_external_sampler=True
+SAMPLER_FOR_MAP = {"stage_1": "stage1", "stage_2": "stage1", "house": "small_house"}
+
+# upright cylinders (cx, cy, radius) crossing the LiDAR plane: models/turtlebot3_world/model.sdf (the nine pillars
+# of the standard TurtleBot3 world; its hexagonal outer wall is a mesh and is not compiled)
+_CYLINDERS = {
+    "turtlebot3_world": [(-1.1, -1.1, 0.15), (-1.1, 0.0, 0.15), (-1.1, 1.1, 0.15), (0.0, -1.1, 0.15), (0.0, 0.0, 0.15),
+                         (0.0, 1.1, 0.15), (1.1, -1.1, 0.15), (1.1, 0.0, 0.15), (1.1, 1.1, 0.15)],
+}
+
+
+def sampler_tables(world_type: str):
+    """(starts [n, 3], goals [n, 2]) float64 arrays of GoalSpawnSampler(world_type)."""
+    if world_type not in SAMPLER_TABLES:
+        raise ValueError(f"Unknown world_type: {world_type}")          # spawn_goal_sampler.py:49
+    st, go = SAMPLER_TABLES[world_type]
+    return np.asarray(st, dtype=np.float64).reshape(-1, 3), np.asarray(go, dtype=np.float64).reshape(-1, 2)
+
+
 def boxes_to_segments(boxes) -> np.ndarray:
     """Four edges per box, counter-clockwise, as float64 [4*len(boxes), 4]."""
     segs = []
@@ -128,8 +176,10 @@ def boxes_to_segments(boxes) -> np.ndarray:
 
 
 def get_map(name: str) -> np.ndarray:
+    if name in _CYLINDERS:
+        return np.concatenate([polygon_segments(cx, cy, r) for cx, cy, r in _CYLINDERS[name]])
     if name not in _BOXES:
-        raise KeyError(f"unknown map {name!r}; known: {sorted(_BOXES)}")
+        raise KeyError(f"unknown map {name!r}; known: {sorted(_BOXES) + sorted(_CYLINDERS)}")
     return boxes_to_segments(_BOXES[name])
 
 

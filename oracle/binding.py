@@ -29,12 +29,14 @@ def build(force: bool = False) -> str:
 
 class _State(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in
-                ("x", "y", "th", "gx", "gy", "past", "pa0", "pa1", "steps", "draws", "ep_ret", "ep_path", "last_move")]
+                ("x", "y", "th", "gx", "gy", "past", "pa0", "pa1", "steps", "draws", "ep_ret", "ep_path", "last_move", "vl", "vr")]
 
 
 class _Map(ctypes.Structure):
     _fields_ = [("seg", ctypes.c_void_p), ("S", ctypes.c_int32), ("closed_boxes", ctypes.c_int32),
-                ("bc", ctypes.c_void_p), ("bs", ctypes.c_void_p)]
+                ("bc", ctypes.c_void_p), ("bs", ctypes.c_void_p),
+                ("starts", ctypes.c_void_p), ("n_starts", ctypes.c_int32),
+                ("goals", ctypes.c_void_p), ("n_goals", ctypes.c_int32)]
 
 
 class OracleCfg(ctypes.Structure):
@@ -53,6 +55,9 @@ class OracleCfg(ctypes.Structure):
         ("diag_norm", ctypes.c_double), ("goal_lo", ctypes.c_double), ("goal_hi", ctypes.c_double),
         ("start_x", ctypes.c_double), ("start_y", ctypes.c_double), ("start_theta", ctypes.c_double),
         ("reset_rects", ctypes.c_double * 32), ("respawn_rects", ctypes.c_double * 32),
+        ("lidar_noise_sigma", ctypes.c_double), ("wheel_accel", ctypes.c_double), ("wheel_separation", ctypes.c_double),
+        ("sampler_min_dist", ctypes.c_double), ("sampler_max_dist", ctypes.c_double),
+        ("sampler_mode", ctypes.c_int32), ("reserved0", ctypes.c_int32),
     ]
 
 
@@ -96,6 +101,10 @@ def lib():
         L.oracle_step.restype = ctypes.c_int
         L.oracle_run_scripted.argtypes = [vp, vp, vp, u64, i32, i32, vp, vp, vp, vp, vp, vp, ctypes.c_int]
         L.oracle_run_scripted.restype = ctypes.c_int
+        L.oracle_table_indices.argtypes = [u64, u64, u32, ctypes.c_int, ctypes.c_int, vp, vp]
+        L.oracle_table_indices.restype = None
+        L.oracle_drive_ramped.argtypes = [vp, vp, vp, vp, vp, d, d, d, d, d, ctypes.c_int]
+        L.oracle_drive_ramped.restype = None
         L.oracle_default_cfg.argtypes = [vp, i32]
         L.oracle_default_cfg.restype = ctypes.c_int
         L.oracle_scripted_actions.argtypes = [u64, ctypes.c_int64, i32, i32, vp]
@@ -123,13 +132,14 @@ def lib():
 
 _FIELDS = [("x", np.float64), ("y", np.float64), ("th", np.float64), ("gx", np.float64), ("gy", np.float64),
            ("past", np.float64), ("pa0", np.float32), ("pa1", np.float32), ("steps", np.int32),
-           ("draws", np.uint32), ("ep_ret", np.float32), ("ep_path", np.float32), ("last_move", np.float32)]
+           ("draws", np.uint32), ("ep_ret", np.float32), ("ep_path", np.float32), ("last_move", np.float32),
+           ("vl", np.float64), ("vr", np.float64)]
 
 
 class OracleSim:
     """N independent reference environments on the CPU (state as numpy SoA arrays)."""
 
-    def __init__(self, cfg, segments, nthreads: int = 1, closed_boxes: bool = True):
+    def __init__(self, cfg, segments, nthreads: int = 1, closed_boxes: bool = True, sampler_tables=None):
         self.cfg = cfg  # a navbot_ppo_b200._capi.NavsimCfg (the public C struct)
         self.n = int(cfg.num_agents)
         self.nthreads = nthreads
@@ -140,8 +150,14 @@ class OracleSim:
         self.segf = np.zeros((len(self.seg), 8), np.float32)
         lib().shim_pack_segments(self.seg.ctypes.data, len(self.seg), cfg.lidar_max, self.segf.ctypes.data)
         self.closed_boxes = 1 if closed_boxes else 0
-        self.map = _Map(self.segf.ctypes.data, len(self.seg), self.closed_boxes, self.bc.ctypes.data,
-                        self.bs.ctypes.data)
+        if sampler_tables is not None:   # (starts [n,3], goals [n,2]) of spawn_goal_sampler.py:5-35
+            self.starts = np.ascontiguousarray(sampler_tables[0], dtype=np.float64).reshape(-1, 3)
+            self.goals = np.ascontiguousarray(sampler_tables[1], dtype=np.float64).reshape(-1, 2)
+            self.map = _Map(self.segf.ctypes.data, len(self.seg), self.closed_boxes, self.bc.ctypes.data, self.bs.ctypes.data,
+                            self.starts.ctypes.data, len(self.starts), self.goals.ctypes.data, len(self.goals))
+        else:
+            self.map = _Map(self.segf.ctypes.data, len(self.seg), self.closed_boxes, self.bc.ctypes.data,
+                            self.bs.ctypes.data, None, 0, None, 0)
         self.arr = {name: np.zeros(self.n, dtype=dt) for name, dt in _FIELDS}
         self.state = _State(*[self.arr[name].ctypes.data for name, _ in _FIELDS])
         self.stats = None

@@ -62,3 +62,41 @@ def test_golden_covers_the_edge_cases():
     assert rel.min() < 0.1 and rel.max() > 0.9
     diff = g1["obs_next"][..., 15]
     assert diff.min() < -0.9 and diff.max() > 0.9
+
+
+def test_table_sampler_restatement_reproduces_the_reference_class():
+    """spawn_goal_sampler.py:52-63 restated in C (oracle: ref_sample_start_and_goal): start pose / goal point
+    sequences and index pairs consumed, for 24 robots x 12 resets, against the recording of the reference's own
+    GoalSpawnSampler driven by the same index stream (oracle/make_golden_sampler.py) — default window on both
+    table sets, and a 1.9 .. 2.0 m window where most calls run into the 100-attempt cut-off."""
+    from navbot_ppo_b200 import maps
+    g = golden("sampler_tables")
+    for tag in ("house_default", "stage1_default", "stage1_tight"):
+        rows, draws = g[tag + "_rows"], g[tag + "_draws"]
+        lo, hi, seed = (float(v) for v in g[tag + "_cfg"])
+        world = str(g[tag + "_world"])
+        agents, episodes = draws.shape
+        cfg = binding.default_cfg(agents)
+        cfg.seed = int(seed)
+        cfg.sampler_mode, cfg.sampler_min_dist, cfg.sampler_max_dist = 1, lo, hi
+        sim = binding.OracleSim(cfg, maps.get_map("house" if world == "small_house" else "stage_1"),
+                                sampler_tables=maps.sampler_tables(world))
+        for e in range(episodes):
+            sim.reset()
+            got = np.stack([sim.arr[k] for k in ("x", "y", "th", "gx", "gy")], 1)
+            assert np.array_equal(got, rows[:, e]), (tag, e)
+            assert np.array_equal(sim.arr["draws"], draws[:, e]), (tag, e)
+        if tag == "stage1_tight":
+            per_call = np.diff(np.concatenate([np.zeros((agents, 1), np.int64), draws], 1), axis=1)
+            assert (per_call == 101).any() and (per_call < 101).any()      # both the cut-off and early exits occur
+
+
+def test_oracle_cfg_mirror_matches_the_public_struct():
+    """oracle/binding.OracleCfg restates include/navsim.h's navsim_cfg so that bench.py's CPU arm never loads
+    the product library: same fields, same defaults, same stage_1 geometry."""
+    import ctypes
+    from navbot_ppo_b200 import _capi, maps
+    assert [f[0] for f in binding.OracleCfg._fields_] == [f[0] for f in _capi.NavsimCfg._fields_]
+    assert ctypes.sizeof(binding.OracleCfg) == ctypes.sizeof(_capi.NavsimCfg)
+    assert bytes(binding.default_cfg(77)) == bytes(_capi.default_cfg(77))
+    assert np.array_equal(binding.stage_1_segments(), maps.get_map("stage_1"))
