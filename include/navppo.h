@@ -167,6 +167,22 @@ int navppo_tc_selftest(const float* A, const float* B, float* D, int32_t N, int3
 int navppo_tc_selftest_bf16(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t a_mode, int32_t b_mode,
                             int32_t passes, void* stream);
 
+/* Gradient exchange over NVLink peer memory, fused into the optimiser step.  Every rank owns two
+ * flat-gradient buffers (epochs alternate between them) and a flag array of 16 words, allocated so that every
+ * rank can address every other rank's copy (CUDA VMM / torch symmetric memory).  grad_ptrs[2 * world]: address, on
+ * THIS device, of buffer b of rank r at [b * world + r]; flag_ptrs[world]: address of rank r's flag array;
+ * multicast_ptrs[2] (may be NULL): NVLS multicast address of buffer b.  The flag arrays must be zero. */
+int navppo_peer_setup(navppo_t* h, int32_t rank, int32_t world, const uint64_t* grad_ptrs, const uint64_t* flag_ptrs,
+                      const uint64_t* multicast_ptrs);
+/* One epoch's optimiser step on every rank: a cross-GPU barrier over the flag arrays (every rank's navppo_grad has
+ * written its own buffer `buffer`; `token` = 1, 2, 3, .. must grow by one per call, the same on every rank, for the
+ * lifetime of the flag arrays), then Adam with the gradient = sum over the ranks of their buffers, read straight
+ * from peer memory in rank order (bit-identical on every rank), or — use_multicast — with one
+ * multimem.ld_reduce per element (the NVSwitch adds).  Replaces ncclAllReduce + navppo_adam; the NCCL path stays as
+ * the fallback and the correctness reference. */
+int navppo_adam_peer(navppo_t* h, float* params, float* exp_avg, float* exp_avg_sq, int32_t step, int32_t buffer,
+                     uint32_t token, int32_t use_multicast, double* metrics, void* stream);
+
 /* Diagnostic: while `device_counters` (32 + 4 * 512 int64 on the device) is non-NULL, split-BF16
  * gradient passes run an instrumented build of the tcgen05 kernel whose CTA (0, 0) writes per-role
  * cycle counters there (epilogue warp 0: [0..7], epilogue warp 4: [8..15], MMA thread: [16..23], flush

@@ -131,6 +131,8 @@ NAVPPO_SYMBOLS = {
     "navppo_tc_selftest": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "navppo_tc_selftest_bf16": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "navppo_tc_profile": (ctypes.c_int, [_vp]),
+    "navppo_peer_setup": (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
+    "navppo_adam_peer": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _u32, _i32, _vp, _vp]),
     "navppo_update": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _f64, _i32, _vp, _vp, _vp, _vp]),
 }
 

@@ -705,15 +705,55 @@ __global__ void grad_reduce_kernel(const float* __restrict__ gpart, const double
   }
 }
 
+// Where the Adam kernel takes the gradient from.
+//   GRAD_LOCAL  g[i]                                             (one GPU, or after an NCCL all-reduce)
+//   GRAD_PEERS  sum over the ranks, in rank order, of peer[r][i]  — every rank's flat gradient sits in a buffer
+//               all ranks have mapped (NVLink peer memory); each rank reads all of them and adds them in the same
+//               order, so the sum is bit-identical on every rank and the all-reduce is fused into the optimiser step
+//   GRAD_NVLS   multimem.ld_reduce.add on the buffers' multicast address: the NVSwitch adds the ranks' values on
+//               the way (one load per element instead of one per rank; the switch's order is its own)
+enum { GRAD_LOCAL = 0, GRAD_PEERS = 1, GRAD_NVLS = 2 };
+constexpr int MAX_PEERS = 16;
+struct PeerPtrs {
+  const float* grad[MAX_PEERS];   // this epoch's buffer of every rank (device pointers valid on THIS rank)
+  const float* mc;                // multicast address of the same buffer, or null
+  int world;
+};
+
+__device__ __forceinline__ float ld_peer(const float* p) {   // bypass L1: a peer's line may have changed since last epoch
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_nvls_sum(const float* mc) {
+  float v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(v) : "l"(mc) : "memory");
+  return v;
+}
+
 // torch.optim.Adam (defaults) on the flat vector; per-block squared-gradient partials.
-__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+template <int SRC>
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, PeerPtrs peers,
                                                    float* __restrict__ m1, float* __restrict__ m2, float lr_over_bc1,
                                                    float inv_sqrt_bc2, float b1, float b2, float eps,
                                                    double* __restrict__ sq_part) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double sa = 0.0, sc = 0.0;
   if (i < NAVPPO_FLAT) {
-    const float gi = g[i];
+    float gi;
+    if (SRC == GRAD_LOCAL) {
+      gi = g[i];
+    } else if (SRC == GRAD_PEERS) {
+      float v[MAX_PEERS];
+#pragma unroll
+      for (int r = 0; r < MAX_PEERS; ++r) v[r] = r < peers.world ? ld_peer(peers.grad[r] + i) : 0.f;   // all loads in flight
+      gi = v[0];
+#pragma unroll
+      for (int r = 1; r < MAX_PEERS; ++r)
+        if (r < peers.world) gi += v[r];
+    } else {
+      gi = ld_nvls_sum(peers.mc + i);
+    }
     const float m = fmaf(1.f - b1, gi - m1[i], m1[i]);          // exp_avg.lerp_(grad, 1 - beta1)
     const float v = fmaf(b2, m2[i], (1.f - b2) * gi * gi);      // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
     m1[i] = m; m2[i] = v;
@@ -733,6 +773,25 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     for (int k = 0; k < 8; ++k) { ta += wa[k]; tc += wc[k]; }
     sq_part[2 * blockIdx.x] = ta;
     sq_part[2 * blockIdx.x + 1] = tc;
+  }
+}
+
+// Cross-GPU barrier over peer memory: rank r writes `token` into slot r of every rank's flag array and waits until
+// its own array holds the token from every rank.  Ordered after the kernel that wrote this rank's gradient buffer
+// (same stream) and before the Adam kernel that reads everyone's: release / acquire at system scope.
+struct PeerFlags {
+  uint32_t* flags[MAX_PEERS];     // flag array (MAX_PEERS words) of every rank, mapped on this rank
+  int rank, world;
+};
+__global__ void peer_barrier_kernel(PeerFlags f, uint32_t token) {
+  const int t = threadIdx.x;
+  if (t < f.world) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.flags[t] + f.rank), "r"(token) : "memory");
+    uint32_t seen;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(f.flags[f.rank] + t) : "memory");
+    } while ((int32_t)(seen - token) < 0);
   }
 }
 
@@ -759,6 +818,11 @@ struct navppo {
   float* grad_ws = nullptr;   // [NAVPPO_FLAT] used by navppo_update
   float* wprep = nullptr;     // tensor-core path: pre-split, pre-tiled weights
   bool tc_single_role = false;  // NAVPPO_TC_KERNEL=single: the first (single-role) tcgen05 kernel, kept as a cross-check
+  // peer-memory gradient exchange (navppo_peer_setup): two gradient buffers + a flag array per rank
+  int peer_rank = 0, peer_world = 0;
+  const float* peer_grad[2][16] = {};
+  const float* peer_mc[2] = {nullptr, nullptr};
+  uint32_t* peer_flags[16] = {};
   int sm_count = 148;
   int64_t launches = 0;
 };
@@ -969,10 +1033,64 @@ int navppo_adam(navppo_t* h, float* params, const float* grad, float* exp_avg, f
   cudaStream_t s = (cudaStream_t)stream;
   const double b1 = h->cfg.beta1, b2 = h->cfg.beta2;
   const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
-  adam_kernel<<<ADAM_GRID, ADAM_BLOCK, 0, s>>>(params, grad, exp_avg, exp_avg_sq, (float)(h->cfg.lr / bc1),
-                                              (float)(1.0 / sqrt(bc2)), (float)b1, (float)b2, (float)h->cfg.adam_eps,
-                                              h->sq_part);
+  adam_kernel<GRAD_LOCAL><<<ADAM_GRID, ADAM_BLOCK, 0, s>>>(params, grad, PeerPtrs{}, exp_avg, exp_avg_sq,
+                                                          (float)(h->cfg.lr / bc1), (float)(1.0 / sqrt(bc2)), (float)b1,
+                                                          (float)b2, (float)h->cfg.adam_eps, h->sq_part);
   h->launches++;
+  if (metrics) {
+    gradnorm_finalize_kernel<<<1, 32, 0, s>>>(h->sq_part, ADAM_GRID, metrics);
+    h->launches++;
+  }
+  NAV_CUDA_TRY(cudaGetLastError());
+  return NAVSIM_OK;
+}
+
+int navppo_peer_setup(navppo_t* h, int32_t rank, int32_t world, const uint64_t* grad_ptrs, const uint64_t* flag_ptrs,
+                      const uint64_t* multicast_ptrs) {
+  if (int rc = check_handle(h)) return rc;
+  if (!grad_ptrs || !flag_ptrs) return nav_fail(NAVSIM_EINVAL, "null pointer table");
+  if (world < 1 || world > MAX_PEERS || rank < 0 || rank >= world) return nav_fail(NAVSIM_EINVAL, "rank / world out of range");
+  for (int b = 0; b < 2; ++b) {
+    for (int r = 0; r < world; ++r) {
+      if (!grad_ptrs[b * world + r]) return nav_fail(NAVSIM_EINVAL, "null peer buffer");
+      h->peer_grad[b][r] = reinterpret_cast<const float*>(grad_ptrs[b * world + r]);
+    }
+    h->peer_mc[b] = multicast_ptrs ? reinterpret_cast<const float*>(multicast_ptrs[b]) : nullptr;
+  }
+  for (int r = 0; r < world; ++r) {
+    if (!flag_ptrs[r]) return nav_fail(NAVSIM_EINVAL, "null peer flag array");
+    h->peer_flags[r] = reinterpret_cast<uint32_t*>(flag_ptrs[r]);
+  }
+  h->peer_rank = rank; h->peer_world = world;
+  return NAVSIM_OK;
+}
+
+int navppo_adam_peer(navppo_t* h, float* params, float* exp_avg, float* exp_avg_sq, int32_t step, int32_t buffer,
+                     uint32_t token, int32_t use_multicast, double* metrics, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (!params || !exp_avg || !exp_avg_sq) return nav_fail(NAVSIM_EINVAL, "null buffer");
+  if (h->peer_world < 1) return nav_fail(NAVSIM_EINVAL, "navppo_peer_setup has not been called");
+  if (step < 1) return nav_fail(NAVSIM_EINVAL, "step is 1-based");
+  if (buffer != 0 && buffer != 1) return nav_fail(NAVSIM_EINVAL, "buffer is 0 or 1");
+  if (use_multicast && !h->peer_mc[buffer]) return nav_fail(NAVSIM_EINVAL, "no multicast address was given to navppo_peer_setup");
+  cudaStream_t s = (cudaStream_t)stream;
+  PeerFlags f{};
+  PeerPtrs pp{};
+  for (int r = 0; r < h->peer_world; ++r) { f.flags[r] = h->peer_flags[r]; pp.grad[r] = h->peer_grad[buffer][r]; }
+  f.rank = h->peer_rank; f.world = h->peer_world;
+  pp.world = h->peer_world; pp.mc = h->peer_mc[buffer];
+  peer_barrier_kernel<<<1, 32, 0, s>>>(f, token);
+  const double b1 = h->cfg.beta1, b2 = h->cfg.beta2;
+  const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
+  if (use_multicast)
+    adam_kernel<GRAD_NVLS><<<ADAM_GRID, ADAM_BLOCK, 0, s>>>(params, nullptr, pp, exp_avg, exp_avg_sq, (float)(h->cfg.lr / bc1),
+                                                           (float)(1.0 / sqrt(bc2)), (float)b1, (float)b2,
+                                                           (float)h->cfg.adam_eps, h->sq_part);
+  else
+    adam_kernel<GRAD_PEERS><<<ADAM_GRID, ADAM_BLOCK, 0, s>>>(params, nullptr, pp, exp_avg, exp_avg_sq, (float)(h->cfg.lr / bc1),
+                                                            (float)(1.0 / sqrt(bc2)), (float)b1, (float)b2,
+                                                            (float)h->cfg.adam_eps, h->sq_part);
+  h->launches += 2;
   if (metrics) {
     gradnorm_finalize_kernel<<<1, 32, 0, s>>>(h->sq_part, ADAM_GRID, metrics);
     h->launches++;

@@ -125,6 +125,7 @@ class PPO:
         self.critic_optim = _FlatAdam(self, "critic")      # ppo.py:117
         self.world = navdist.world_size()
         self.rank = navdist.rank()
+        self._peer = None                                  # gradient exchange over NVLink peer memory (else NCCL)
         if self.world > 1:
             navdist.broadcast_(self.flat)                  # every rank starts from rank 0's weights
 
@@ -136,6 +137,8 @@ class PPO:
         self.horizon = max(1, math.ceil(self.timesteps_per_batch / n_env)) if self.vectorized else self.timesteps_per_batch
         self._max_T = self.horizon * n_env if self.vectorized else self.timesteps_per_batch
         self._h = self._handle_for(self._max_T)
+        if self.world > 1:
+            self._setup_peer_exchange()
         self._draw = 0                                     # Philox counter of the action noise
         self._stats = torch.zeros(3, dtype=torch.float64, device=self.device)
         self.logger = {"delta_t": time.time(), "t_so_far": 0, "i_so_far": 0, "batch_lens": [], "batch_rews": [],
@@ -170,6 +173,7 @@ class PPO:
         self.continue_episodes = False
         self.bootstrap_value = False
         self.graph_rollout = True         # vectorised rollouts: replay the step loop as one CUDA graph
+        self.gradient_exchange = "peer"   # multi-GPU: "peer" | "nvls" | "nccl" (see _setup_peer_exchange)
         self.log_episodes = True          # vectorised rollouts: one csv row per completed episode ...
         self.max_logged_episodes = 4096   # ... up to this many per iteration (None: all)
         for k, v in hyperparameters.items():
@@ -180,6 +184,47 @@ class PPO:
         if self.seed is not None:                          # ppo.py:805-811
             assert type(self.seed) == int
             torch.manual_seed(self.seed)
+
+    def _setup_peer_exchange(self):
+        """Per-epoch gradient exchange fused into the optimiser step: every rank's flat gradient lives in
+        symmetric (peer-mapped) memory, and the Adam kernel adds the ranks' buffers itself, straight over
+        NVLink (navppo_adam_peer).  gradient_exchange = "peer" (default: ordered peer loads, identical bits on
+        every rank), "nvls" (multimem.ld_reduce on the multicast address) or "nccl" (all-reduce + Adam, the
+        fallback and the correctness reference).  Anything the platform lacks falls back to NCCL."""
+        mode = os.environ.get("NAVPPO_GRAD_EXCHANGE", self.gradient_exchange)
+        if mode == "nccl" or self.device.type != "cuda":
+            return
+        try:
+            import torch.distributed as td
+            import torch.distributed._symmetric_memory as symm
+            F = _capi.PPO_FLAT
+            buf = symm.empty(2 * F + 16, dtype=torch.float32, device=self.device)
+            hdl = symm.rendezvous(buf, group=td.group.WORLD)
+            buf.zero_()
+            torch.cuda.synchronize(self.device)
+            hdl.barrier()
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            W, R = int(hdl.world_size), int(hdl.rank)
+            grad_ptrs = (ctypes.c_uint64 * (2 * W))(*[ptrs[r] + b * F * 4 for b in range(2) for r in range(W)])
+            flag_ptrs = (ctypes.c_uint64 * W)(*[ptrs[r] + 2 * F * 4 for r in range(W)])
+            mc = int(hdl.multicast_ptr) if getattr(hdl, "has_multicast_support", lambda *a: False) and hdl.multicast_ptr else 0
+            mc_ptrs = (ctypes.c_uint64 * 2)(mc, mc + F * 4) if mc else None
+            if mode == "nvls" and not mc:
+                mode = "peer"
+            self._peer = dict(buf=buf, hdl=hdl, grads=[buf[:F], buf[F:2 * F]], epoch=0, nvls=(mode == "nvls"),
+                              tables=(R, W, grad_ptrs, flag_ptrs, mc_ptrs), bound=None)
+            self._bind_peer()
+        except Exception as e:  # noqa: BLE001 - no peer access / no symmetric memory: NCCL does the exchange
+            if self.verbose and self.rank == 0:
+                print(f"[PPO] peer-memory gradient exchange unavailable ({type(e).__name__}: {e}); using NCCL", flush=True)
+            self._peer = None
+
+    def _bind_peer(self, force=False):
+        """Hand the peer pointer tables to the navppo handle in use (handles are re-picked when the batch grows)."""
+        if self._peer is not None and (force or self._peer["bound"] != self._h.value):
+            R, W, grad_ptrs, flag_ptrs, mc_ptrs = self._peer["tables"]
+            _capi.check(_capi.lib().navppo_peer_setup(self._h, R, W, grad_ptrs, flag_ptrs, mc_ptrs))
+            self._peer["bound"] = self._h.value
 
     def _alloc_rollout_buffers(self):
         if not self.vectorized:
@@ -204,6 +249,8 @@ class PPO:
         """navppo handle whose gradient workspace covers T samples."""
         self._max_T = max(self._max_T, int(T), 1)
         self._h = _Handles.get(self.device, self._max_T, self.clip, self.lr, self.precision)
+        if getattr(self, "_peer", None) is not None:
+            self._bind_peer()
         return self._h
 
     @property
@@ -431,8 +478,21 @@ class PPO:
             navdist.all_reduce_sum_(self._stats)                       # global mean / std (ppo.py:284)
             n_global = int(round(float(self._stats[2].item())))
             _capi.check(L.navppo_adv_normalize(rtg.data_ptr(), v.data_ptr(), T, self._stats.data_ptr(), adv.data_ptr(), sp))
+            self._bind_peer(force=True)        # (handles are shared between trainers of one process)
             for e in range(epochs):
                 row = metrics[e]
+                if self._peer is not None:
+                    # the rank's gradient goes straight into its peer-mapped buffer; the optimiser step adds the
+                    # ranks' buffers over NVLink (one barrier + one kernel instead of ncclAllReduce + Adam)
+                    b = self._peer["epoch"] & 1
+                    _capi.check(L.navppo_grad(self._h, self.flat.data_ptr(), obs.data_ptr(), act.data_ptr(),
+                                              logp_old.data_ptr(), adv.data_ptr(), rtg.data_ptr(), T, n_global, self.var,
+                                              self._peer["grads"][b].data_ptr(), row.data_ptr(), sp))
+                    self._peer["epoch"] += 1
+                    _capi.check(L.navppo_adam_peer(self._h, self.flat.data_ptr(), self._exp_avg.data_ptr(),
+                                                   self._exp_avg_sq.data_ptr(), self._adam_step + e + 1, b,
+                                                   self._peer["epoch"], 1 if self._peer["nvls"] else 0, row.data_ptr(), sp))
+                    continue
                 _capi.check(L.navppo_grad(self._h, self.flat.data_ptr(), obs.data_ptr(), act.data_ptr(),
                                           logp_old.data_ptr(), adv.data_ptr(), rtg.data_ptr(), T, n_global, self.var,
                                           self._grad.data_ptr(), row.data_ptr(), sp))

@@ -410,3 +410,19 @@ def test_vectorised_learn_counts_every_simulated_step_and_checks_the_episode_cap
     with pytest.raises(ValueError):
         PPO(NetActor, NetCritic, env, 16, 2, timesteps_per_batch=256 * 8, max_timesteps_per_episode=800,
             output_dir=str(tmp_path), method_name="d", verbose=False)
+
+
+def test_sharded_update_equals_single_gpu_update_on_two_ranks():
+    """Two NCCL ranks, each on half of a fixed batch, land on the parameters one GPU reaches on the whole batch, for
+    the NCCL all-reduce and for the peer-memory exchange fused into Adam (tools/dist_check.py; skipped on a box with
+    one GPU)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "dist_check.py")],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert "DIST_CHECK OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]

@@ -1,7 +1,9 @@
 """torchrun --nproc-per-node 2 tools/dist_check.py
-Two ranks each update on half of a fixed batch (NCCL all-reduce of the flat gradient per epoch,
-3-double all-reduce of the advantage statistics) and must land on the parameters a single GPU
-reaches on the whole batch."""
+The ranks each update on their share of a fixed batch (3-double all-reduce of the advantage statistics, per-epoch
+exchange of the flat gradient) and must land on the parameters a single GPU reaches on the whole batch — for every
+gradient-exchange mode: "nccl" (all-reduce + Adam), "peer" (Adam adds the ranks' peer-mapped buffers itself, in rank
+order) and "nvls" (multimem.ld_reduce, where the platform has a multicast address).  Every rank must end with
+bit-identical weights in the nccl and peer modes."""
 import os
 import sys
 import tempfile
@@ -30,14 +32,19 @@ def main():
     obs = (g["obs"][idx] + rng.normal(scale=0.01, size=(T, 16))).astype(np.float32)
     act, lp, rtg = g["acts"][idx], g["logp"][idx], g["rtgs"][idx]
     ok = True
-    for prec, tol in ((_capi.PREC_FP32, 2e-5), (_capi.PREC_BF16X3, 5e-5)):
+    for prec, tol, exchange in ((_capi.PREC_FP32, 2e-5, "nccl"), (_capi.PREC_FP32, 2e-5, "peer"), (_capi.PREC_BF16X3, 5e-5, "peer"),
+                                (_capi.PREC_BF16X3, 5e-5, "nvls"), (_capi.PREC_BF16X3, 5e-5, "nccl")):
         results = {}
+        used = exchange
         for mode in ("sharded", "single"):
             with tempfile.TemporaryDirectory() as tmp:
                 torch.manual_seed(0)
                 env = VecEnv(64, device=local, seed=0, agent_id_offset=rank * 64)
                 agent = PPO(NetActor, NetCritic, env, 16, 2, timesteps_per_batch=64, n_updates_per_iteration=3, lr=3e-4,
-                            output_dir=tmp, method_name=f"r{rank}", verbose=False, precision=prec)
+                            output_dir=tmp, method_name=f"r{rank}", verbose=False, precision=prec,
+                            gradient_exchange=exchange)
+                if mode == "sharded":
+                    used = "nccl" if agent._peer is None else ("nvls" if agent._peer["nvls"] else "peer")
                 if mode == "single":
                     agent.world = 1
                     lo, hi = 0, T
@@ -54,9 +61,9 @@ def main():
         dist.broadcast(w, src=0)
         same = bool(torch.equal(w, results["sharded"][0]))
         if rank == 0:
-            print(f"precision={prec} world={world}: max |param(sharded) - param(single)| = {d:.3e} (tol {tol:.0e}); "
+            print(f"precision={prec} world={world} exchange={exchange} (in force: {used}): max |param(sharded) - param(single)| = {d:.3e} (tol {tol:.0e}); "
                   f"actor-loss diff {la:.2e}; critic-loss rel diff {lc:.2e}", flush=True)
-        flag = torch.tensor([1.0 if (same and d <= tol) else 0.0], device=dev)
+        flag = torch.tensor([1.0 if ((same or used == "nvls") and d <= tol) else 0.0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         ok = ok and bool(flag.item() == 1.0)
         if rank == 0:
