@@ -42,6 +42,15 @@ BYTES_SURVEY_FP64_POSE = 174
 NCU_TRAFFIC_BYTES_PER_LAUNCH = {(8192, 128): 739072 + 17440768}   # profiles/r01p_step_8192_fused_ncu.csv
 
 
+# FP32 work of one env-step on the house map by beam count: (fadd + fmul + 2 ffma) thread-level instruction counts of
+# one fused launch from `ncu --metrics smsp__sass_thread_inst_executed_op_{fadd,fmul,ffma}_pred_on.sum`
+# (profiles/r02_c5_house_flops.txt), divided by the env-steps of that launch
+NCU_FP32_FLOP_PER_ENV_STEP = {("house", 10): 4396.0, ("house", 12): 9012.0, ("house", 18): 9120.0, ("house", 24): 9210.0,
+                              ("house", 36): 9434.0}
+# FP32 ALU peak the c5 figures are quoted against: 148 SMs x 128 lanes x 2 flop x 1.965 GHz (nominal)
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -347,6 +356,31 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * N * e2e_steps / float(t.item())
+    # the asynchronous form: two buffer sets, step t + 1 is enqueued before step t's results are awaited (every step
+    # still takes its actions from host memory and delivers its results to host memory)
+    depth = 4                                            # NAVSIM_ASYNC_DEPTH
+    sets = [hb] + [env.alloc_host_buffers() for _ in range(depth - 1)]
+    for sb in sets[1:]:
+        sb["act"][:] = hb["act"]
+
+    def pipelined(nsteps):
+        tickets = []
+        for i in range(nsteps):
+            if len(tickets) == depth:
+                env.wait(tickets.pop(0))                # the oldest step's obs / reward / flags are in host memory
+            sb = sets[i % depth]
+            tickets.append(env.step_host_async(sb["act"], sb))
+        env.wait(0)
+
+    pipelined(8)
+    barrier()
+    t0 = time.perf_counter()
+    pipelined(e2e_steps)
+    e2e_async_dt = time.perf_counter() - t0
+    t = torch.tensor([e2e_async_dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_async_value = world * N * e2e_steps / float(t.item())
     # the same call with ordinary (pageable) numpy arrays, as a drop-in caller would pass them
     acts_pageable = np.array(hb["act"])
     for _ in range(3):
@@ -425,29 +459,49 @@ def main():
             e2.close()
             del e2, ob
 
-    # ---- the other BASELINE.json configurations, per GPU (parity-tested in tests/; shown for scale)
+    # ---- the other BASELINE.json configurations (parity-tested in tests/): configs[2] per GPU, and configs[4] /
+    # ---- SURVEY.md 8(d) c5 as written: house map, 4096 agents per GPU (32,768 over 8), start / goal from the
+    # ---- GoalSpawnSampler tables, beam sweep B in {10, 12, 18, 24, 36}; run on every rank, max over ranks
     other = []
-    if not args.no_sweep and world == 1:
-        for label, mp, n_c, beams in (("configs[2] stage_2 16384 agents", "stage_2", 16384, 10),
-                                      ("configs[4] house 4096 agents/GPU 10 beams", "house", 4096, 10),
-                                      ("configs[4] house 4096 agents/GPU 36 beams", "house", 4096, 36)):
-            e3 = VecEnv(n_c, map=mp, device=local, seed=0, num_beams=beams)
+    c5 = []
+    if not args.no_sweep:
+        sweep_cfgs = [("configs[2] stage_2 16384 agents/GPU", "stage_2", 16384, 10, False)] if world == 1 else []
+        sweep_cfgs += [(f"configs[4] house 4096 agents/GPU {b} beams, table start/goal", "house", 4096, b, True)
+                       for b in (10, 12, 18, 24, 36)]
+        for label, mp, n_c, beams, tables in sweep_cfgs:
+            e3 = VecEnv(n_c, map=mp, device=local, seed=0, num_beams=beams, agent_id_offset=rank * n_c,
+                        use_external_sampler=("small_house" if tables else False))
             e3.reset()
             ob = e3.rollout_scripted(H, 0)
-            for _ in range(3):                      # let the robots leave the common spawn pose
+            for _ in range(3):                      # let the robots spread out
                 e3.rollout_scripted(H, 0, out=ob)
-            torch.cuda.synchronize()
+            barrier()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             for _ in range(3):
                 e3.rollout_scripted(H, 0, out=ob)
             b.record()
             torch.cuda.synchronize()
-            s3 = a.elapsed_time(b) * 1e-3 / (3 * H)
+            t3 = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+            s3 = float(t3.item()) * 1e-3 / (3 * H)
             nseg = int(e3.segments.shape[0])
-            other.append({"config": label, "agents": n_c, "beams": beams, "walls": nseg, "lanes_per_agent": e3.lanes_per_agent,
-                          "us_per_env_step_batch": s3 * 1e6, "env_steps_per_s": n_c / s3,
-                          "nominal_ray_wall_tests_per_s": n_c * beams * nseg / s3})
+            row = {"config": label, "agents_per_gpu": n_c, "agents_total": n_c * world, "beams": beams, "walls": nseg,
+                   "lanes_per_agent": e3.lanes_per_agent, "us_per_env_step_batch": s3 * 1e6,
+                   "env_steps_per_s": world * n_c / s3, "nominal_ray_wall_tests_per_s": world * n_c * beams * nseg / s3}
+            if tables:
+                gbs = BYTES_SURVEY * n_c / s3 / 1e9                       # per GPU
+                row["hbm"] = {"bytes_per_env_step": BYTES_SURVEY, "achieved_GBps_per_gpu": gbs, "frac": gbs / peak_gbs}
+                fl = NCU_FP32_FLOP_PER_ENV_STEP.get(("house", beams))
+                row["fp32"] = None if fl is None else {
+                    "flop_per_env_step": fl, "achieved_TFLOPs_per_gpu": fl * n_c / s3 / 1e12,
+                    "peak_TFLOPs": FP32_PEAK_TFLOPS, "frac": fl * n_c / s3 / 1e12 / FP32_PEAK_TFLOPS,
+                    "source": "thread-level FADD + FMUL + 2 FFMA counts of one launch under ncu (profiles/README.md), "
+                              "divided by its env-steps"}
+                c5.append(row)
+            else:
+                other.append(row)
             e3.close()
             del e3, ob
 
@@ -478,11 +532,15 @@ def main():
                 "api": "navsim_step_host via VecEnv.step_host: host actions in, host obs/reward/flags out, every env step; "
                        "caller buffers page-locked (VecEnv.alloc_host_buffers): the kernel reads the actions and writes the "
                        "observations in host memory over PCIe (zero-copy), reward/flags via a mapped block",
+                "async_pipelined_value": e2e_async_value,
+                "async_api": "navsim_step_host_async / navsim_wait (VecEnv.step_host_async / wait): pipeline of depth 4, "
+                             "observations through the copy engine under the next step's kernel, four host buffer sets",
                 "pageable_buffers_value": e2e_pageable},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "roofline_sweep": sweep,
         "other_configs": other,
+        "c5_house_beam_sweep": c5,
         "training": training,
         "cpu_baseline": cpu_baseline,
     }

@@ -166,6 +166,19 @@ int navsim_reset_host(navsim_t* h, const uint8_t* mask_host, float* obs_host);
 int navsim_step_host(navsim_t* h, const float* act_host, float* obs_host, float* rew_host,
                      uint8_t* done_host, uint8_t* arrive_host, uint8_t* trunc_host);
 
+/* Asynchronous form of navsim_step_host, a pipeline: the call enqueues one Env.step with HOST buffers and returns
+ * a ticket (1, 2, 3, ..; negative = error) at once; navsim_wait(h, ticket) blocks until that step's outputs are in
+ * the caller's buffers (ticket 0: every step issued so far).  At most NAVSIM_ASYNC_DEPTH steps may be in flight, so
+ * a caller cycles through that many sets of output buffers and prepares later steps while earlier observations
+ * cross PCIe.  All buffers must be page-locked.  Stream rules for ALL entry points: device entry points run on the
+ * caller's stream, host entry points on streams the handle owns; the library orders the two kinds against each other
+ * (a host call first waits for the last caller stream used, a device call waits for asynchronous host steps still
+ * in flight), so they can be mixed on one handle without explicit synchronisation. */
+#define NAVSIM_ASYNC_DEPTH 4
+int64_t navsim_step_host_async(navsim_t* h, const float* act_host, float* obs_host, float* rew_host,
+                               uint8_t* done_host, uint8_t* arrive_host, uint8_t* trunc_host);
+int navsim_wait(navsim_t* h, int64_t ticket);
+
 /* The one-robot calling convention of the reference, Env.step(action, past_action) /
  * Env.reset() followed by reads of env.position / env.goal_position / env.past_distance
  * (environment_new.py:272,299-300; ppo.py:535, main.py:202), in ONE launch and one

@@ -890,6 +890,17 @@ struct navsim {
   float *h_past = nullptr, *h_past_dev = nullptr;        // [N,2]
   double *h_pose = nullptr, *h_pose_dev = nullptr;       // [N,6]
   double* reset_pose_out = nullptr;                      // set around a navsim_reset_host_ex launch
+  // Mixing device entry points (caller's stream) with host entry points (own_stream): the host side waits for the
+  // last caller stream before it touches the agent state; host calls end synchronised (or, for the asynchronous
+  // form, leave `async_tail` for the next device call to wait on).
+  cudaStream_t last_dev_stream = nullptr;
+  bool dev_dirty = false;
+  // navsim_step_host_async: pipeline of up to kAsyncDepth steps (kernel on own_stream, observation DMA on copy_stream)
+  cudaStream_t copy_stream = nullptr;
+  float* d_obs2[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_kernel[4] = {nullptr, nullptr, nullptr, nullptr}, ev_copy[4] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t async_issued = 0, async_waited = 0;
+  std::vector<std::pair<const void*, void*>> alias_cache;   // host pointer -> device alias (null: not page-locked)
   // GoalSpawnSampler tables (navsim_set_sampler) and the host copy of the packed map they are cast against
   double *d_starts = nullptr, *d_goals = nullptr;
   float* d_start_scans = nullptr;
@@ -969,6 +980,26 @@ int check_ready(const navsim* h) {
   if (!h->d_map) return fail(NAVSIM_EINVAL, "navsim_set_map has not been called");
   if (h->cfg.sampler_mode == 1 && h->c.n_starts == 0)
     return fail(NAVSIM_EINVAL, "sampler_mode = 1 but navsim_set_sampler has not been called");
+  return NAVSIM_OK;
+}
+
+// Device entry point on the caller's stream: remember the stream (the host entry points wait for it) and wait for
+// asynchronous host steps still in flight on the handle's own streams.
+int begin_device_call(navsim* h, cudaStream_t s) {
+  if (h->async_issued > h->async_waited) {
+    const int k = (int)((h->async_issued - 1) & 3);
+    CUDA_TRY(cudaStreamWaitEvent(s, h->ev_kernel[k], 0));    // the agent state is final once the last kernel ran
+  }
+  h->last_dev_stream = s;
+  h->dev_dirty = true;
+  return NAVSIM_OK;
+}
+// Host entry point: device work enqueued on the caller's stream since the last host call must have finished.
+int begin_host_call(navsim* h) {
+  if (h->dev_dirty) {
+    CUDA_TRY(cudaStreamSynchronize(h->last_dev_stream));
+    h->dev_dirty = false;
+  }
   return NAVSIM_OK;
 }
 
@@ -1213,6 +1244,13 @@ int navsim_destroy(navsim_t* h) {
   if (h->d_obs) cudaFree(h->d_obs);
   if (h->d_rew) cudaFree(h->d_rew);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (int k = 1; k < 4; ++k)
+    if (h->d_obs2[k]) cudaFree(h->d_obs2[k]);
+  for (int k = 0; k < 4; ++k) {
+    if (h->ev_kernel[k]) cudaEventDestroy(h->ev_kernel[k]);
+    if (h->ev_copy[k]) cudaEventDestroy(h->ev_copy[k]);
+  }
   delete h;
   return NAVSIM_OK;
 }
@@ -1344,6 +1382,8 @@ int navsim_set_sampler(navsim_t* h, const double* starts_host, int32_t n_starts,
 
 int navsim_reset(navsim_t* h, const uint8_t* mask_dev, float* obs_dev, void* stream) {
   if (int rc = check_ready(h)) return rc;
+  if ((cudaStream_t)stream != h->own_stream)
+    if (int rc = begin_device_call(h, (cudaStream_t)stream)) return rc;
   navsim_reset_kernel<<<aux_grid_of(h), kBlock, aux_smem_bytes(h), (cudaStream_t)stream>>>(h->c, h->st, h->d_map, h->d_rt,
                                                                                          mask_dev, obs_dev, h->reset_pose_out);
   h->launches++;
@@ -1354,6 +1394,7 @@ int navsim_reset(navsim_t* h, const uint8_t* mask_dev, float* obs_dev, void* str
 int navsim_step(navsim_t* h, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev,
                 uint8_t* arrive_dev, uint8_t* trunc_dev, void* stream) {
   if (int rc = check_ready(h)) return rc;
+  if (int rc = begin_device_call(h, (cudaStream_t)stream)) return rc;
   if (!act_dev || !obs_dev || !rew_dev || !done_dev || !arrive_dev) return fail(NAVSIM_EINVAL, "null buffer");
   return launch_step(h, make_io(act_dev, obs_dev, rew_dev, done_dev, arrive_dev, trunc_dev, 0, 0), (cudaStream_t)stream,
                      false, 0, 1);
@@ -1361,6 +1402,7 @@ int navsim_step(navsim_t* h, const float* act_dev, float* obs_dev, float* rew_de
 
 int navsim_step_ex(navsim_t* h, const float* act_dev, const navsim_step_out* out, void* stream) {
   if (int rc = check_ready(h)) return rc;
+  if (int rc = begin_device_call(h, (cudaStream_t)stream)) return rc;
   if (!act_dev || !out || !out->obs || !out->rew || !out->done || !out->arrive) return fail(NAVSIM_EINVAL, "null buffer");
   if ((out->ep_return == nullptr) != (out->ep_path == nullptr))
     return fail(NAVSIM_EINVAL, "ep_return and ep_path must be given together");
@@ -1374,6 +1416,7 @@ int navsim_step_ex(navsim_t* h, const float* act_dev, const navsim_step_out* out
 int navsim_step_scripted(navsim_t* h, int32_t num_steps, uint64_t action_seed, float* obs_dev, float* rew_dev,
                          uint8_t* done_dev, uint8_t* arrive_dev, void* stream) {
   if (int rc = check_ready(h)) return rc;
+  if (int rc = begin_device_call(h, (cudaStream_t)stream)) return rc;
   if (!obs_dev || !rew_dev || !done_dev || !arrive_dev) return fail(NAVSIM_EINVAL, "null buffer");
   return launch_step(h, make_io(nullptr, obs_dev, rew_dev, done_dev, arrive_dev, nullptr, 0, 0), (cudaStream_t)stream, true,
                      action_seed, num_steps);
@@ -1382,6 +1425,7 @@ int navsim_step_scripted(navsim_t* h, int32_t num_steps, uint64_t action_seed, f
 int navsim_rollout_scripted(navsim_t* h, int32_t num_steps, uint64_t action_seed, float* obs_dev, float* rew_dev,
                             uint8_t* done_dev, uint8_t* arrive_dev, uint8_t* trunc_dev, void* stream) {
   if (int rc = check_ready(h)) return rc;
+  if (int rc = begin_device_call(h, (cudaStream_t)stream)) return rc;
   if (!obs_dev || !rew_dev || !done_dev || !arrive_dev) return fail(NAVSIM_EINVAL, "null buffer");
   const long long N = h->c.N;
   return launch_step(h, make_io(nullptr, obs_dev, rew_dev, done_dev, arrive_dev, trunc_dev, N * NAVSIM_OBS_DIM, N),
@@ -1390,6 +1434,8 @@ int navsim_rollout_scripted(navsim_t* h, int32_t num_steps, uint64_t action_seed
 
 int navsim_reset_host(navsim_t* h, const uint8_t* mask_host, float* obs_host) {
   if (int rc = check_ready(h)) return rc;
+  if (int rc = begin_host_call(h)) return rc;
+  if (int rc = navsim_wait(h, 0)) return rc;
   if (!obs_host) return fail(NAVSIM_EINVAL, "null buffer");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   const size_t N = (size_t)h->c.N;
@@ -1429,6 +1475,8 @@ int navsim_reset_host_ex(navsim_t* h, const uint8_t* mask_host, float* obs_host,
 int navsim_step_host_ex(navsim_t* h, const float* act_host, const float* past_act_host, float* obs_host, float* rew_host,
                         uint8_t* done_host, uint8_t* arrive_host, uint8_t* trunc_host, double* pose_host) {
   if (int rc = check_ready(h)) return rc;
+  if (int rc = begin_host_call(h)) return rc;
+  if (int rc = navsim_wait(h, 0)) return rc;
   if (!act_host || !obs_host || !rew_host || !done_host || !arrive_host) return fail(NAVSIM_EINVAL, "null buffer");
   if (!h->h_rew_dev || !h->h_past_dev || !h->h_pose_dev)
     return fail(NAVSIM_ECUDA, "mapped host memory is not available on this device");
@@ -1462,6 +1510,8 @@ int navsim_step_host_ex(navsim_t* h, const float* act_host, const float* past_ac
 int navsim_step_host(navsim_t* h, const float* act_host, float* obs_host, float* rew_host, uint8_t* done_host,
                      uint8_t* arrive_host, uint8_t* trunc_host) {
   if (int rc = check_ready(h)) return rc;
+  if (int rc = begin_host_call(h)) return rc;
+  if (int rc = navsim_wait(h, 0)) return rc;
   if (!act_host || !obs_host || !rew_host || !done_host || !arrive_host) return fail(NAVSIM_EINVAL, "null buffer");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   const size_t N = (size_t)h->c.N;
@@ -1500,6 +1550,69 @@ int navsim_step_host(navsim_t* h, const float* act_host, float* obs_host, float*
   memcpy(done_host, h->h_flags, N);
   memcpy(arrive_host, h->h_flags + N, N);
   if (trunc_host) memcpy(trunc_host, h->h_flags + 2 * N, N);
+  return NAVSIM_OK;
+}
+
+int64_t navsim_step_host_async(navsim_t* h, const float* act_host, float* obs_host, float* rew_host, uint8_t* done_host,
+                               uint8_t* arrive_host, uint8_t* trunc_host) {
+  if (int rc = check_ready(h)) return rc;
+  if (!act_host || !obs_host || !rew_host || !done_host || !arrive_host) return fail(NAVSIM_EINVAL, "null buffer");
+  if (h->async_issued - h->async_waited >= NAVSIM_ASYNC_DEPTH)
+    return fail(NAVSIM_EINVAL, "NAVSIM_ASYNC_DEPTH asynchronous steps are already in flight: navsim_wait for the oldest first");
+  if (int rc = begin_host_call(h)) return rc;
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const size_t N = (size_t)h->c.N;
+  if (!h->copy_stream) {   // first use: second stream, second device observation buffer, events
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    h->d_obs2[0] = h->d_obs;
+    for (int k = 1; k < NAVSIM_ASYNC_DEPTH; ++k) CUDA_TRY(cudaMalloc(&h->d_obs2[k], N * NAVSIM_OBS_DIM * sizeof(float)));
+    for (int k = 0; k < NAVSIM_ASYNC_DEPTH; ++k) {
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_kernel[k], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_copy[k], cudaEventDisableTiming));
+    }
+  }
+  // every buffer must be page-locked: the kernel reads the actions and writes reward / flags through their device
+  // aliases (7 bytes per agent over PCIe), the observations take the copy engine so that the next step's kernel
+  // overlaps their transfer
+  auto alias = [h](const void* p) -> void* {        // one driver query per new pointer (a loop reuses its buffers)
+    for (const auto& kv : h->alias_cache)
+      if (kv.first == p) return kv.second;
+    cudaPointerAttributes at;
+    void* a = nullptr;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) cudaGetLastError();
+    else if (at.type == cudaMemoryTypeHost) a = at.devicePointer;
+    if (h->alias_cache.size() >= 32) h->alias_cache.clear();
+    h->alias_cache.emplace_back(p, a);
+    return a;
+  };
+  const float* act_dev = static_cast<const float*>(alias(act_host));
+  float* rew_dev = static_cast<float*>(alias(rew_host));
+  uint8_t* done_dev = static_cast<uint8_t*>(alias(done_host));
+  uint8_t* arrive_dev = static_cast<uint8_t*>(alias(arrive_host));
+  uint8_t* trunc_dev = trunc_host ? static_cast<uint8_t*>(alias(trunc_host)) : nullptr;
+  if (!act_dev || !rew_dev || !done_dev || !arrive_dev || (trunc_host && !trunc_dev) || !alias(obs_host))
+    return fail(NAVSIM_EINVAL, "navsim_step_host_async needs page-locked buffers (cudaHostAlloc / cudaHostRegister / pin_memory)");
+  const int k = (int)(h->async_issued & (NAVSIM_ASYNC_DEPTH - 1));
+  cudaStream_t s = h->own_stream;
+  if (h->async_issued >= NAVSIM_ASYNC_DEPTH) CUDA_TRY(cudaStreamWaitEvent(s, h->ev_copy[k], 0));   // the copy of step t - depth has left d_obs2[k]
+  if (int rc = launch_step(h, make_io(act_dev, h->d_obs2[k], rew_dev, done_dev, arrive_dev, trunc_dev, 0, 0), s, false, 0, 1))
+    return rc;
+  CUDA_TRY(cudaEventRecord(h->ev_kernel[k], s));
+  CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_kernel[k], 0));
+  CUDA_TRY(cudaMemcpyAsync(obs_host, h->d_obs2[k], N * NAVSIM_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+  CUDA_TRY(cudaEventRecord(h->ev_copy[k], h->copy_stream));
+  return ++h->async_issued;
+}
+
+int navsim_wait(navsim_t* h, int64_t ticket) {
+  if (!h) return fail(NAVSIM_EINVAL, "null handle");
+  if (ticket < 0 || ticket > h->async_issued) return fail(NAVSIM_EINVAL, "unknown ticket");
+  const int64_t upto = ticket == 0 ? h->async_issued : ticket;
+  while (h->async_waited < upto) {
+    const int k = (int)(h->async_waited & (NAVSIM_ASYNC_DEPTH - 1));
+    CUDA_TRY(cudaEventSynchronize(h->ev_copy[k]));     // kernel done (reward / flags written) and observations copied
+    h->async_waited++;
+  }
   return NAVSIM_OK;
 }
 

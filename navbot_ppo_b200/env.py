@@ -96,6 +96,7 @@ class VecEnv:
         self.trunc = torch.zeros(n, dtype=torch.uint8, device=dev)
         self._host_ptr_key, self._host_ptrs, self._host_keepalive = None, None, None
         self._step_host_fn = L.navsim_step_host
+        self._step_async_fn, self._async_ptrs, self._async_keepalive = L.navsim_step_host_async, {}, None
 
     def set_sampler(self, starts, goals):
         """GoalSpawnSampler tables: starts [n, 3] (x, y, yaw), goals [n, 2] (navsim_set_sampler)."""
@@ -206,6 +207,28 @@ class VecEnv:
         if rc:
             _capi.check(rc)
         return obs, rew, done, arrive, trunc
+
+    def step_host_async(self, actions: np.ndarray, out: dict) -> int:
+        """Enqueue Env.step with page-locked HOST buffers (alloc_host_buffers()) and return a ticket at once;
+        wait(ticket) blocks until `out` holds that step's results.  Up to four steps may be in flight: cycle through
+        as many buffer sets and prepare later steps while earlier observations cross PCIe (navsim_step_host_async)."""
+        key = (id(actions), id(out))
+        ptrs = self._async_ptrs.get(key)
+        if ptrs is None:
+            ptrs = tuple(int(x.__array_interface__["data"][0]) for x in (actions, out["obs"], out["rew"], out["done"],
+                                                                          out["arrive"], out["trunc"]))
+            if len(self._async_ptrs) > 8:
+                self._async_ptrs.clear()
+            self._async_ptrs[key] = ptrs
+            self._async_keepalive = (actions, out)
+        t = self._step_async_fn(self._h, *ptrs)
+        if t < 0:
+            _capi.check(int(t))
+        return int(t)
+
+    def wait(self, ticket: int = 0) -> None:
+        """Block until the asynchronous step `ticket` (0: every step issued so far) has delivered its outputs."""
+        _capi.check(_capi.lib().navsim_wait(self._h, int(ticket)))
 
     # -- state inspection / injection ------------------------------------------------------
     def get_state(self, field: int) -> np.ndarray:

@@ -517,3 +517,45 @@ def test_open_world_single_wall_and_oversized_map():
     big = maps.synthetic_map(8000, seed=1, extent=60.0)     # 32,000 walls = 1 MB of wall records
     with pytest.raises(_capi.NavError):
         VecEnv(16, map=big)
+
+
+def test_async_host_steps_equal_blocking_host_steps_and_mix_with_device_calls():
+    """navsim_step_host_async / navsim_wait (pipeline of depth 4, observations through the copy engine) deliver the
+    same results as the blocking navsim_step_host, refuse a step when the pipeline is full, and can be mixed with device
+    entry points on the same handle without explicit synchronisation (the library orders its own streams against
+    the caller's)."""
+    n = 3000
+    a, b = VecEnv(n, map="stage_2", seed=4, max_episode_steps=30), VecEnv(n, map="stage_2", seed=4, max_episode_steps=30)
+    depth = 4                                                        # NAVSIM_ASYNC_DEPTH
+    sets = [a.alloc_host_buffers() for _ in range(depth)]
+    ref = b.alloc_host_buffers()
+    np.testing.assert_array_equal(a.reset_host(), b.reset_host())
+    tickets = []
+    for t in range(40):
+        hb = sets[t % depth]
+        if len(tickets) == depth:
+            with pytest.raises(_capi.NavError):
+                a.step_host_async(hb["act"], hb)                     # the pipeline is full
+            tk, t_old = tickets.pop(0)
+            a.wait(tk)
+            ref["act"][:] = binding.scripted_actions(9, 0, t_old, n)
+            b.step_host(ref["act"], out=ref)
+            for key in ("obs", "rew", "done", "arrive", "trunc"):
+                np.testing.assert_array_equal(sets[t_old % depth][key], ref[key], err_msg=f"{key} t={t_old}")
+        hb["act"][:] = binding.scripted_actions(9, 0, t, n)
+        tickets.append((a.step_host_async(hb["act"], hb), t))
+    a.wait(0)
+    for tk, t_old in tickets:
+        ref["act"][:] = binding.scripted_actions(9, 0, t_old, n)
+        b.step_host(ref["act"], out=ref)
+        np.testing.assert_array_equal(sets[t_old % depth]["obs"], ref["obs"])
+    # device call right after an asynchronous host step, host call right after a device call: no explicit sync
+    hb = sets[0]
+    hb["act"][:] = 0.5
+    a.step_host_async(hb["act"], hb)
+    obs_d, *_ = a.step(torch.full((n, 2), 0.5, device="cuda"))
+    o_h, *_ = a.step_host(np.full((n, 2), 0.5, np.float32))
+    b.step_host(np.full((n, 2), 0.5, np.float32)); o2 = b.step_host(np.full((n, 2), 0.5, np.float32))[0].copy()
+    np.testing.assert_array_equal(obs_d.cpu().numpy(), o2)
+    np.testing.assert_array_equal(o_h, b.step_host(np.full((n, 2), 0.5, np.float32))[0])
+    np.testing.assert_array_equal(a.get_state(_capi.F_X), b.get_state(_capi.F_X))
