@@ -201,7 +201,7 @@ __device__ __forceinline__ uint64_t words_desc(uint32_t lo, uint32_t sbo) {
 // (A = weights, B = activations) then adds (activation lo x weight hi) first, like the product it mirrors.
 template <int PASSES, int KSTEPS, bool SWAP = false>
 __device__ __forceinline__ void gemm(uint32_t tmem_d, const Opnd& A, const Opnd& B, uint32_t idesc, bool accumulate) {
-  if (elect_one()) {
+  {   // the caller is the one elected lane of the issuing warp
     uint32_t acc = accumulate ? 1u : 0u;
     const uint32_t a0 = A.start | (A.lbo << 16), b0 = B.start | (B.lbo << 16);
 #pragma unroll
@@ -220,13 +220,12 @@ __device__ __forceinline__ void gemm(uint32_t tmem_d, const Opnd& A, const Opnd&
       tc::mma_bf16(tmem_d, ah, bh, idesc, acc); acc = 1u;
     }
   }
-  __syncwarp();
 }
 // D (+)= A B over K = 64 with A in tensor memory, as the epilogue warps leave it: per 32 k [16 packed hi
 // columns | 16 packed lo columns], 8 packed columns per instruction
 template <int PASSES>
 __device__ __forceinline__ void gemm_ts(uint32_t tmem_d, uint32_t tmem_a, const Opnd& B, uint32_t idesc, bool accumulate) {
-  if (elect_one()) {
+  {   // the caller is the one elected lane of the issuing warp
     uint32_t acc = accumulate ? 1u : 0u;
     const uint32_t b0 = B.start | (B.lbo << 16);
 #pragma unroll
@@ -240,13 +239,9 @@ __device__ __forceinline__ void gemm_ts(uint32_t tmem_d, uint32_t tmem_a, const 
       tc::mma_bf16_ts(tmem_d, ah, bh, idesc, acc); acc = 1u;
     }
   }
-  __syncwarp();
 }
-// tcgen05.commit by the lane that issues the MMAs
-__device__ __forceinline__ void commit(uint64_t* bar) {
-  if (elect_one()) tc::mma_commit(bar);
-  __syncwarp();
-}
+// tcgen05.commit by the lane that issued the MMAs (the caller is that lane)
+__device__ __forceinline__ void commit(uint64_t* bar) { tc::mma_commit(bar); }
 
 // 8 consecutive columns of one row -> one 16-byte granule of the hi tile (and of the lo tile)
 template <int PASSES>
@@ -745,43 +740,57 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
           tc::mbar_wait(bars + B_XREADY, px); px ^= 1;    // the pass's input tile (X or GU) is published
           tc::fence_after_sync();
           PT(0);
+          // Every step below has the same shape: the whole warp waits on the mbarriers the step depends on, then ONE
+          // elected lane issues all of the step's MMAs and commits back to back.
+          auto wait_bar = [&](uint64_t* bar, uint32_t& parity_bits, int bit) {
+            tc::mbar_wait(bar, (parity_bits >> bit) & 1);
+            parity_bits ^= 1u << bit;
+          };
           if (pass < 2) {
             // ============================================================== forward: half-chunks of 64 hidden units
             const uint32_t wp = wpart(IN);
             const uint32_t id_z = tc::make_idesc_bf16(128, HC, 0, 0), id_u = tc::make_idesc_bf16(128, IN, 0, 0);
             // Z of half-chunk h into ring slot h & 1: A = X (K-major), B = Wa (rows = hidden units, K-major), K = IN
-            auto issue_z = [&](int h) {
+            auto issue_z = [&](int h, int wslot) {
               const int s = h & 1;
-              PT(4);
-              tc::mbar_wait(bars + B_WFULL + wslot_p1, (pw >> wslot_p1) & 1); pw ^= 1u << wslot_p1;
-              tc::fence_after_sync();
-              PT(2);
-              const uint32_t w = aWF + wslot_p1 * WSLOT;
+              const uint32_t w = aWF + wslot * WSLOT;
               const Opnd Wk{w >> 4, wp >> 4, HC, 8, 2 * HC};
               if (blk) gemm<PASSES, 2>(tmem + TM_ZG + s * 128, Xk, Wk, id_z, false);
               else gemm<PASSES, 1>(tmem + TM_ZG + s * 128, Xk, Wk, id_z, false);
               PT(5);
               commit(bars + B_ZFULL + s);
-              wslot_p1 = next_slot(wslot_p1);
             };
-            issue_z(0);
-            issue_z(1);
+            const int w0 = wslot_p1, w1 = next_slot(w0);
+            PT(4);
+            wait_bar(bars + B_WFULL + w0, pw, w0);
+            wait_bar(bars + B_WFULL + w1, pw, w1);
+            tc::fence_after_sync();
+            PT(2);
+            if (elect_one()) { issue_z(0, w0); issue_z(1, w1); }
+            __syncwarp();
+            wslot_p1 = next_slot(w1);
 #pragma unroll 1
             for (int h = 0; h < NHC; ++h) {
               const int s = h & 1;
               PT(4);
-              tc::mbar_wait(bars + B_EFULL + s, (pe >> s) & 1); pe ^= 1u << s;   // H of half-chunk h sits packed in the slot
-              tc::fence_after_sync();
+              wait_bar(bars + B_EFULL + s, pe, s);                       // H of half-chunk h sits packed in the slot
               PT(1);
-              {   // U += H Wb^T: A = H (tensor memory), B = Wb (rows = output features, K-major)
+              if (h + 2 < NHC) wait_bar(bars + B_WFULL + wslot_p1, pw, wslot_p1);
+              tc::fence_after_sync();
+              PT(2);
+              if (elect_one()) {
+                // U += H Wb^T: A = H (tensor memory), B = Wb (rows = output features, K-major)
                 const uint32_t w = aWF + wslot_p2 * WSLOT;
                 const Opnd Wbk{(w + 2 * wp) >> 4, wp >> 4, (uint32_t)IN, 8, 2u * IN};
                 gemm_ts<PASSES>(tmem + TM_U, tmem + TM_ZG + s * 128, Wbk, id_u, h > 0);
                 PT(6);
                 commit(bars + B_WFREE + wslot_p2);
-                wslot_p2 = next_slot(wslot_p2);
+                if (h + 2 < NHC) issue_z(h + 2, wslot_p1);
+                else if (h == NHC - 1) commit(bars + B_ACC);              // everything issued so far: U is complete
               }
-              if (h + 2 < NHC) issue_z(h + 2);
+              __syncwarp();
+              wslot_p2 = next_slot(wslot_p2);
+              if (h + 2 < NHC) wslot_p1 = next_slot(wslot_p1);
             }
           } else {
             // ============================================================== backward: chunks of 128 hidden units x halves
@@ -793,12 +802,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
             // Z^T = Wa X^T and GH^T = Wb^T GU^T of unit u = (chunk u / 2, sample half u % 2) into ring slot u & 1
             auto issue_zt = [&](int u) {
               const int c = u >> 1, sh = u & 1, b = c & 1;
-              if (sh == 0) {
-                PT(4);
-                tc::mbar_wait(bars + B_CFULL + b, (pc_full >> b) & 1); pc_full ^= 1u << b;
-                tc::fence_after_sync();
-                PT(2);
-              }
               const uint32_t w = aWB + b * CSLOT;
               const Opnd Wa_k{w >> 4, cp >> 4, CH, 8, 2 * CH};                                // rows = hidden units = M
               const Opnd Wb_m{(w + 2 * cp) >> 4, cp >> 4, 8, (uint32_t)IN, 16};               // rows = K = output features
@@ -816,43 +819,50 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
               commit(bars + B_ZFULL + sh);
               if (!blk && sh == 1) commit(bars + B_CFREE + b);    // backward block 1 has no GX: last reader of the chunk
             };
-            issue_zt(0);
-            issue_zt(1);
+            PT(4);
+            wait_bar(bars + B_CFULL + 0, pc_full, 0);
+            tc::fence_after_sync();
+            PT(2);
+            if (elect_one()) { issue_zt(0); issue_zt(1); }
+            __syncwarp();
 #pragma unroll 1
             for (int u = 0; u < 2 * NCH; ++u) {
               const int c = u >> 1, sh = u & 1, b = c & 1;
               PT(4);
-              tc::mbar_wait(bars + B_EFULL + sh, (pe >> sh) & 1); pe ^= 1u << sh;   // H^T / GZ^T of unit u sit packed in the slot
-              tc::fence_after_sync();
+              wait_bar(bars + B_EFULL + sh, pe, sh);                     // H^T / GZ^T of unit u sit packed in the slot
               PT(1);
-              if (sh == 1 && blk) {   // GX += GZ Wa over the chunk's 128 hidden units: both operands MN-major (rows = K).
-                // First: the next chunk's epilogue waits for the GZ^T tile
-                const uint32_t w = aWB + b * CSLOT;
-                const Opnd Wa_m{w >> 4, cp >> 4, 8, CH, 16};
-                gemm<PASSES, 8>(tmem + TM_GX, GZTm, Wa_m, id_gx, c > 0);
-                PT(6);
-                commit(bars + B_GZFREE);
-                commit(bars + B_CFREE + b);
-              }
               if (sh == 0) {
-                PT(4);
-                tc::mbar_wait(bars + B_DWFREE + b, (pdfree >> b) & 1); pdfree ^= 1u << b;   // accumulator buffer b was flushed
-                tc::fence_after_sync();
+                wait_bar(bars + B_DWFREE + b, pdfree, b);                // accumulator buffer b was flushed
                 PT(3);
+                if (u + 2 < 2 * NCH) wait_bar(bars + B_CFULL + ((c + 1) & 1), pc_full, (c + 1) & 1);   // next chunk's weights
+                PT(2);
               }
-              {   // dWa += GZ^T [X | 1], dWbT += H^T GU over the unit's 64 samples: A in tensor memory, B MN-major
-                const Opnd Xs{(aX >> 4) + 64 * sh, SX_PART >> 4, 8, RG, 16};
-                const Opnd GUs{(aGU >> 4) + 64 * sh, SGU_PART >> 4, 8, RG, 16};
-                const uint32_t slot = tmem + TM_ZG + sh * 128, d = tmem + TM_DW + b * 80;
-                gemm_ts<PASSES>(d, slot + 64, Xs, id_dwa, sh > 0);
-                gemm_ts<PASSES>(d + 48, slot, GUs, id_dwb, sh > 0);
-                PT(7);
-                if (sh == 1) commit(bars + B_DWFULL + b);
+              tc::fence_after_sync();
+              if (elect_one()) {
+                if (sh == 1 && blk) {   // GX += GZ Wa over the chunk's 128 hidden units: both operands MN-major (rows = K).
+                  // First: the next chunk's epilogue waits for the GZ^T tile
+                  const uint32_t w = aWB + b * CSLOT;
+                  const Opnd Wa_m{w >> 4, cp >> 4, 8, CH, 16};
+                  gemm<PASSES, 8>(tmem + TM_GX, GZTm, Wa_m, id_gx, c > 0);
+                  PT(6);
+                  commit(bars + B_GZFREE);
+                  commit(bars + B_CFREE + b);
+                }
+                {   // dWa += GZ^T [X | 1], dWbT += H^T GU over the unit's 64 samples: A in tensor memory, B MN-major
+                  const Opnd Xs{(aX >> 4) + 64 * sh, SX_PART >> 4, 8, RG, 16};
+                  const Opnd GUs{(aGU >> 4) + 64 * sh, SGU_PART >> 4, 8, RG, 16};
+                  const uint32_t slot = tmem + TM_ZG + sh * 128, d = tmem + TM_DW + b * 80;
+                  gemm_ts<PASSES>(d, slot + 64, Xs, id_dwa, sh > 0);
+                  gemm_ts<PASSES>(d + 48, slot, GUs, id_dwb, sh > 0);
+                  PT(7);
+                  if (sh == 1) commit(bars + B_DWFULL + b);
+                }
+                if (u + 2 < 2 * NCH) issue_zt(u + 2);
+                else if (u == 2 * NCH - 1) commit(bars + B_ACC);          // everything issued so far: GX / the tile is complete
               }
-              if (u + 2 < 2 * NCH) issue_zt(u + 2);
+              __syncwarp();
             }
           }
-          commit(bars + B_ACC);                   // everything issued so far: U / GX / the tile is complete
         }
       }
       PT(4);
