@@ -13,13 +13,16 @@
 //               sample row each (block outputs, heads, losses)
 //   warps 8-11  weight-gradient flush: TMEM (lane = hidden unit) -> red.global.add into the CTA's
 //               partial-gradient row
-//   warp 12     issues every tcgen05.mma (converged warp, one elected lane)
-//   warp 13     one thread streams pre-tiled weights through TMA rings
+//   warp 12     issues the tcgen05.mma that FILL the TMEM ring (Z; Z^T / GH^T) — converged warp, one elected lane
+//   warp 14     issues the tcgen05.mma that CONSUME what the epilogue packed (U; dWa / dWb, GX): two issuers
+//               because one thread's waits, descriptor moves and commits were the longest chain of the tile
+//   warp 13     one thread streams pre-tiled weights through one TMA ring of 7 x 16 KB slots
 //
-// Forward (per block, half-chunks of 64 hidden units, 2-slot TMEM ring):
+// Forward (per block, half-chunks of 64 hidden units, 4-slot TMEM ring of 64 columns):
 //     Z = X Wa^T  [128 samples x 64]  (operands in shared memory)
 //     H = lrelu(Z + ba) -> packed over Z;   U += H Wb^T  (A = H in tensor memory)
-// Backward (per block, chunks of 128 hidden units x halves of 64 samples, TRANSPOSED: lane = hidden unit):
+// Backward (per block, chunks of 128 hidden units x halves of 64 samples, TRANSPOSED: lane = hidden unit; 2-slot
+// TMEM ring of 128 columns):
 //     Z^T = Wa X^T, GH^T = Wb^T GU^T  [128 hidden x 64 samples]
 //     H^T = lrelu(.), GZ^T = GH^T * lrelu'(.) -> packed over Z^T / GH^T
 //     dWa += GZ^T [X | 1],  dWb^T += H^T GU   (A in tensor memory, K = the 64 samples; double-buffered
@@ -115,25 +118,25 @@ constexpr uint32_t SGZ_PART = (128 / 8) * ROWG;             // 32 KB: GZ^T of on
 constexpr uint32_t OFF_SX = 0;
 constexpr uint32_t OFF_SGU = OFF_SX + 2 * SX_PART;          // 24 KB
 constexpr uint32_t OFF_SGZT = OFF_SGU + 2 * SGU_PART;       // 40 KB
-constexpr uint32_t WSLOT = wblob(X1);                       // 16 KB: one forward weight half-chunk
-constexpr int NWSLOT = 3;
-constexpr uint32_t OFF_WF = OFF_SGZT + 2 * SGZ_PART;        // 104 KB: forward ring
-constexpr uint32_t CSLOT = cblob(X1);                       // 32 KB: one backward weight chunk
-constexpr int NCSLOT = 2;
-constexpr uint32_t OFF_WB = OFF_WF + NWSLOT * WSLOT;        // 152 KB: backward ring
-constexpr uint32_t OFF_BIAS = OFF_WB + NCSLOT * CSLOT;      // 216 KB: fc1 biases of both blocks, 2 x 512 floats
+// One weight ring for both directions: 7 slots of 16 KB.  A forward half-chunk blob takes one slot; a backward
+// chunk blob takes two ([Wa hi | Wa lo] and [Wb hi | Wb lo]), so every pass consumes exactly 8 slots and the
+// producer runs up to 7 slots (5 forward steps, 3 backward chunks) ahead of the products.
+constexpr uint32_t WSLOT = wblob(X1);                       // 16 KB
+constexpr int NWSLOT = 7;
+constexpr uint32_t OFF_WF = OFF_SGZT + 2 * SGZ_PART;        // 104 KB: the ring
+constexpr uint32_t OFF_BIAS = OFF_WF + NWSLOT * WSLOT;      // 216 KB: fc1 biases of both blocks, 2 x 512 floats
 constexpr uint32_t OFF_RED = OFF_BIAS + 2 * HID * 4;        // head / bias-b gradient partials [4 warps][128] floats
 constexpr uint32_t OFF_PAR = OFF_RED + 4 * 128 * 4;         // fc2 biases and head weights, 128 floats
 constexpr int P_B1B = 0, P_B2B = OBS, P_HEAD = OBS + X1;    // offsets inside that block
 constexpr uint32_t OFF_BAR = OFF_PAR + 128 * 4;             // mbarriers, tmem base
-constexpr uint32_t WS_SMEM_BYTES = OFF_BAR + 256;           // 228,096 B of the 232,448 B a CTA may have
+constexpr uint32_t WS_SMEM_BYTES = OFF_BAR + 384;           // 228,224 B of the 232,448 B a CTA may have
 
 // mbarrier indices
-enum { B_ZFULL = 0, B_EFULL = 2, B_WFULL = 4, B_WFREE = 7, B_CFULL = 10, B_CFREE = 12, B_DWFULL = 14, B_DWFREE = 16,
-       B_GZFREE = 18, B_ACC = 19, B_XREADY = 20, B_COUNT = 21 };
+enum { B_ZFULL = 0, B_EFULL = 4, B_SFREE = 8, B_WFULL = 12, B_WFREE = 19, B_DWFULL = 26, B_DWFREE = 28,
+       B_GZFREE = 30, B_ACC = 31, B_XREADY = 32, B_COUNT = 33 };
 
-// TMEM columns: ring of two 128-column slots (forward: Z in the first 64; backward: Z^T | GH^T), two
-// weight-gradient accumulator buffers (dWa 48 | dWb 32 columns each), U and GX
+// TMEM columns: 256 columns of product ring (forward: four 64-column slots of Z; backward: two 128-column slots
+// of Z^T | GH^T), two weight-gradient accumulator buffers (dWa 48 | dWb 32 columns each), U and GX
 constexpr uint32_t TM_ZG = 0;
 constexpr uint32_t TM_DW = 256;      // buffer b at + 80 b: dWa at + 0, dWb at + 48
 constexpr uint32_t TM_U = 416;       // 32 columns
@@ -141,7 +144,7 @@ constexpr uint32_t TM_GX = 448;      // 32 columns
 constexpr uint32_t TM_COLS = 512;
 
 constexpr int WS_THREADS = 512;
-constexpr int W_FLUSH0 = 8, W_MMA = 12, W_TMA = 13;
+constexpr int W_FLUSH0 = 8, W_MMA = 12, W_TMA = 13, W_MMA2 = 14;
 
 struct WsGradArgs {
   GradArgs g;
@@ -332,11 +335,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
   const int ntiles = (a.T + 127) / 128;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(bars + B_ZFULL + i, 1); tc::mbar_init(bars + B_EFULL + i, 8);
-      tc::mbar_init(bars + B_CFULL + i, 1); tc::mbar_init(bars + B_CFREE + i, 1);
-      tc::mbar_init(bars + B_DWFULL + i, 1); tc::mbar_init(bars + B_DWFREE + i, 4);
+    for (int i = 0; i < 4; ++i) {
+      tc::mbar_init(bars + B_ZFULL + i, 1); tc::mbar_init(bars + B_EFULL + i, 8); tc::mbar_init(bars + B_SFREE + i, 1);
     }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(bars + B_DWFULL + i, 1); tc::mbar_init(bars + B_DWFREE + i, 4); }
     for (int i = 0; i < NWSLOT; ++i) { tc::mbar_init(bars + B_WFULL + i, 1); tc::mbar_init(bars + B_WFREE + i, 1); }
     tc::mbar_init(bars + B_GZFREE, 1);
     tc::mbar_init(bars + B_ACC, 1);
@@ -431,12 +433,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
         // -------------------------------------------------------------- the 8 half-chunks of this pass
 #pragma unroll 1
         for (int h = 0; h < NHC; ++h) {
-          const int s = h & 1;
+          const int s = fwd ? (h & 3) : (h & 1);
           PT(5);
           tc::mbar_wait(bars + B_ZFULL + s, (pz >> s) & 1); pz ^= 1u << s;    // Z (and GH) of half-chunk h are in TMEM
           tc::fence_after_sync();
           PT(0);
-          const uint32_t tz = trow + TM_ZG + s * 128 + ch * 32;
+          const uint32_t tz = trow + TM_ZG + s * (fwd ? 64 : 128) + ch * 32;
           if (fwd) {
             // half-chunk h of 64 hidden units; lane = sample row.  H = lrelu(Z + ba), written back over the
             // columns this warp just read as the A operand of U += H Wb^T: [hi: 16 packed columns | lo: 16]
@@ -646,7 +648,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
     // thread never waits for the old value (every address has ONE writer, in tile order -> the sum is the same
     // sequence of IEEE additions as a load-add-store; a load-add-store flush was tried and is slower: its five
     // dependent round trips per chunk take 5.5 k cycles against 2 k for the reds; pausing between the reds to leave
-    // the load/store unit to the epilogue warps changes nothing)
+    // the load/store unit to the epilogue warps changes nothing, nor does a nanosleep back-off in this role's waits)
     auto accum16 = [&](float* dst, uint32_t taddr) {
       float v[16];
       tc::tmem_ld16(taddr, v);
@@ -691,44 +693,131 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
     reg_dec<88>();
     if (warp == W_TMA && lane == 0) {
       // ==================================================================== weight producer
-      uint32_t pfree = 0x7, pcfree = 0x3;             // every ring slot starts free
+      uint32_t pfree = (1u << NWSLOT) - 1;            // every ring slot starts free
       int slot = 0;
+      auto load = [&](const unsigned char* src, uint32_t bytes) {
+        tc::mbar_wait(bars + B_WFREE + slot, (pfree >> slot) & 1); pfree ^= 1u << slot;
+        tma_load(smem + OFF_WF + slot * WSLOT, src, bytes, bars + B_WFULL + slot);
+        slot = slot == NWSLOT - 1 ? 0 : slot + 1;
+      };
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
 #pragma unroll 1
         for (int pass = 0; pass < 4; ++pass) {
           const int blk = pass_block(pass);
-          if (pass < 2) {      // forward: half-chunk blobs through the 3-slot ring
+          if (pass < 2) {      // forward: one half-chunk blob per slot
             const uint32_t bytes = wblob(blk ? X1 : OBS);
 #pragma unroll 1
-            for (int h = 0; h < NHC; ++h) {
-              tc::mbar_wait(bars + B_WFREE + slot, (pfree >> slot) & 1); pfree ^= 1u << slot;
-              tma_load(smem + OFF_WF + slot * WSLOT, wblob_g + wblob_off(blk, h), bytes, bars + B_WFULL + slot);
-              slot = slot == NWSLOT - 1 ? 0 : slot + 1;
-            }
-          } else {             // backward: chunk blobs through the 2-slot ring
-            const uint32_t bytes = cblob(blk ? X1 : OBS);
+            for (int h = 0; h < NHC; ++h) load(wblob_g + wblob_off(blk, h), bytes);
+          } else {             // backward: a chunk blob as two slots, [Wa hi | Wa lo] then [Wb hi | Wb lo]
+            const uint32_t half = 2 * cpart(blk ? X1 : OBS);
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
-              const int b = c & 1;
-              tc::mbar_wait(bars + B_CFREE + b, (pcfree >> b) & 1); pcfree ^= 1u << b;
-              tma_load(smem + OFF_WB + b * CSLOT, wblob_g + cblob_off(blk, c), bytes, bars + B_CFULL + b);
+              load(wblob_g + cblob_off(blk, c), half);
+              load(wblob_g + cblob_off(blk, c) + half, half);
             }
           }
         }
       }
     } else if (warp == W_MMA) {
-      // ==================================================================== the MMA-issuing warp (converged; one elected lane issues)
-      const uint32_t aX = tc::smem_u32(sX), aGU = tc::smem_u32(sGU), aGZT = tc::smem_u32(sGZT),
-                     aWF = tc::smem_u32(smem + OFF_WF), aWB = tc::smem_u32(smem + OFF_WB);
-      // activation tiles: K-major (rows = samples are the M / N index) and MN-major (rows = samples are K)
+      // ==================================================================== MMA warp 1 (converged; one elected lane issues):
+      // the products that FILL the TMEM ring — Z (forward), Z^T / GH^T (backward) — as soon as their weights
+      // have landed and the slot's previous consumer product has completed
+      const uint32_t aX = tc::smem_u32(sX), aGU = tc::smem_u32(sGU), aWF = tc::smem_u32(smem + OFF_WF);
       constexpr uint32_t RG = ROWG >> 4;
-      const Opnd Xk{aX >> 4, SX_PART >> 4, RG, 8, 2 * RG};
-      const Opnd GZTm{aGZT >> 4, SGZ_PART >> 4, 8, RG, 16};   // GZ^T tile read as A = GZ: rows = K = hidden units
-      uint32_t pe = 0, pw = 0, pc_full = 0, pdfree = 0x3, px = 0;
-      int wslot_p1 = 0;       // forward ring slot of the next half-chunk whose Z is to be issued
-      int wslot_p2 = 0;       // forward ring slot of the next half-chunk whose U is to be issued
+      const Opnd Xk{aX >> 4, SX_PART >> 4, RG, 8, 2 * RG};   // K-major: rows = samples are the M / N index
+      uint32_t pw = 0, psf = 0, px = 0;
+      int wslot = 0;          // weight ring slot of the next load in sequence
       auto next_slot = [](int s) { return s == NWSLOT - 1 ? 0 : s + 1; };
-
+      auto wait_bar = [&](uint64_t* bar, uint32_t& parity_bits, int bit) {
+        tc::mbar_wait(bar, (parity_bits >> bit) & 1);
+        parity_bits ^= 1u << bit;
+      };
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+#pragma unroll 1
+        for (int pass = 0; pass < 4; ++pass) {
+          const int blk = pass_block(pass);
+          const int IN = blk ? X1 : OBS;
+          tc::mbar_wait(bars + B_XREADY, px); px ^= 1;    // the pass's input tile (X or GU) is published
+          if (pass < 2) {
+            // ============================================================== forward: half-chunks of 64 hidden units
+            const uint32_t wp = wpart(IN);
+            const uint32_t id_z = tc::make_idesc_bf16(128, HC, 0, 0);
+#pragma unroll 1
+            for (int h = 0; h < NHC; ++h) {
+              const int s = h & 3;
+              if (h >= 4) wait_bar(bars + B_SFREE + s, psf, s);           // U of half-chunk h - 4 has read the slot
+              wait_bar(bars + B_WFULL + wslot, pw, wslot);
+              tc::fence_after_sync();
+              if (elect_one()) {
+                // Z of half-chunk h into ring slot h & 3: A = X (K-major), B = Wa (rows = hidden units, K-major), K = IN
+                const uint32_t w = aWF + wslot * WSLOT;
+                const Opnd Wk{w >> 4, wp >> 4, HC, 8, 2 * HC};
+                if (blk) gemm<PASSES, 2>(tmem + TM_ZG + s * 64, Xk, Wk, id_z, false);
+                else gemm<PASSES, 1>(tmem + TM_ZG + s * 64, Xk, Wk, id_z, false);
+                commit(bars + B_ZFULL + s);
+              }
+              __syncwarp();
+              wslot = next_slot(wslot);
+            }
+          } else {
+            // ============================================================== backward: chunks of 128 hidden units x halves
+            // of 64 samples, transposed (D lanes = hidden units); the chunk's weights sit in ring slots sa
+            // ([Wa hi | Wa lo]) and sb ([Wb hi | Wb lo])
+            const uint32_t cp = cpart(IN);
+            const uint32_t id_zt = tc::make_idesc_bf16(128, 64, 0, 0), id_ght = tc::make_idesc_bf16(128, 64, 1, 0);
+#pragma unroll 1
+            for (int u = 0; u < 2 * NCH; ++u) {
+              const int sh = u & 1;
+              const int sa = sh ? (wslot >= 2 ? wslot - 2 : wslot + NWSLOT - 2) : wslot;
+              const int sb = next_slot(sa);
+              if (sh == 0) {
+                wait_bar(bars + B_WFULL + sa, pw, sa);
+                wait_bar(bars + B_WFULL + sb, pw, sb);
+                wslot = next_slot(sb);
+              }
+              if (u >= 2) wait_bar(bars + B_SFREE + sh, psf, sh);         // dW of unit u - 2 has read the slot
+              tc::fence_after_sync();
+              if (elect_one()) {
+                // Z^T = Wa X^T and GH^T = Wb^T GU^T of unit u = (chunk u / 2, sample half u % 2) into ring slot u & 1
+                const uint32_t wa = aWF + sa * WSLOT, wb = aWF + sb * WSLOT;
+                const Opnd Wa_k{wa >> 4, cp >> 4, CH, 8, 2 * CH};                               // rows = hidden units = M
+                const Opnd Wb_m{wb >> 4, cp >> 4, 8, (uint32_t)IN, 16};                         // rows = K = output features
+                const Opnd Xs{(aX >> 4) + 64 * sh, SX_PART >> 4, RG, 8, 2 * RG};                // the 64 sample rows = N
+                const Opnd GUs{(aGU >> 4) + 64 * sh, SGU_PART >> 4, RG, 8, 2 * RG};
+                const uint32_t d = tmem + TM_ZG + sh * 128;
+                if (blk) {
+                  gemm<PASSES, 2, true>(d, Wa_k, Xs, id_zt, false);
+                  gemm<PASSES, 2, true>(d + 64, Wb_m, GUs, id_ght, false);
+                } else {
+                  gemm<PASSES, 1, true>(d, Wa_k, Xs, id_zt, false);
+                  gemm<PASSES, 1, true>(d + 64, Wb_m, GUs, id_ght, false);
+                }
+                commit(bars + B_ZFULL + sh);
+                if (sh == 1) {                                      // last reader of Wb; block 1 has no GX: of Wa too
+                  commit(bars + B_WFREE + sb);
+                  if (!blk) commit(bars + B_WFREE + sa);
+                }
+              }
+              __syncwarp();
+            }
+          }
+        }
+      }
+    } else if (warp == W_MMA2) {
+      // ==================================================================== MMA warp 2 (converged; one elected lane issues):
+      // the products that CONSUME what the epilogue warps packed into the ring — U (forward), GX and the weight
+      // gradients (backward)
+      const uint32_t aX = tc::smem_u32(sX), aGU = tc::smem_u32(sGU), aGZT = tc::smem_u32(sGZT),
+                     aWF = tc::smem_u32(smem + OFF_WF);
+      constexpr uint32_t RG = ROWG >> 4;
+      const Opnd GZTm{aGZT >> 4, SGZ_PART >> 4, 8, RG, 16};   // GZ^T tile read as A = GZ: rows = K = hidden units
+      uint32_t pe = 0, pw = 0, pdfree = 0x3, px = 0;
+      int wslot = 0;          // weight ring slot of the next load in sequence
+      auto next_slot = [](int s) { return s == NWSLOT - 1 ? 0 : s + 1; };
+      auto wait_bar = [&](uint64_t* bar, uint32_t& parity_bits, int bit) {
+        tc::mbar_wait(bar, (parity_bits >> bit) & 1);
+        parity_bits ^= 1u << bit;
+      };
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         TRACE_END();
         TRACE_BEGIN(2, lane == 0);
@@ -738,115 +827,64 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
           const int IN = blk ? X1 : OBS;
           PT(4);
           tc::mbar_wait(bars + B_XREADY, px); px ^= 1;    // the pass's input tile (X or GU) is published
-          tc::fence_after_sync();
           PT(0);
-          // Every step below has the same shape: the whole warp waits on the mbarriers the step depends on, then ONE
-          // elected lane issues all of the step's MMAs and commits back to back.
-          auto wait_bar = [&](uint64_t* bar, uint32_t& parity_bits, int bit) {
-            tc::mbar_wait(bar, (parity_bits >> bit) & 1);
-            parity_bits ^= 1u << bit;
-          };
           if (pass < 2) {
-            // ============================================================== forward: half-chunks of 64 hidden units
             const uint32_t wp = wpart(IN);
-            const uint32_t id_z = tc::make_idesc_bf16(128, HC, 0, 0), id_u = tc::make_idesc_bf16(128, IN, 0, 0);
-            // Z of half-chunk h into ring slot h & 1: A = X (K-major), B = Wa (rows = hidden units, K-major), K = IN
-            auto issue_z = [&](int h, int wslot) {
-              const int s = h & 1;
-              const uint32_t w = aWF + wslot * WSLOT;
-              const Opnd Wk{w >> 4, wp >> 4, HC, 8, 2 * HC};
-              if (blk) gemm<PASSES, 2>(tmem + TM_ZG + s * 128, Xk, Wk, id_z, false);
-              else gemm<PASSES, 1>(tmem + TM_ZG + s * 128, Xk, Wk, id_z, false);
-              PT(5);
-              commit(bars + B_ZFULL + s);
-            };
-            const int w0 = wslot_p1, w1 = next_slot(w0);
-            PT(4);
-            wait_bar(bars + B_WFULL + w0, pw, w0);
-            wait_bar(bars + B_WFULL + w1, pw, w1);
-            tc::fence_after_sync();
-            PT(2);
-            if (elect_one()) { issue_z(0, w0); issue_z(1, w1); }
-            __syncwarp();
-            wslot_p1 = next_slot(w1);
+            const uint32_t id_u = tc::make_idesc_bf16(128, IN, 0, 0);
 #pragma unroll 1
             for (int h = 0; h < NHC; ++h) {
-              const int s = h & 1;
+              const int s = h & 3;
               PT(4);
               wait_bar(bars + B_EFULL + s, pe, s);                       // H of half-chunk h sits packed in the slot
               PT(1);
-              if (h + 2 < NHC) wait_bar(bars + B_WFULL + wslot_p1, pw, wslot_p1);
+              wait_bar(bars + B_WFULL + wslot, pw, wslot);               // (long complete: Z of the half-chunk read the same load)
               tc::fence_after_sync();
               PT(2);
               if (elect_one()) {
                 // U += H Wb^T: A = H (tensor memory), B = Wb (rows = output features, K-major)
-                const uint32_t w = aWF + wslot_p2 * WSLOT;
+                const uint32_t w = aWF + wslot * WSLOT;
                 const Opnd Wbk{(w + 2 * wp) >> 4, wp >> 4, (uint32_t)IN, 8, 2u * IN};
-                gemm_ts<PASSES>(tmem + TM_U, tmem + TM_ZG + s * 128, Wbk, id_u, h > 0);
+                gemm_ts<PASSES>(tmem + TM_U, tmem + TM_ZG + s * 64, Wbk, id_u, h > 0);
                 PT(6);
-                commit(bars + B_WFREE + wslot_p2);
-                if (h + 2 < NHC) issue_z(h + 2, wslot_p1);
-                else if (h == NHC - 1) commit(bars + B_ACC);              // everything issued so far: U is complete
+                commit(bars + B_WFREE + wslot);
+                if (h + 4 < NHC) commit(bars + B_SFREE + s);
+                if (h == NHC - 1) commit(bars + B_ACC);                   // U is complete
               }
               __syncwarp();
-              wslot_p2 = next_slot(wslot_p2);
-              if (h + 2 < NHC) wslot_p1 = next_slot(wslot_p1);
+              wslot = next_slot(wslot);
             }
           } else {
-            // ============================================================== backward: chunks of 128 hidden units x halves
-            // of 64 samples, transposed (D lanes = hidden units)
             const uint32_t cp = cpart(IN);
-            const uint32_t id_zt = tc::make_idesc_bf16(128, 64, 0, 0), id_ght = tc::make_idesc_bf16(128, 64, 1, 0);
             const uint32_t id_dwa = tc::make_idesc_bf16(128, XCOLS, 0, 1), id_dwb = tc::make_idesc_bf16(128, IN, 0, 1);
             const uint32_t id_gx = tc::make_idesc_bf16(128, IN, 1, 1);
-            // Z^T = Wa X^T and GH^T = Wb^T GU^T of unit u = (chunk u / 2, sample half u % 2) into ring slot u & 1
-            auto issue_zt = [&](int u) {
-              const int c = u >> 1, sh = u & 1, b = c & 1;
-              const uint32_t w = aWB + b * CSLOT;
-              const Opnd Wa_k{w >> 4, cp >> 4, CH, 8, 2 * CH};                                // rows = hidden units = M
-              const Opnd Wb_m{(w + 2 * cp) >> 4, cp >> 4, 8, (uint32_t)IN, 16};               // rows = K = output features
-              const Opnd Xs{(aX >> 4) + 64 * sh, SX_PART >> 4, RG, 8, 2 * RG};                // the 64 sample rows = N
-              const Opnd GUs{(aGU >> 4) + 64 * sh, SGU_PART >> 4, RG, 8, 2 * RG};
-              const uint32_t d = tmem + TM_ZG + sh * 128;
-              if (blk) {
-                gemm<PASSES, 2, true>(d, Wa_k, Xs, id_zt, false);
-                gemm<PASSES, 2, true>(d + 64, Wb_m, GUs, id_ght, false);
-              } else {
-                gemm<PASSES, 1, true>(d, Wa_k, Xs, id_zt, false);
-                gemm<PASSES, 1, true>(d + 64, Wb_m, GUs, id_ght, false);
-              }
-              PT(5);
-              commit(bars + B_ZFULL + sh);
-              if (!blk && sh == 1) commit(bars + B_CFREE + b);    // backward block 1 has no GX: last reader of the chunk
-            };
-            PT(4);
-            wait_bar(bars + B_CFULL + 0, pc_full, 0);
-            tc::fence_after_sync();
-            PT(2);
-            if (elect_one()) { issue_zt(0); issue_zt(1); }
-            __syncwarp();
 #pragma unroll 1
             for (int u = 0; u < 2 * NCH; ++u) {
               const int c = u >> 1, sh = u & 1, b = c & 1;
               PT(4);
               wait_bar(bars + B_EFULL + sh, pe, sh);                     // H^T / GZ^T of unit u sit packed in the slot
               PT(1);
+              int sa = 0;
               if (sh == 0) {
                 wait_bar(bars + B_DWFREE + b, pdfree, b);                // accumulator buffer b was flushed
                 PT(3);
-                if (u + 2 < 2 * NCH) wait_bar(bars + B_CFULL + ((c + 1) & 1), pc_full, (c + 1) & 1);   // next chunk's weights
+              } else {                                                   // the chunk's two loads, in sequence
+                sa = wslot;
+                const int sb = next_slot(sa);
+                if (blk) tc::mbar_wait(bars + B_WFULL + sa, (pw >> sa) & 1);   // (long complete: Z^T read the same load)
+                pw ^= (1u << sa) | (1u << sb);
+                wslot = next_slot(sb);
                 PT(2);
               }
               tc::fence_after_sync();
               if (elect_one()) {
                 if (sh == 1 && blk) {   // GX += GZ Wa over the chunk's 128 hidden units: both operands MN-major (rows = K).
                   // First: the next chunk's epilogue waits for the GZ^T tile
-                  const uint32_t w = aWB + b * CSLOT;
+                  const uint32_t w = aWF + sa * WSLOT;
                   const Opnd Wa_m{w >> 4, cp >> 4, 8, CH, 16};
                   gemm<PASSES, 8>(tmem + TM_GX, GZTm, Wa_m, id_gx, c > 0);
                   PT(6);
                   commit(bars + B_GZFREE);
-                  commit(bars + B_CFREE + b);
+                  commit(bars + B_WFREE + sa);
                 }
                 {   // dWa += GZ^T [X | 1], dWbT += H^T GU over the unit's 64 samples: A in tensor memory, B MN-major
                   const Opnd Xs{(aX >> 4) + 64 * sh, SX_PART >> 4, 8, RG, 16};
@@ -855,10 +893,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
                   gemm_ts<PASSES>(d, slot + 64, Xs, id_dwa, sh > 0);
                   gemm_ts<PASSES>(d + 48, slot, GUs, id_dwb, sh > 0);
                   PT(7);
+                  if (u + 2 < 2 * NCH) commit(bars + B_SFREE + sh);
                   if (sh == 1) commit(bars + B_DWFULL + b);
+                  if (u == 2 * NCH - 1) commit(bars + B_ACC);             // GX / the tile is complete
                 }
-                if (u + 2 < 2 * NCH) issue_zt(u + 2);
-                else if (u == 2 * NCH - 1) commit(bars + B_ACC);          // everything issued so far: GX / the tile is complete
               }
               __syncwarp();
             }
