@@ -39,6 +39,8 @@ int navppo_tc_init();
 int navppo_tcws_grad_launch(const ppo::GradArgs& a, int rows, int passes, float* wprep, cudaStream_t s);
 size_t navppo_tcws_prep_bytes();
 int navppo_tcws_init();
+int navppo_tcws_prep_launch(const float* params, float* wprep, cudaStream_t s);
+int navppo_tcws_infer_launch(const ppo::InferArgs& a, int mode, bool both_nets, int passes, const float* wprep, cudaStream_t s);
 
 namespace {
 
@@ -106,30 +108,6 @@ __device__ __forceinline__ void resblock_fwd(const float* __restrict__ sWa, cons
     }
   }
 }
-
-enum { INFER_FORWARD = 0, INFER_ACT = 1, INFER_EVALUATE = 2 };
-
-struct InferArgs {
-  const float* params;   // flat [actor | critic]
-  const float* obs;      // [T,16]
-  int T;
-  float var;
-  // forward
-  float* mu;             // [T,2] or null
-  float* v;              // [T]   or null
-  // act
-  uint64_t seed;
-  int64_t agent_off;
-  uint32_t draw;
-  const float* noise_in; // [T,2] or null
-  float* act;            // [T,2]
-  float* logp;           // [T]
-  // evaluate
-  const float* act_in;   // [T,2]
-  // act, optional: device words {float bits of var, draw increment} read at run time, so that a captured
-  // CUDA graph of the rollout can be replayed with a new variance / noise counter
-  const uint32_t* dyn;
-};
 
 // ----------------------------------------------------------------------------------------
 // Inference (NetActor / NetCritic forward + the get_action / evaluate epilogues).
@@ -818,6 +796,8 @@ struct navppo {
   float* grad_ws = nullptr;   // [NAVPPO_FLAT] used by navppo_update
   float* wprep = nullptr;     // tensor-core path: pre-split, pre-tiled weights
   bool tc_single_role = false;  // NAVPPO_TC_KERNEL=single: the first (single-role) tcgen05 kernel, kept as a cross-check
+  bool tc_infer = false;        // tensor-core precision: the rollout's and the update's forward passes run on the tensor cores
+                                // too (NAVPPO_TC_INFER=0 keeps them on the fp32 CUDA-core kernel)
   // peer-memory gradient exchange (navppo_peer_setup): two gradient buffers + a flag array per rank
   int peer_rank = 0, peer_world = 0;
   const float* peer_grad[2][16] = {};
@@ -840,6 +820,11 @@ int check_handle(const navppo* h) {
 template <int MODE>
 int launch_infer(navppo* h, const InferArgs& a, bool both_nets, cudaStream_t s) {
   if (a.T <= 0) return nav_fail(NAVSIM_EINVAL, "T must be positive");
+  if (h->tc_infer) {   // a tensor-core handle runs every network product on the tensor cores: re-tile the weights, then infer
+    if (int rc = navppo_tcws_prep_launch(a.params, h->wprep, s)) return rc;
+    h->launches += 2;
+    return navppo_tcws_infer_launch(a, MODE, both_nets, h->cfg.precision == NAVPPO_BF16X3 ? 3 : 1, h->wprep, s);
+  }
   const int grid = (a.T + CF_TILE - 1) / CF_TILE;
   mlp_infer_kernel<MODE><<<dim3(grid, both_nets ? 2 : 1), CF_THREADS, CF_SMEM, s>>>(a);
   h->launches++;
@@ -897,6 +882,8 @@ int navppo_create(navppo_t** out, const navppo_cfg* cfg) {
   if (e == cudaSuccess && cfg->precision != NAVPPO_FP32) {
     const char* which = getenv("NAVPPO_TC_KERNEL");
     h->tc_single_role = which && std::string(which) == "single";
+    const char* ti = std::getenv("NAVPPO_TC_INFER");
+    h->tc_infer = !(ti && std::string(ti) == "0");
     const size_t wb = navppo_tc_prep_bytes() > navppo_tcws_prep_bytes() ? navppo_tc_prep_bytes() : navppo_tcws_prep_bytes();
     e = cudaMalloc(&h->wprep, wb);
     if (e == cudaSuccess && (navppo_tc_init() != NAVSIM_OK || navppo_tcws_init() != NAVSIM_OK)) {
@@ -1109,13 +1096,21 @@ int navppo_rollout_ex(navppo_t* h, navsim_t* sim, const float* params, int32_t H
   if (H < 1) return nav_fail(NAVSIM_EINVAL, "H must be positive");
   if (!(var > 0.0)) return nav_fail(NAVSIM_EINVAL, "var must be positive");
   const size_t N = (size_t)navsim_num_agents(sim);
+  const int tc_passes = h->cfg.precision == NAVPPO_BF16X3 ? 3 : 1;
+  if (h->tc_infer) {   // the policy does not change inside a rollout: re-tile its weights once
+    if (int rc = navppo_tcws_prep_launch(params, h->wprep, (cudaStream_t)stream)) return rc;
+    h->launches++;
+  }
   for (int t = 0; t < H; ++t) {
     float* o_t = obs + (size_t)t * N * OBS;
     float* o_next = (t + 1 < H) ? obs + (size_t)(t + 1) * N * OBS : next_obs;
     InferArgs a{};
     a.params = params; a.obs = o_t; a.T = (int)N; a.var = (float)var; a.seed = seed; a.agent_off = agent_id_offset;
     a.draw = draw0 + (uint32_t)t; a.act = act + (size_t)t * N * 2; a.logp = logp + (size_t)t * N; a.dyn = dyn_dev;
-    if (int rc = launch_infer<INFER_ACT>(h, a, false, (cudaStream_t)stream)) return rc;
+    if (h->tc_infer) {
+      if (int rc = navppo_tcws_infer_launch(a, INFER_ACT, false, tc_passes, h->wprep, (cudaStream_t)stream)) return rc;
+      h->launches++;
+    } else if (int rc = launch_infer<INFER_ACT>(h, a, false, (cudaStream_t)stream)) return rc;
     navsim_step_out out;
     out.obs = o_next; out.rew = rew + (size_t)t * N; out.done = done + (size_t)t * N; out.arrive = arrive + (size_t)t * N;
     out.trunc = trunc + (size_t)t * N;

@@ -41,6 +41,7 @@
 
 #include "../../include/navppo.h"
 #include "nav_common.h"
+#include "navsim_math.h"
 #include "ppo_common.cuh"
 #include "tc_common.cuh"
 
@@ -225,18 +226,18 @@ __device__ __forceinline__ void gemm(uint32_t tmem_d, const Opnd& A, const Opnd&
   }
 }
 // D (+)= A B over K = 64 with A in tensor memory, as the epilogue warps leave it: per 32 k [16 packed hi
-// columns | 16 packed lo columns], 8 packed columns per instruction
-template <int PASSES>
+// columns | 16 packed lo columns] (or, L16, per 16 k [8 packed hi | 8 packed lo]), 8 packed columns per instruction
+template <int PASSES, bool L16 = false>
 __device__ __forceinline__ void gemm_ts(uint32_t tmem_d, uint32_t tmem_a, const Opnd& B, uint32_t idesc, bool accumulate) {
   {   // the caller is the one elected lane of the issuing warp
     uint32_t acc = accumulate ? 1u : 0u;
     const uint32_t b0 = B.start | (B.lbo << 16);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      const uint32_t ah = tmem_a + 32 * (kk >> 1) + 8 * (kk & 1);
+      const uint32_t ah = L16 ? tmem_a + 16 * kk : tmem_a + 32 * (kk >> 1) + 8 * (kk & 1);
       const uint64_t bh = words_desc(b0 + kk * B.step, B.sbo);
       if (PASSES == 3) {  // small terms first
-        tc::mma_bf16_ts(tmem_d, ah + 16, bh, idesc, acc); acc = 1u;
+        tc::mma_bf16_ts(tmem_d, ah + (L16 ? 8 : 16), bh, idesc, acc); acc = 1u;
         tc::mma_bf16_ts(tmem_d, ah, words_desc(b0 + kk * B.step + B.part, B.sbo), idesc, acc);
       }
       tc::mma_bf16_ts(tmem_d, ah, bh, idesc, acc); acc = 1u;
@@ -925,6 +926,281 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
   }
 }
 
+// ========================================================================================
+// Inference on the tensor cores: the forward half of the gradient kernel (same products, same epilogue
+// arithmetic, same order — a sample's mean / value is bit-identical to what the update recomputes for it),
+// one tile of 128 samples per CTA, + the get_action / evaluate epilogues of mlp_infer_kernel
+// (ppo.py:690-705, 725-737).  Used by the fused rollout and by the update's first evaluate when the handle's
+// precision is NAVPPO_BF16X3 / NAVPPO_BF16.
+//   warps 0 .. 4 EW - 1   epilogue: EW warps per TMEM lane quarter, 64 / EW columns of a half-chunk each;
+//                         warps 0-3 also own one sample row each
+//   warp 4 EW             issues every tcgen05.mma;   warp 4 EW + 1: one thread streams the weights (TMA ring)
+// ========================================================================================
+constexpr int INF_EW = 4;
+constexpr int INF_CW = HC / INF_EW;                          // columns of a half-chunk per epilogue warp
+constexpr int INF_EWARPS = 4 * INF_EW;
+constexpr int INF_W_TMA = INF_EWARPS + 1;                    // the MMA warp is the one before it
+constexpr int INF_THREADS = 32 * (INF_EWARPS + 2);
+constexpr uint32_t IOFF_WF = 2 * SX_PART;                    // 24 KB: weight ring
+constexpr uint32_t IOFF_BIAS = IOFF_WF + NWSLOT * WSLOT;     // 136 KB
+constexpr uint32_t IOFF_PAR = IOFF_BIAS + 2 * HID * 4;
+constexpr uint32_t IOFF_BAR = IOFF_PAR + 128 * 4;
+constexpr uint32_t INF_SMEM_BYTES = IOFF_BAR + 256;
+enum { I_ZFULL = 0, I_EFULL = 4, I_WFULL = 8, I_WFREE = 15, I_ACC = 22, I_XREADY = 23, I_COUNT = 24 };
+
+struct WsInferArgs {
+  InferArgs g;
+  const unsigned char* wprep;
+  int mode;
+};
+
+template <int PASSES>
+__global__ void __launch_bounds__(INF_THREADS, 1) mlp_infer_ws_kernel(WsInferArgs ta) {
+  const InferArgs& a = ta.g;
+  const int net = blockIdx.y;
+  if (ta.mode == INFER_FORWARD && ((net == 0 && !a.mu) || (net == 1 && !a.v))) return;
+  unsigned char* smem = ws_smem;
+  unsigned char* sX = smem + OFF_SX;
+  float* sBias = reinterpret_cast<float*>(smem + IOFF_BIAS);
+  float* sPar = reinterpret_cast<float*>(smem + IOFF_PAR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + IOFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + IOFF_BAR + I_COUNT * 8);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* __restrict__ p = a.params + (net ? NAVPPO_CRITIC_OFFSET : 0);
+  const unsigned char* __restrict__ wblob_g = ta.wprep + (size_t)net * WS_NET_BLOB;
+  const int tile = blockIdx.x;
+
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) { tc::mbar_init(bars + I_ZFULL + i, 1); tc::mbar_init(bars + I_EFULL + i, INF_EWARPS); }
+    for (int i = 0; i < NWSLOT; ++i) { tc::mbar_init(bars + I_WFULL + i, 1); tc::mbar_init(bars + I_WFREE + i, 1); }
+    tc::mbar_init(bars + I_ACC, 1);
+    tc::mbar_init(bars + I_XREADY, 4);
+  }
+  if (warp == 0) tc::tmem_alloc(tmem_slot, TM_COLS);
+  for (int i = tid; i < 2 * HID; i += INF_THREADS) sBias[i] = p[(i < HID ? O_B1A : O_B2A - HID) + i];
+  if (tid < OBS) sPar[P_B1B + tid] = p[O_B1B + tid];
+  else if (tid < OBS + X1) sPar[tid] = p[O_B2B + tid - OBS];
+  else if (tid < OBS + X1 + (net == 0 ? ACTOR_HEAD : CRITIC_HEAD)) sPar[tid] = p[O_HEAD + tid - OBS - X1];
+  tc::fence_smem_to_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < INF_EWARPS) {
+    // ====================================================================== epilogue warps
+    const int q = warp & 3, ch = warp >> 2;            // TMEM lane quarter / column share of a half-chunk
+    const int row = q * 32 + lane;                     // sample row
+    const bool owner = ch == 0;
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    const int si = tile * 128 + row;
+    const bool valid = owner && si < a.T;
+    uint32_t pz = 0;
+    auto publish = [&](uint64_t* bar, bool wrote_smem) {
+      if (wrote_smem) tc::fence_smem_to_async();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
+    float x1[X1];
+    if (owner) {
+      if (si < a.T) {
+        const float4* o = reinterpret_cast<const float4*>(a.obs + (size_t)si * OBS);
+#pragma unroll
+        for (int k4 = 0; k4 < OBS / 4; ++k4) {
+          const float4 t = o[k4];
+          x1[4 * k4] = t.x; x1[4 * k4 + 1] = t.y; x1[4 * k4 + 2] = t.z; x1[4 * k4 + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < OBS; ++k) x1[k] = 0.f;
+      }
+      store8<PASSES>(sX, SX_PART, row, 0, x1);
+      store8<PASSES>(sX, SX_PART, row, 8, x1 + 8);
+      publish(bars + I_XREADY, true);
+    }
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      const int blk = pass;
+#pragma unroll 1
+      for (int h = 0; h < NHC; ++h) {
+        const int s = h & 3;
+        tc::mbar_wait(bars + I_ZFULL + s, (pz >> s) & 1); pz ^= 1u << s;
+        tc::fence_after_sync();
+        // H = lrelu(Z + ba) of this warp's INF_CW columns, packed over the columns it just read as the A operand
+        // of U += H Wb^T: per 16 columns [hi: 8 packed words | lo: 8 packed words]
+        const int c0 = ch * INF_CW;
+        const uint32_t tslot = trow + TM_ZG + s * 64;
+        const float* sBa = sBias + blk * HID + h * HC + c0;
+        float v[INF_CW];
+#pragma unroll
+        for (int i = 0; i < INF_CW; i += 16) tc::tmem_ld16_nowait(tslot + c0 + i, v + i);
+        tc::tmem_ld_wait();
+        uint32_t hi[INF_CW / 2], lo[INF_CW / 2];
+#pragma unroll
+        for (int i4 = 0; i4 < INF_CW / 4; ++i4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(sBa + 4 * i4);
+          const float h0 = lrelu_fast(v[4 * i4] + b4.x), h1 = lrelu_fast(v[4 * i4 + 1] + b4.y);
+          const float h2 = lrelu_fast(v[4 * i4 + 2] + b4.z), h3 = lrelu_fast(v[4 * i4 + 3] + b4.w);
+          tc::split_bf16x2(h0, h1, &hi[2 * i4], &lo[2 * i4]);
+          tc::split_bf16x2(h2, h3, &hi[2 * i4 + 1], &lo[2 * i4 + 1]);
+        }
+#pragma unroll
+        for (int j = 0; j < INF_CW / 16; ++j) {
+          tc::tmem_st8(tslot + c0 + 16 * j, hi + 8 * j);
+          if (PASSES == 3) tc::tmem_st8(tslot + c0 + 16 * j + 8, lo + 8 * j);
+        }
+        tc::tmem_st_wait();
+        publish(bars + I_EFULL + s, false);
+      }
+      if (!owner) continue;
+      tc::mbar_wait(bars + I_ACC, pass);              // every product of this pass has completed
+      tc::fence_after_sync();
+      if (pass == 0) {
+        // block-1 output: u1 = x0 + U + bb, y1 = lrelu(u1) -> X columns 16..31
+        float acc[16];
+        tc::tmem_ld16(trow + TM_U, acc);
+#pragma unroll
+        for (int k = 0; k < OBS; ++k) x1[OBS + k] = lrelu(x1[k] + acc[k] + sPar[P_B1B + k]);
+        store8<PASSES>(sX, SX_PART, row, 16, x1 + 16);
+        store8<PASSES>(sX, SX_PART, row, 24, x1 + 24);
+        publish(bars + I_XREADY, true);
+      } else {
+        float y2[X1];
+        {
+          float acc[32];
+          tc::tmem_ld16_nowait(trow + TM_U, acc);
+          tc::tmem_ld16_nowait(trow + TM_U + 16, acc + 16);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < X1; ++k) y2[k] = lrelu(x1[k] + acc[k] + sPar[P_B2B + k]);
+        }
+        const float* hw = sPar + P_HEAD;
+        if (net == 1) {                        // critic: V = out(X), net_critic.py:129
+          float v = hw[X1];
+#pragma unroll
+          for (int k = 0; k < X1; ++k) v = fmaf(hw[k], y2[k], v);
+          if (valid) a.v[si] = v;
+        } else {
+          float o1 = hw[X1], o2 = hw[2 * X1 + 1];
+#pragma unroll
+          for (int k = 0; k < X1; ++k) { o1 = fmaf(hw[k], y2[k], o1); o2 = fmaf(hw[X1 + 1 + k], y2[k], o2); }
+          const float m0 = sigmoidf_(o1), m1 = tanhf(o2);  // net_actor.py:141-142
+          if (valid) {
+            if (ta.mode == INFER_FORWARD) {
+              reinterpret_cast<float2*>(a.mu)[si] = make_float2(m0, m1);
+            } else if (ta.mode == INFER_ACT) {
+              const float var_ = a.dyn ? __uint_as_float(a.dyn[0]) : a.var;
+              const uint32_t draw_ = a.dyn ? a.draw + a.dyn[1] : a.draw;
+              float e0, e1;
+              if (a.noise_in) {
+                const float2 e = reinterpret_cast<const float2*>(a.noise_in)[si];
+                e0 = e.x; e1 = e.y;
+              } else {  // Box-Muller on two Philox words
+                uint32_t r[4];
+                const uint64_t agent = (uint64_t)(a.agent_off + si);
+                nv_philox4x32_10(draw_, 2u, (uint32_t)agent, (uint32_t)(agent >> 32), (uint32_t)a.seed,
+                                 (uint32_t)(a.seed >> 32), r);
+                const float uu = ((float)(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0, 1)
+                const float vv = ((float)(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+                const float rad = sqrtf(-2.0f * logf(uu));
+                float sn, cs;
+                sincosf(6.283185307179586f * vv, &sn, &cs);
+                e0 = rad * cs; e1 = rad * sn;
+              }
+              const float sd = sqrtf(var_);
+              float a0 = fmaf(sd, e0, m0), a1 = fmaf(sd, e1, m1);       // dist.sample(), ppo.py:698-699
+              a0 = fminf(fmaxf(a0, 0.f), 1.f);                          // ppo.py:701
+              a1 = fminf(fmaxf(a1, -1.f), 1.f);                         // ppo.py:702
+              reinterpret_cast<float2*>(a.act)[si] = make_float2(a0, a1);
+              a.logp[si] = gauss_logp(a0, a1, m0, m1, var_);            // ppo.py:704 (at the clamped action)
+              if (a.mu) reinterpret_cast<float2*>(a.mu)[si] = make_float2(m0, m1);
+            } else {
+              const float2 av = reinterpret_cast<const float2*>(a.act_in)[si];
+              a.logp[si] = gauss_logp(av.x, av.y, m0, m1, a.var);       // ppo.py:734-735
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == INF_W_TMA) {
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t pfree = (1u << NWSLOT) - 1;
+#pragma unroll 1
+      for (int i = 0; i < 2 * NHC; ++i) {
+        const int blk = i >> 3, h = i & 7;
+        tc::mbar_wait(bars + I_WFREE + slot, (pfree >> slot) & 1); pfree ^= 1u << slot;
+        tma_load(smem + IOFF_WF + slot * WSLOT, wblob_g + wblob_off(blk, h), wblob(blk ? X1 : OBS), bars + I_WFULL + slot);
+        slot = slot == NWSLOT - 1 ? 0 : slot + 1;
+      }
+    }
+  } else {
+    // ====================================================================== the MMA-issuing warp
+    const uint32_t aX = tc::smem_u32(sX), aWF = tc::smem_u32(smem + IOFF_WF);
+    constexpr uint32_t RG = ROWG >> 4;
+    const Opnd Xk{aX >> 4, SX_PART >> 4, RG, 8, 2 * RG};
+    uint32_t pe = 0, pw = 0;
+    int wz = 0, wu = 0;     // weight ring slot of the next Z / of the next U
+    auto next_slot = [](int s) { return s == NWSLOT - 1 ? 0 : s + 1; };
+    auto wait_bar = [&](uint64_t* bar, uint32_t& parity_bits, int bit) {
+      tc::mbar_wait(bar, (parity_bits >> bit) & 1);
+      parity_bits ^= 1u << bit;
+    };
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      const int blk = pass;
+      const int IN = blk ? X1 : OBS;
+      const uint32_t wp = wpart(IN);
+      const uint32_t id_z = tc::make_idesc_bf16(128, HC, 0, 0), id_u = tc::make_idesc_bf16(128, IN, 0, 0);
+      auto issue_z = [&](int h, int wslot) {
+        const int s = h & 3;
+        const uint32_t w = aWF + wslot * WSLOT;
+        const Opnd Wk{w >> 4, wp >> 4, HC, 8, 2 * HC};
+        if (blk) gemm<PASSES, 2>(tmem + TM_ZG + s * 64, Xk, Wk, id_z, false);
+        else gemm<PASSES, 1>(tmem + TM_ZG + s * 64, Xk, Wk, id_z, false);
+        commit(bars + I_ZFULL + s);
+      };
+      tc::mbar_wait(bars + I_XREADY, pass);
+      {
+        int w = wz;
+        for (int i = 0; i < 4; ++i) { wait_bar(bars + I_WFULL + w, pw, w); w = next_slot(w); }
+      }
+      tc::fence_after_sync();
+      if (elect_one()) {
+        int w = wz;
+        for (int i = 0; i < 4; ++i) { issue_z(i, w); w = next_slot(w); }
+      }
+      __syncwarp();
+      for (int i = 0; i < 4; ++i) wz = next_slot(wz);
+#pragma unroll 1
+      for (int h = 0; h < NHC; ++h) {
+        const int s = h & 3;
+        wait_bar(bars + I_EFULL + s, pe, s);
+        if (h + 4 < NHC) wait_bar(bars + I_WFULL + wz, pw, wz);
+        tc::fence_after_sync();
+        if (elect_one()) {
+          const uint32_t w = aWF + wu * WSLOT;
+          const Opnd Wbk{(w + 2 * wp) >> 4, wp >> 4, (uint32_t)IN, 8, 2u * IN};
+          gemm_ts<PASSES, true>(tmem + TM_U, tmem + TM_ZG + s * 64, Wbk, id_u, h > 0);
+          commit(bars + I_WFREE + wu);
+          if (h + 4 < NHC) issue_z(h + 4, wz);
+          else if (h == NHC - 1) commit(bars + I_ACC);
+        }
+        __syncwarp();
+        wu = next_slot(wu);
+        if (h + 4 < NHC) wz = next_slot(wz);
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem, TM_COLS);
+  }
+}
+
 }  // namespace
 
 // ---- internal entry points used by navppo_kernels.cu -----------------------------------
@@ -936,6 +1212,25 @@ int navppo_tcws_init() {
   NAV_CUDA_TRY(cudaFuncSetAttribute(mlp_grad_ws_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES));
   NAV_CUDA_TRY(cudaFuncSetAttribute(mlp_grad_ws_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES));
   NAV_CUDA_TRY(cudaFuncSetAttribute(mlp_grad_ws_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES));
+  NAV_CUDA_TRY(cudaFuncSetAttribute(mlp_infer_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INF_SMEM_BYTES));
+  NAV_CUDA_TRY(cudaFuncSetAttribute(mlp_infer_ws_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INF_SMEM_BYTES));
+  return NAVSIM_OK;
+}
+
+// Re-tile the current weights for the tensor-core kernels (one launch; the rollout does it once for all its steps).
+int navppo_tcws_prep_launch(const float* params, float* wprep, cudaStream_t s) {
+  ws_prep_weights_kernel<<<dim3(24, 2), 256, 0, s>>>(params, reinterpret_cast<unsigned char*>(wprep));
+  NAV_CUDA_TRY(cudaGetLastError());
+  return NAVSIM_OK;
+}
+
+// One inference pass on the tensor cores over weights already re-tiled into `wprep`.
+int navppo_tcws_infer_launch(const ppo::InferArgs& a, int mode, bool both_nets, int passes, const float* wprep, cudaStream_t s) {
+  WsInferArgs ta{a, reinterpret_cast<const unsigned char*>(wprep), mode};
+  const dim3 grid((a.T + 127) / 128, both_nets ? 2 : 1);
+  if (passes == 3) mlp_infer_ws_kernel<3><<<grid, INF_THREADS, INF_SMEM_BYTES, s>>>(ta);
+  else mlp_infer_ws_kernel<1><<<grid, INF_THREADS, INF_SMEM_BYTES, s>>>(ta);
+  NAV_CUDA_TRY(cudaGetLastError());
   return NAVSIM_OK;
 }
 

@@ -64,6 +64,31 @@ struct GradArgs {
   double* mpart;      // [2][rows][4] per-CTA metric sums
 };
 
+enum { INFER_FORWARD = 0, INFER_ACT = 1, INFER_EVALUATE = 2 };
+
+// arguments of one inference pass over T samples (NetActor / NetCritic forward + the get_action / evaluate epilogues)
+struct InferArgs {
+  const float* params;   // flat [actor | critic]
+  const float* obs;      // [T,16]
+  int T;
+  float var;
+  // forward
+  float* mu;             // [T,2] or null
+  float* v;              // [T]   or null
+  // act
+  uint64_t seed;
+  int64_t agent_off;
+  uint32_t draw;
+  const float* noise_in; // [T,2] or null
+  float* act;            // [T,2]
+  float* logp;           // [T]
+  // evaluate
+  const float* act_in;   // [T,2]
+  // act, optional: device words {float bits of var, draw increment} read at run time, so that a captured
+  // CUDA graph of the rollout can be replayed with a new variance / noise counter
+  const uint32_t* dyn;
+};
+
 }  // namespace ppo
 
 #endif  // NAVPPO_COMMON_CUH_
