@@ -40,7 +40,10 @@ int navppo_tcws_grad_launch(const ppo::GradArgs& a, int rows, int passes, float*
 size_t navppo_tcws_prep_bytes();
 int navppo_tcws_init();
 int navppo_tcws_prep_launch(const float* params, float* wprep, cudaStream_t s);
-int navppo_tcws_infer_launch(const ppo::InferArgs& a, int mode, bool both_nets, int passes, const float* wprep, cudaStream_t s);
+int navppo_tcws_infer_launch(const ppo::InferArgs& a, int mode, bool both_nets, int passes, const float* wprep, bool chained,
+                             bool weights_ready, cudaStream_t s);
+// navsim_step_ex as a programmatic dependent launch (navsim_kernels.cu)
+int navsim_step_chained(navsim_t* h, const float* act_dev, const navsim_step_out* out, void* stream);
 
 namespace {
 
@@ -796,6 +799,7 @@ struct navppo {
   float* grad_ws = nullptr;   // [NAVPPO_FLAT] used by navppo_update
   float* wprep = nullptr;     // tensor-core path: pre-split, pre-tiled weights
   bool tc_single_role = false;  // NAVPPO_TC_KERNEL=single: the first (single-role) tcgen05 kernel, kept as a cross-check
+  bool chain = false;           // rollout: policy and step kernels as programmatic dependent launches (NAVPPO_ROLLOUT_CHAIN=0: plain)
   bool tc_infer = false;        // tensor-core precision: the rollout's and the update's forward passes run on the tensor cores
                                 // too (NAVPPO_TC_INFER=0 keeps them on the fp32 CUDA-core kernel)
   // peer-memory gradient exchange (navppo_peer_setup): two gradient buffers + a flag array per rank
@@ -823,7 +827,7 @@ int launch_infer(navppo* h, const InferArgs& a, bool both_nets, cudaStream_t s) 
   if (h->tc_infer) {   // a tensor-core handle runs every network product on the tensor cores: re-tile the weights, then infer
     if (int rc = navppo_tcws_prep_launch(a.params, h->wprep, s)) return rc;
     h->launches += 2;
-    return navppo_tcws_infer_launch(a, MODE, both_nets, h->cfg.precision == NAVPPO_BF16X3 ? 3 : 1, h->wprep, s);
+    return navppo_tcws_infer_launch(a, MODE, both_nets, h->cfg.precision == NAVPPO_BF16X3 ? 3 : 1, h->wprep, false, false, s);
   }
   const int grid = (a.T + CF_TILE - 1) / CF_TILE;
   mlp_infer_kernel<MODE><<<dim3(grid, both_nets ? 2 : 1), CF_THREADS, CF_SMEM, s>>>(a);
@@ -884,6 +888,8 @@ int navppo_create(navppo_t** out, const navppo_cfg* cfg) {
     h->tc_single_role = which && std::string(which) == "single";
     const char* ti = std::getenv("NAVPPO_TC_INFER");
     h->tc_infer = !(ti && std::string(ti) == "0");
+    const char* ch = std::getenv("NAVPPO_ROLLOUT_CHAIN");
+    h->chain = !(ch && std::string(ch) == "0");
     const size_t wb = navppo_tc_prep_bytes() > navppo_tcws_prep_bytes() ? navppo_tc_prep_bytes() : navppo_tcws_prep_bytes();
     e = cudaMalloc(&h->wprep, wb);
     if (e == cudaSuccess && (navppo_tc_init() != NAVSIM_OK || navppo_tcws_init() != NAVSIM_OK)) {
@@ -1108,7 +1114,7 @@ int navppo_rollout_ex(navppo_t* h, navsim_t* sim, const float* params, int32_t H
     a.params = params; a.obs = o_t; a.T = (int)N; a.var = (float)var; a.seed = seed; a.agent_off = agent_id_offset;
     a.draw = draw0 + (uint32_t)t; a.act = act + (size_t)t * N * 2; a.logp = logp + (size_t)t * N; a.dyn = dyn_dev;
     if (h->tc_infer) {
-      if (int rc = navppo_tcws_infer_launch(a, INFER_ACT, false, tc_passes, h->wprep, (cudaStream_t)stream)) return rc;
+      if (int rc = navppo_tcws_infer_launch(a, INFER_ACT, false, tc_passes, h->wprep, h->chain, t > 0, (cudaStream_t)stream)) return rc;
       h->launches++;
     } else if (int rc = launch_infer<INFER_ACT>(h, a, false, (cudaStream_t)stream)) return rc;
     navsim_step_out out;
@@ -1117,7 +1123,9 @@ int navppo_rollout_ex(navppo_t* h, navsim_t* sim, const float* params, int32_t H
     out.ep_return = ep_return ? ep_return + (size_t)t * N : nullptr;
     out.ep_path = ep_path ? ep_path + (size_t)t * N : nullptr;
     out.ep_len = ep_len ? ep_len + (size_t)t * N : nullptr;
-    if (int rc = navsim_step_ex(sim, act + (size_t)t * N * 2, &out, stream)) return rc;
+    if (h->tc_infer && h->chain) {
+      if (int rc = navsim_step_chained(sim, act + (size_t)t * N * 2, &out, stream)) return rc;
+    } else if (int rc = navsim_step_ex(sim, act + (size_t)t * N * 2, &out, stream)) return rc;
   }
   return NAVSIM_OK;
 }

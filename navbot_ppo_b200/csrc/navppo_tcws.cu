@@ -227,13 +227,13 @@ __device__ __forceinline__ void gemm(uint32_t tmem_d, const Opnd& A, const Opnd&
 }
 // D (+)= A B over K = 64 with A in tensor memory, as the epilogue warps leave it: per 32 k [16 packed hi
 // columns | 16 packed lo columns] (or, L16, per 16 k [8 packed hi | 8 packed lo]), 8 packed columns per instruction
-template <int PASSES, bool L16 = false>
+template <int PASSES, bool L16 = false, int KSTEPS = 4>
 __device__ __forceinline__ void gemm_ts(uint32_t tmem_d, uint32_t tmem_a, const Opnd& B, uint32_t idesc, bool accumulate) {
   {   // the caller is the one elected lane of the issuing warp
     uint32_t acc = accumulate ? 1u : 0u;
     const uint32_t b0 = B.start | (B.lbo << 16);
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
+    for (int kk = 0; kk < KSTEPS; ++kk) {
       const uint32_t ah = L16 ? tmem_a + 16 * kk : tmem_a + 32 * (kk >> 1) + 8 * (kk & 1);
       const uint64_t bh = words_desc(b0 + kk * B.step, B.sbo);
       if (PASSES == 3) {  // small terms first
@@ -932,12 +932,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
 // one tile of 128 samples per CTA, + the get_action / evaluate epilogues of mlp_infer_kernel
 // (ppo.py:690-705, 725-737).  Used by the fused rollout and by the update's first evaluate when the handle's
 // precision is NAVPPO_BF16X3 / NAVPPO_BF16.
-//   warps 0 .. 4 EW - 1   epilogue: EW warps per TMEM lane quarter, 64 / EW columns of a half-chunk each;
+// A lone tile is a latency chain (wait, TMEM load, pack, TMEM store, arrive: ~0.45 us per step whatever its width),
+// so the steps are as wide as tensor memory allows: chunks of 128 hidden units (the backward pass's weight blobs,
+// which hold Wa with 128 rows and Wb with 128 k), 4 steps per block, three 128-column Z slots.  The k-order of
+// every accumulation is unchanged.
+//   warps 0 .. 4 EW - 1   epilogue: EW warps per TMEM lane quarter, 128 / EW columns of a chunk each;
 //                         warps 0-3 also own one sample row each
 //   warp 4 EW             issues every tcgen05.mma;   warp 4 EW + 1: one thread streams the weights (TMA ring)
 // ========================================================================================
 constexpr int INF_EW = 4;
-constexpr int INF_CW = HC / INF_EW;                          // columns of a half-chunk per epilogue warp
+constexpr int INF_CW = CH / INF_EW;                          // columns of a chunk per epilogue warp
+constexpr int INF_ZSLOTS = 3;
 constexpr int INF_EWARPS = 4 * INF_EW;
 constexpr int INF_W_TMA = INF_EWARPS + 1;                    // the MMA warp is the one before it
 constexpr int INF_THREADS = 32 * (INF_EWARPS + 2);
@@ -947,12 +952,21 @@ constexpr uint32_t IOFF_PAR = IOFF_BIAS + 2 * HID * 4;
 constexpr uint32_t IOFF_BAR = IOFF_PAR + 128 * 4;
 constexpr uint32_t INF_SMEM_BYTES = IOFF_BAR + 256;
 enum { I_ZFULL = 0, I_EFULL = 4, I_WFULL = 8, I_WFREE = 15, I_ACC = 22, I_XREADY = 23, I_COUNT = 24 };
+static_assert(INF_ZSLOTS * CH <= (int)TM_U, "Z slots must end below the U accumulator");
 
 struct WsInferArgs {
   InferArgs g;
   const unsigned char* wprep;
   int mode;
+  int weights_ready;  // chained launch: `wprep` was written before the predecessor started (not by it): stream it at once
+  long long* prof;    // diagnostic: nanosecond timestamps of CTA (0, 0)'s first row owner (navppo_tc_profile), else null
 };
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define ISTAMP(k) do { if (ta.prof && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) ta.prof[4096 + (k)] = global_ns(); } while (0)
 
 template <int PASSES>
 __global__ void __launch_bounds__(INF_THREADS, 1) mlp_infer_ws_kernel(WsInferArgs ta) {
@@ -969,9 +983,10 @@ __global__ void __launch_bounds__(INF_THREADS, 1) mlp_infer_ws_kernel(WsInferArg
   const float* __restrict__ p = a.params + (net ? NAVPPO_CRITIC_OFFSET : 0);
   const unsigned char* __restrict__ wblob_g = ta.wprep + (size_t)net * WS_NET_BLOB;
   const int tile = blockIdx.x;
+  ISTAMP(0);
 
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) { tc::mbar_init(bars + I_ZFULL + i, 1); tc::mbar_init(bars + I_EFULL + i, INF_EWARPS); }
+    for (int i = 0; i < INF_ZSLOTS; ++i) { tc::mbar_init(bars + I_ZFULL + i, 1); tc::mbar_init(bars + I_EFULL + i, INF_EWARPS); }
     for (int i = 0; i < NWSLOT; ++i) { tc::mbar_init(bars + I_WFULL + i, 1); tc::mbar_init(bars + I_WFREE + i, 1); }
     tc::mbar_init(bars + I_ACC, 1);
     tc::mbar_init(bars + I_XREADY, 4);
@@ -986,6 +1001,12 @@ __global__ void __launch_bounds__(INF_THREADS, 1) mlp_infer_ws_kernel(WsInferArg
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  ISTAMP(1);
+  // chained launch (rollout): everything above — it reads only the parameters — ran under the previous kernel's
+  // tail; the observations (and, first step, the re-tiled weights) are touched after this wait
+  if (!(warp == INF_W_TMA && ta.weights_ready)) asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  ISTAMP(2);
 
   if (warp < INF_EWARPS) {
     // ====================================================================== epilogue warps
@@ -1018,20 +1039,22 @@ __global__ void __launch_bounds__(INF_THREADS, 1) mlp_infer_ws_kernel(WsInferArg
       store8<PASSES>(sX, SX_PART, row, 0, x1);
       store8<PASSES>(sX, SX_PART, row, 8, x1 + 8);
       publish(bars + I_XREADY, true);
+      ISTAMP(3);
     }
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
       const int blk = pass;
 #pragma unroll 1
-      for (int h = 0; h < NHC; ++h) {
-        const int s = h & 3;
+      for (int c = 0; c < NCH; ++c) {
+        const int s = c % INF_ZSLOTS;
         tc::mbar_wait(bars + I_ZFULL + s, (pz >> s) & 1); pz ^= 1u << s;
         tc::fence_after_sync();
+        if (c == 0) ISTAMP(4 + 4 * pass);
         // H = lrelu(Z + ba) of this warp's INF_CW columns, packed over the columns it just read as the A operand
         // of U += H Wb^T: per 16 columns [hi: 8 packed words | lo: 8 packed words]
         const int c0 = ch * INF_CW;
-        const uint32_t tslot = trow + TM_ZG + s * 64;
-        const float* sBa = sBias + blk * HID + h * HC + c0;
+        const uint32_t tslot = trow + TM_ZG + s * CH;
+        const float* sBa = sBias + blk * HID + c * CH + c0;
         float v[INF_CW];
 #pragma unroll
         for (int i = 0; i < INF_CW; i += 16) tc::tmem_ld16_nowait(tslot + c0 + i, v + i);
@@ -1054,8 +1077,10 @@ __global__ void __launch_bounds__(INF_THREADS, 1) mlp_infer_ws_kernel(WsInferArg
         publish(bars + I_EFULL + s, false);
       }
       if (!owner) continue;
+      ISTAMP(5 + 4 * pass);
       tc::mbar_wait(bars + I_ACC, pass);              // every product of this pass has completed
       tc::fence_after_sync();
+      ISTAMP(6 + 4 * pass);
       if (pass == 0) {
         // block-1 output: u1 = x0 + U + bb, y1 = lrelu(u1) -> X columns 16..31
         float acc[16];
@@ -1065,6 +1090,7 @@ __global__ void __launch_bounds__(INF_THREADS, 1) mlp_infer_ws_kernel(WsInferArg
         store8<PASSES>(sX, SX_PART, row, 16, x1 + 16);
         store8<PASSES>(sX, SX_PART, row, 24, x1 + 24);
         publish(bars + I_XREADY, true);
+        ISTAMP(7);
       } else {
         float y2[X1];
         {
@@ -1128,10 +1154,11 @@ __global__ void __launch_bounds__(INF_THREADS, 1) mlp_infer_ws_kernel(WsInferArg
       int slot = 0;
       uint32_t pfree = (1u << NWSLOT) - 1;
 #pragma unroll 1
-      for (int i = 0; i < 2 * NHC; ++i) {
-        const int blk = i >> 3, h = i & 7;
+      for (int i = 0; i < 4 * NCH; ++i) {       // per block and chunk: [Wa hi | Wa lo], then [Wb hi | Wb lo]
+        const int blk = i >> 3, c = (i >> 1) & 3, part = i & 1;
+        const uint32_t half = 2 * cpart(blk ? X1 : OBS);
         tc::mbar_wait(bars + I_WFREE + slot, (pfree >> slot) & 1); pfree ^= 1u << slot;
-        tma_load(smem + IOFF_WF + slot * WSLOT, wblob_g + wblob_off(blk, h), wblob(blk ? X1 : OBS), bars + I_WFULL + slot);
+        tma_load(smem + IOFF_WF + slot * WSLOT, wblob_g + cblob_off(blk, c) + part * half, half, bars + I_WFULL + slot);
         slot = slot == NWSLOT - 1 ? 0 : slot + 1;
       }
     }
@@ -1141,8 +1168,8 @@ __global__ void __launch_bounds__(INF_THREADS, 1) mlp_infer_ws_kernel(WsInferArg
     constexpr uint32_t RG = ROWG >> 4;
     const Opnd Xk{aX >> 4, SX_PART >> 4, RG, 8, 2 * RG};
     uint32_t pe = 0, pw = 0;
-    int wz = 0, wu = 0;     // weight ring slot of the next Z / of the next U
-    auto next_slot = [](int s) { return s == NWSLOT - 1 ? 0 : s + 1; };
+    int wz = 0, wu = 1;     // weight ring slot of the next Z (a chunk's [Wa] load) / of the next U (its [Wb] load)
+    auto next2 = [](int s) { return s + 2 >= NWSLOT ? s + 2 - NWSLOT : s + 2; };
     auto wait_bar = [&](uint64_t* bar, uint32_t& parity_bits, int bit) {
       tc::mbar_wait(bar, (parity_bits >> bit) & 1);
       parity_bits ^= 1u << bit;
@@ -1151,54 +1178,60 @@ __global__ void __launch_bounds__(INF_THREADS, 1) mlp_infer_ws_kernel(WsInferArg
     for (int pass = 0; pass < 2; ++pass) {
       const int blk = pass;
       const int IN = blk ? X1 : OBS;
-      const uint32_t wp = wpart(IN);
-      const uint32_t id_z = tc::make_idesc_bf16(128, HC, 0, 0), id_u = tc::make_idesc_bf16(128, IN, 0, 0);
-      auto issue_z = [&](int h, int wslot) {
-        const int s = h & 3;
+      const uint32_t cp = cpart(IN);
+      const uint32_t id_z = tc::make_idesc_bf16(128, CH, 0, 0), id_u = tc::make_idesc_bf16(128, IN, 0, 0);
+      // Z of chunk c into slot c % 3: A = X (K-major), B = Wa (rows = the chunk's 128 hidden units, K-major), K = IN
+      auto issue_z = [&](int c, int wslot) {
+        const int s = c % INF_ZSLOTS;
         const uint32_t w = aWF + wslot * WSLOT;
-        const Opnd Wk{w >> 4, wp >> 4, HC, 8, 2 * HC};
-        if (blk) gemm<PASSES, 2>(tmem + TM_ZG + s * 64, Xk, Wk, id_z, false);
-        else gemm<PASSES, 1>(tmem + TM_ZG + s * 64, Xk, Wk, id_z, false);
+        const Opnd Wk{w >> 4, cp >> 4, CH, 8, 2 * CH};
+        if (blk) gemm<PASSES, 2>(tmem + TM_ZG + s * CH, Xk, Wk, id_z, false);
+        else gemm<PASSES, 1>(tmem + TM_ZG + s * CH, Xk, Wk, id_z, false);
         commit(bars + I_ZFULL + s);
+        commit(bars + I_WFREE + wslot);          // Z is the only reader of the chunk's [Wa] load
       };
       tc::mbar_wait(bars + I_XREADY, pass);
       {
         int w = wz;
-        for (int i = 0; i < 4; ++i) { wait_bar(bars + I_WFULL + w, pw, w); w = next_slot(w); }
+        for (int i = 0; i < INF_ZSLOTS; ++i) { wait_bar(bars + I_WFULL + w, pw, w); w = next2(w); }
       }
       tc::fence_after_sync();
       if (elect_one()) {
         int w = wz;
-        for (int i = 0; i < 4; ++i) { issue_z(i, w); w = next_slot(w); }
+        for (int i = 0; i < INF_ZSLOTS; ++i) { issue_z(i, w); w = next2(w); }
       }
       __syncwarp();
-      for (int i = 0; i < 4; ++i) wz = next_slot(wz);
+      for (int i = 0; i < INF_ZSLOTS; ++i) wz = next2(wz);
 #pragma unroll 1
-      for (int h = 0; h < NHC; ++h) {
-        const int s = h & 3;
+      for (int c = 0; c < NCH; ++c) {
+        const int s = c % INF_ZSLOTS;
         wait_bar(bars + I_EFULL + s, pe, s);
-        if (h + 4 < NHC) wait_bar(bars + I_WFULL + wz, pw, wz);
+        wait_bar(bars + I_WFULL + wu, pw, wu);
+        if (c + INF_ZSLOTS < NCH) wait_bar(bars + I_WFULL + wz, pw, wz);
         tc::fence_after_sync();
         if (elect_one()) {
+          // U += H Wb^T over the chunk's 128 hidden units: A = H (tensor memory), B = Wb (rows = output features, K-major)
           const uint32_t w = aWF + wu * WSLOT;
-          const Opnd Wbk{(w + 2 * wp) >> 4, wp >> 4, (uint32_t)IN, 8, 2u * IN};
-          gemm_ts<PASSES, true>(tmem + TM_U, tmem + TM_ZG + s * 64, Wbk, id_u, h > 0);
+          const Opnd Wbk{w >> 4, cp >> 4, (uint32_t)IN, 8, 2u * IN};
+          gemm_ts<PASSES, true, 8>(tmem + TM_U, tmem + TM_ZG + s * CH, Wbk, id_u, c > 0);
           commit(bars + I_WFREE + wu);
-          if (h + 4 < NHC) issue_z(h + 4, wz);
-          else if (h == NHC - 1) commit(bars + I_ACC);
+          if (c + INF_ZSLOTS < NCH) issue_z(c + INF_ZSLOTS, wz);
+          else if (c == NCH - 1) commit(bars + I_ACC);
         }
         __syncwarp();
-        wu = next_slot(wu);
-        if (h + 4 < NHC) wz = next_slot(wz);
+        wu = next2(wu);
+        if (c + INF_ZSLOTS < NCH) wz = next2(wz);
       }
     }
   }
+  ISTAMP(11);
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem, TM_COLS);
   }
+  ISTAMP(12);
 }
 
 }  // namespace
@@ -1225,12 +1258,23 @@ int navppo_tcws_prep_launch(const float* params, float* wprep, cudaStream_t s) {
 }
 
 // One inference pass on the tensor cores over weights already re-tiled into `wprep`.
-int navppo_tcws_infer_launch(const ppo::InferArgs& a, int mode, bool both_nets, int passes, const float* wprep, cudaStream_t s) {
-  WsInferArgs ta{a, reinterpret_cast<const unsigned char*>(wprep), mode};
-  const dim3 grid((a.T + 127) / 128, both_nets ? 2 : 1);
-  if (passes == 3) mlp_infer_ws_kernel<3><<<grid, INF_THREADS, INF_SMEM_BYTES, s>>>(ta);
-  else mlp_infer_ws_kernel<1><<<grid, INF_THREADS, INF_SMEM_BYTES, s>>>(ta);
-  NAV_CUDA_TRY(cudaGetLastError());
+// `chained`: programmatic dependent launch — the kernel may start under its predecessor's tail (it waits for the
+// predecessor before touching anything but the parameters and, with `weights_ready` — the predecessor is not the
+// kernel that re-tiled them — the weights).
+int navppo_tcws_infer_launch(const ppo::InferArgs& a, int mode, bool both_nets, int passes, const float* wprep, bool chained,
+                             bool weights_ready, cudaStream_t s) {
+  WsInferArgs ta{a, reinterpret_cast<const unsigned char*>(wprep), mode, weights_ready ? 1 : 0, g_prof};
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3((a.T + 127) / 128, both_nets ? 2 : 1);
+  lc.blockDim = dim3(INF_THREADS);
+  lc.dynamicSmemBytes = INF_SMEM_BYTES;
+  lc.stream = s;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  if (chained) { lc.attrs = &attr; lc.numAttrs = 1; }
+  if (passes == 3) NAV_CUDA_TRY(cudaLaunchKernelEx(&lc, mlp_infer_ws_kernel<3>, ta));
+  else NAV_CUDA_TRY(cudaLaunchKernelEx(&lc, mlp_infer_ws_kernel<1>, ta));
   return NAVSIM_OK;
 }
 

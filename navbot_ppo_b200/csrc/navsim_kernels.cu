@@ -446,6 +446,15 @@ __device__ __forceinline__ float sanitised_range(float q, float rmin, float rmax
 
 extern __shared__ __align__(16) unsigned char dyn_smem[];
 
+// Programmatic dependent launch (the rollout chains policy and step kernels): a kernel launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor is still running; it must
+// not touch what the predecessor writes before this wait (which returns once the predecessor has completed and
+// its writes are visible), and then lets ITS successor start early.  Both are no-ops in an ordinary launch.
+__device__ __forceinline__ void grid_dependency_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------------------------
 // Env.step for all agents, `nsteps` consecutive steps per launch.
 //   G        lanes per agent (1, 2, 4, .. 32): the host picks it from N so that small batches
@@ -475,6 +484,7 @@ __global__ void __launch_bounds__(kBlock, KB != NAVSIM_LIDAR_FEATS ? 1 : (G == 1
   uint16_t* s_list = reinterpret_cast<uint16_t*>(s_cnt + APB);
   stage_map(s_map, g_map, map_bytes, bar);
   const MapView mv = map_view(s_map, c.B, c.S);
+  grid_dependency_wait();   // chained launch (rollout): everything above ran under the previous kernel's tail
 
   const int lane = threadIdx.x & 31;
   const int g = threadIdx.x & (G - 1);
@@ -658,6 +668,7 @@ __global__ void __launch_bounds__(kBlock) navsim_step_anybeam_kernel(SimConst c,
   float* s_obs = reinterpret_cast<float*>(dyn_smem + 16 + map_bytes);
   stage_map(s_map, g_map, map_bytes, bar);
   const MapView mv = map_view(s_map, c.B, c.S);
+  grid_dependency_wait();
   int* s_cnt = reinterpret_cast<int*>(s_obs + APB * kObsPad);
   const int g = threadIdx.x & 31, slot = threadIdx.x >> 5;
   uint16_t* my_list = reinterpret_cast<uint16_t*>(s_cnt + APB) + (size_t)slot * c.S;
@@ -1049,7 +1060,8 @@ step_kernel_t step_kernel_of(const navsim* h, bool scripted) {
 }
 
 // One launch = `nsteps` consecutive Env.step calls for every agent.
-int launch_step(navsim* h, const StepIO& io, cudaStream_t s, bool scripted, uint64_t action_seed, int nsteps) {
+int launch_step(navsim* h, const StepIO& io, cudaStream_t s, bool scripted, uint64_t action_seed, int nsteps,
+                bool chained = false) {
   if (nsteps < 1) return NAVSIM_OK;
   const size_t smem = step_smem_bytes(h);
   const int g = lanes_of(h);
@@ -1057,12 +1069,18 @@ int launch_step(navsim* h, const StepIO& io, cudaStream_t s, bool scripted, uint
   const dim3 grid((h->c.N + apb - 1) / apb), block(kBlock);
   const uint32_t script_step = scripted ? h->script_step : 0u;
   if (scripted) h->script_step += (uint32_t)nsteps;
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = s;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  if (chained) { lc.attrs = &attr; lc.numAttrs = 1; }
   if (variant_of(h) == 2) {
-    navsim_step_anybeam_kernel<<<grid, block, smem, s>>>(h->c, h->st, h->d_map, h->d_rt, io, h->d_stats, action_seed,
-                                                         script_step, nsteps, scripted ? 1 : 0);
+    CUDA_TRY(cudaLaunchKernelEx(&lc, navsim_step_anybeam_kernel, h->c, h->st, (const float*)h->d_map, (const uint16_t*)h->d_rt, io,
+                                h->d_stats, action_seed, script_step, nsteps, scripted ? 1 : 0));
   } else {
-    step_kernel_of(h, scripted)<<<grid, block, smem, s>>>(h->c, h->st, h->d_map, h->d_rt, io, h->d_stats, action_seed,
-                                                          script_step, nsteps);
+    CUDA_TRY(cudaLaunchKernelEx(&lc, step_kernel_of(h, scripted), h->c, h->st, (const float*)h->d_map, (const uint16_t*)h->d_rt, io,
+                                h->d_stats, action_seed, script_step, nsteps));
   }
   h->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -1412,6 +1430,22 @@ int navsim_step_ex(navsim_t* h, const float* act_dev, const navsim_step_out* out
   io.ep_len = out->ep_len;
   return launch_step(h, io, (cudaStream_t)stream, false, 0, 1);
 }
+
+}  // extern "C"
+
+// navsim_step_ex as a programmatic dependent launch (internal: navppo_rollout_ex chains it behind the policy kernel)
+int navsim_step_chained(navsim_t* h, const float* act_dev, const navsim_step_out* out, void* stream) {
+  if (int rc = check_ready(h)) return rc;
+  if (int rc = begin_device_call(h, (cudaStream_t)stream)) return rc;
+  if (!act_dev || !out || !out->obs || !out->rew || !out->done || !out->arrive) return fail(NAVSIM_EINVAL, "null buffer");
+  StepIO io = make_io(act_dev, out->obs, out->rew, out->done, out->arrive, out->trunc, 0, 0);
+  io.ep_ret = out->ep_return;
+  io.ep_path = out->ep_path;
+  io.ep_len = out->ep_len;
+  return launch_step(h, io, (cudaStream_t)stream, false, 0, 1, true);
+}
+
+extern "C" {
 
 int navsim_step_scripted(navsim_t* h, int32_t num_steps, uint64_t action_seed, float* obs_dev, float* rew_dev,
                          uint8_t* done_dev, uint8_t* arrive_dev, void* stream) {

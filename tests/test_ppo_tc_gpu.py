@@ -166,3 +166,70 @@ def test_warp_specialised_kernel_is_bit_identical_to_the_single_role_kernel(T, p
     assert torch.equal(out[0][0], out[1][0])
     assert np.array_equal(out[0][1], out[1][1])
     assert float(out[1][0].abs().max()) > 0
+
+
+# ---------------------------------------------------------------------------------------- tensor-core inference
+def _infer_all(h, flat, obs, act_in, noise, var):
+    L = _capi.lib()
+    T = obs.shape[0]
+    z = lambda *s: torch.zeros(*s, device=DEV)  # noqa: E731
+    out = dict(mu=z(T, 2), v=z(T), act=z(T, 2), lp=z(T), mu_act=z(T, 2), v_ev=z(T), lp_ev=z(T))
+    _capi.check(L.navppo_forward(h, flat.data_ptr(), obs.data_ptr(), T, out["mu"].data_ptr(), out["v"].data_ptr(), _sp()))
+    _capi.check(L.navppo_act(h, flat.data_ptr(), obs.data_ptr(), T, var, 7, 0, 3, noise.data_ptr(), out["act"].data_ptr(),
+                             out["lp"].data_ptr(), out["mu_act"].data_ptr(), _sp()))
+    _capi.check(L.navppo_evaluate(h, flat.data_ptr(), obs.data_ptr(), act_in.data_ptr(), T, var, out["v_ev"].data_ptr(),
+                                  out["lp_ev"].data_ptr(), _sp()))
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("prec,tol", [(_capi.PREC_BF16X3, 2e-5), (_capi.PREC_BF16, 2e-2)])
+@pytest.mark.parametrize("T", [1, 127, 128, 129, 5000])
+def test_tc_inference_matches_the_float64_oracle(T, prec, tol):
+    """forward / get_action / evaluate of a tensor-core handle (mlp_infer_ws_kernel) against the float64 restatement
+    of net_actor.py / net_critic.py / ppo.py:690-737, ragged sizes.  Tolerance relative to 1 + max |reference|:
+    2e-5 for split-bf16 operands (measured ~5e-6), 2e-2 for plain bf16 (measured ~2e-3)."""
+    g = golden("ppo_learn_b")
+    rng = np.random.RandomState(T)
+    idx = rng.randint(0, len(g["obs"]), T)
+    obs = (g["obs"][idx] + rng.normal(scale=0.01, size=(T, 16))).astype(np.float32)
+    acts = np.ascontiguousarray(g["acts"][idx])
+    noise = rng.normal(size=(T, 2)).astype(np.float32)
+    var = float(g["var"])
+    h = _Handles.get(torch.device(DEV), 1 << 16, 0.2, 3e-4, prec)
+    flat = _flat_from(g["actor_after"], g["critic_after"])
+    out = _infer_all(h, flat, _t(obs), _t(acts), _t(noise), var)
+    v_ref, lp_ref = po.evaluate(g["actor_after"], g["critic_after"], obs, acts, var)
+    mu_ref = po.actor_forward(g["actor_after"], obs)
+    close = lambda got, want: np.abs(got.cpu().numpy() - want).max() <= tol * (1.0 + np.abs(want).max())  # noqa: E731
+    assert close(out["mu"], mu_ref) and close(out["v"], v_ref) and close(out["v_ev"], v_ref) and close(out["lp_ev"], lp_ref)
+    assert torch.equal(out["mu"], out["mu_act"]) and torch.equal(out["v"], out["v_ev"])
+    # get_action: a = clamp(mu + sqrt(var) eps), log-prob at the clamped action (ppo.py:698-704)
+    a_ref = mu_ref + np.sqrt(var) * noise
+    a_ref[:, 0] = np.clip(a_ref[:, 0], 0.0, 1.0); a_ref[:, 1] = np.clip(a_ref[:, 1], -1.0, 1.0)
+    assert close(out["act"], a_ref)
+    _, lp_act_ref = po.evaluate(g["actor_after"], g["critic_after"], obs, out["act"].cpu().numpy(), var)
+    assert close(out["lp"], lp_act_ref)
+
+
+@pytest.mark.parametrize("prec", [_capi.PREC_BF16X3, _capi.PREC_BF16])
+def test_rollout_log_probs_are_bit_identical_to_what_the_update_recomputes(prec):
+    """The inference kernel is the forward half of the gradient kernel: with unchanged weights the update's
+    ratio exp(logp - logp_old) is exactly 1 for every sample — approx-KL and clip fraction are exactly 0
+    (ppo.py:316,326,335) — wherever a sample sits in its tile."""
+    g = golden("ppo_learn_b")
+    T = 3 * 128 + 77
+    rng = np.random.RandomState(5)
+    idx = rng.randint(0, len(g["obs"]), T)
+    obs = _t((g["obs"][idx] + rng.normal(scale=0.01, size=(T, 16))).astype(np.float32))
+    var = float(g["var"])
+    h = _Handles.get(torch.device(DEV), 1 << 16, 0.2, 3e-4, prec)
+    flat = _flat_from(g["actor_after"], g["critic_after"])
+    act = torch.zeros(T, 2, device=DEV); lp = torch.zeros(T, device=DEV)
+    _capi.check(_capi.lib().navppo_act(h, flat.data_ptr(), obs.data_ptr(), T, var, 11, 0, 0, None, act.data_ptr(), lp.data_ptr(),
+                                       None, _sp()))
+    perm = torch.from_numpy(rng.permutation(T)).to(DEV)            # the update sees the samples at other tile rows
+    adv = _t(rng.normal(size=T).astype(np.float32)); rtg = _t(rng.normal(size=T).astype(np.float32))
+    _, m = _grad(h, flat, obs[perm].contiguous(), act[perm].contiguous(), lp[perm].contiguous(), adv, rtg, T, var)
+    assert m[_capi.M_APPROX_KL] == 0.0 and m[_capi.M_CLIP_FRAC] == 0.0
+    assert abs(m[_capi.M_ACTOR_LOSS] + float(adv.double().mean())) < 1e-6        # every surrogate is exactly 1 * A
