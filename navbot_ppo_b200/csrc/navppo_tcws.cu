@@ -272,7 +272,6 @@ __device__ __forceinline__ void red_add4(float* addr, float a, float b, float c,
 __device__ __forceinline__ void red_add1(float* addr, float a) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
 }
-__device__ __forceinline__ float lrelu_fast(float x) { return fmaxf(x, LEAK * x); }
 
 // Sums over the 32 lanes of a warp of V per-lane values at once: every round hands half of the values to
 // the partner lane (the pairs and their order are those of the xor butterfly 16, 8, 4, 2, 1, so each
@@ -450,13 +449,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
             tc::tmem_ld_wait();
             uint32_t hi[16], lo[16];
 #pragma unroll
-            for (int i4 = 0; i4 < 8; ++i4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(sBa + 4 * i4);
-              const float h0 = lrelu_fast(v[4 * i4] + b4.x), h1 = lrelu_fast(v[4 * i4 + 1] + b4.y);
-              const float h2 = lrelu_fast(v[4 * i4 + 2] + b4.z), h3 = lrelu_fast(v[4 * i4 + 3] + b4.w);
-              tc::split_bf16x2(h0, h1, &hi[2 * i4], &lo[2 * i4]);
-              tc::split_bf16x2(h2, h3, &hi[2 * i4 + 1], &lo[2 * i4 + 1]);
-            }
+            for (int i4 = 0; i4 < 8; ++i4)
+              tc::bias_lrelu_split4(v + 4 * i4, *reinterpret_cast<const float4*>(sBa + 4 * i4), LEAK, hi + 2 * i4, lo + 2 * i4);
             tc::tmem_st16(tz, hi);
             if (PASSES == 3) tc::tmem_st16(tz + 16, lo);
             tc::tmem_st_wait();
@@ -474,18 +468,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
             tc::tmem_ld16_nowait(tz + 80, g + 16);
             tc::tmem_ld_wait();
             uint32_t hh[16], hl[16], gh[16], gl[16];
+            const uint64_t ba2 = tc::pack2(ba, ba);
 #pragma unroll
             for (int i2 = 0; i2 < 16; ++i2) {
-#pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                const int i = 2 * i2 + k;
-                const float zz = z[i] + ba;
-                const float sl = zz > 0.f ? 1.f : LEAK;       // LeakyReLU slope: h = zz * slope, g_z = g_h * slope
-                z[i] = zz * sl;
-                g[i] = g[i] * sl;
-              }
-              tc::split_bf16x2(z[2 * i2], z[2 * i2 + 1], &hh[i2], &hl[i2]);
-              tc::split_bf16x2(g[2 * i2], g[2 * i2 + 1], &gh[i2], &gl[i2]);
+              // LeakyReLU slope per value: h = zz * slope, g_z = g_h * slope (two values per instruction)
+              const uint64_t zz = tc::add2(tc::pack2(z[2 * i2], z[2 * i2 + 1]), ba2);
+              float za, zb;
+              tc::unpack2(zz, za, zb);
+              const uint64_t sl = tc::pack2(za > 0.f ? 1.f : LEAK, zb > 0.f ? 1.f : LEAK);
+              float ha, hb, ga, gb;
+              tc::unpack2(tc::mul2(zz, sl), ha, hb);
+              tc::unpack2(tc::mul2(tc::pack2(g[2 * i2], g[2 * i2 + 1]), sl), ga, gb);
+              tc::split_bf16x2(ha, hb, &hh[i2], &hl[i2]);
+              tc::split_bf16x2(ga, gb, &gh[i2], &gl[i2]);
             }
             tc::tmem_st16(tz, hh);
             tc::tmem_st16(tz + 64, gh);
@@ -1061,13 +1056,8 @@ __global__ void __launch_bounds__(INF_THREADS, 1) mlp_infer_ws_kernel(WsInferArg
         tc::tmem_ld_wait();
         uint32_t hi[INF_CW / 2], lo[INF_CW / 2];
 #pragma unroll
-        for (int i4 = 0; i4 < INF_CW / 4; ++i4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(sBa + 4 * i4);
-          const float h0 = lrelu_fast(v[4 * i4] + b4.x), h1 = lrelu_fast(v[4 * i4 + 1] + b4.y);
-          const float h2 = lrelu_fast(v[4 * i4 + 2] + b4.z), h3 = lrelu_fast(v[4 * i4 + 3] + b4.w);
-          tc::split_bf16x2(h0, h1, &hi[2 * i4], &lo[2 * i4]);
-          tc::split_bf16x2(h2, h3, &hi[2 * i4 + 1], &lo[2 * i4 + 1]);
-        }
+        for (int i4 = 0; i4 < INF_CW / 4; ++i4)
+          tc::bias_lrelu_split4(v + 4 * i4, *reinterpret_cast<const float4*>(sBa + 4 * i4), LEAK, hi + 2 * i4, lo + 2 * i4);
 #pragma unroll
         for (int j = 0; j < INF_CW / 16; ++j) {
           tc::tmem_st8(tslot + c0 + 16 * j, hi + 8 * j);

@@ -195,14 +195,48 @@ __device__ __forceinline__ void split_bf16(float x, uint16_t* hi, uint16_t* lo) 
   asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(l) : "f"(x - hf));
   *hi = h; *lo = l;
 }
+// ---- packed fp32 pairs (FADD2 / FMUL2: one issue slot for two IEEE operations — the epilogues are issue-bound)
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 // two floats -> packed bf16x2 (lo half = a, hi half = b) and the packed residuals
 __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t* hi, uint32_t* lo) {
   uint32_t h;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
-  const float ha = __uint_as_float(h << 16), hb = __uint_as_float(h & 0xFFFF0000u);
+  float la, lb;
+  unpack2(sub2(pack2(a, b), pack2(__uint_as_float(h << 16), __uint_as_float(h & 0xFFFF0000u))), la, lb);
   uint32_t l;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(b - hb), "f"(a - ha));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(lb), "f"(la));
   *hi = h; *lo = l;
+}
+// H = lrelu(v + b) of four values (slope `leak` < 1: lrelu(x) = max(x, leak x)), packed: hi[0..1], lo[0..1]
+__device__ __forceinline__ void bias_lrelu_split4(const float* v, float4 b, float leak, uint32_t* hi, uint32_t* lo) {
+  const uint64_t lk = pack2(leak, leak);
+  const uint64_t p0 = add2(pack2(v[0], v[1]), pack2(b.x, b.y)), p1 = add2(pack2(v[2], v[3]), pack2(b.z, b.w));
+  const uint64_t q0 = mul2(p0, lk), q1 = mul2(p1, lk);
+  float x0, x1, x2, x3, y0, y1, y2, y3;
+  unpack2(p0, x0, x1); unpack2(p1, x2, x3); unpack2(q0, y0, y1); unpack2(q1, y2, y3);
+  split_bf16x2(fmaxf(x0, y0), fmaxf(x1, y1), &hi[0], &lo[0]);
+  split_bf16x2(fmaxf(x2, y2), fmaxf(x3, y3), &hi[1], &lo[1]);
 }
 
 }  // namespace tc
