@@ -27,8 +27,11 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler",
 UNITS = [
     ("navsim_kernels.cu", ["-fmad=false"]),
     ("navppo_kernels.cu", []),
-    ("navppo_tc.cu", []),
-    ("navppo_tcws.cu", []),
+    # -fmad=false: navppo_tcws.cu steps the simulator inside its fused rollout kernel (navsim_device.cuh), whose fp64
+    # chains must round exactly like navsim_kernels.cu's; navppo_tc.cu is its bit-exact cross-check and follows suit
+    # (every fused multiply-add of the network arithmetic is an explicit fmaf)
+    ("navppo_tc.cu", ["-fmad=false"]),
+    ("navppo_tcws.cu", ["-fmad=false"]),
 ]
 
 
@@ -57,12 +60,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if not os.path.exists(spath):
             continue
         opath = os.path.join(OBJ, src.replace(".cu", ".o"))
-        if force or _stale(opath, [spath] + headers):
-            cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", spath, "-o", opath]
+        cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", spath, "-o", opath]
+        stamp = opath + ".cmd"                       # a changed command line (flags) rebuilds too
+        same_cmd = os.path.exists(stamp) and open(stamp).read() == " ".join(cmd)
+        if force or not same_cmd or _stale(opath, [spath] + headers):
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), flush=True)
             subprocess.run(cmd, check=True)
+            with open(stamp, "w") as f:
+                f.write(" ".join(c for c in cmd if c != "-Xptxas=-v"))
         objs.append(opath)
     if force or _stale(LIB, objs):
         cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "--cudart", "static", "-Xlinker", "--no-undefined",

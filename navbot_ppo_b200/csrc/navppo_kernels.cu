@@ -42,6 +42,10 @@ int navppo_tcws_init();
 int navppo_tcws_prep_launch(const float* params, float* wprep, cudaStream_t s);
 int navppo_tcws_infer_launch(const ppo::InferArgs& a, int mode, bool both_nets, int passes, const float* wprep, bool chained,
                              bool weights_ready, cudaStream_t s);
+// the whole step loop of a rollout as one launch (navppo_tcws.cu); *unsupported = 1: fall back to chained kernels
+int navppo_tcws_rollout_launch(navsim_t* sim, const ppo::InferArgs& a, int H, int passes, const float* wprep, float* obs_rows,
+                               float* next_obs, float* rew, uint8_t* done, uint8_t* arrive, uint8_t* trunc, float* ep_ret,
+                               float* ep_path, int32_t* ep_len, int* unsupported, cudaStream_t s);
 // navsim_step_ex as a programmatic dependent launch (navsim_kernels.cu)
 int navsim_step_chained(navsim_t* h, const float* act_dev, const navsim_step_out* out, void* stream);
 
@@ -799,6 +803,7 @@ struct navppo {
   float* grad_ws = nullptr;   // [NAVPPO_FLAT] used by navppo_update
   float* wprep = nullptr;     // tensor-core path: pre-split, pre-tiled weights
   bool tc_single_role = false;  // NAVPPO_TC_KERNEL=single: the first (single-role) tcgen05 kernel, kept as a cross-check
+  bool fused_rollout = false;   // rollout: ONE persistent launch, each CTA keeps 128 robots for all H steps (NAVPPO_ROLLOUT_FUSED=0: off)
   bool chain = false;           // rollout: policy and step kernels as programmatic dependent launches (NAVPPO_ROLLOUT_CHAIN=0: plain)
   bool tc_infer = false;        // tensor-core precision: the rollout's and the update's forward passes run on the tensor cores
                                 // too (NAVPPO_TC_INFER=0 keeps them on the fp32 CUDA-core kernel)
@@ -888,6 +893,8 @@ int navppo_create(navppo_t** out, const navppo_cfg* cfg) {
     h->tc_single_role = which && std::string(which) == "single";
     const char* ti = std::getenv("NAVPPO_TC_INFER");
     h->tc_infer = !(ti && std::string(ti) == "0");
+    const char* fr = std::getenv("NAVPPO_ROLLOUT_FUSED");
+    h->fused_rollout = h->tc_infer && !(fr && std::string(fr) == "0");
     const char* ch = std::getenv("NAVPPO_ROLLOUT_CHAIN");
     h->chain = !(ch && std::string(ch) == "0");
     const size_t wb = navppo_tc_prep_bytes() > navppo_tcws_prep_bytes() ? navppo_tc_prep_bytes() : navppo_tcws_prep_bytes();
@@ -1106,6 +1113,16 @@ int navppo_rollout_ex(navppo_t* h, navsim_t* sim, const float* params, int32_t H
   if (h->tc_infer) {   // the policy does not change inside a rollout: re-tile its weights once
     if (int rc = navppo_tcws_prep_launch(params, h->wprep, (cudaStream_t)stream)) return rc;
     h->launches++;
+  }
+  if (h->fused_rollout) {
+    InferArgs a{};
+    a.params = params; a.obs = obs; a.T = (int)N; a.var = (float)var; a.seed = seed; a.agent_off = agent_id_offset;
+    a.draw = draw0; a.act = act; a.logp = logp; a.dyn = dyn_dev;
+    int unsupported = 0;
+    const int rc = navppo_tcws_rollout_launch(sim, a, H, tc_passes, h->wprep, obs, next_obs, rew, done, arrive, trunc, ep_return,
+                                              ep_path, ep_len, &unsupported, (cudaStream_t)stream);
+    if (rc == NAVSIM_OK) { h->launches++; return NAVSIM_OK; }
+    if (!unsupported) return rc;
   }
   for (int t = 0; t < H; ++t) {
     float* o_t = obs + (size_t)t * N * OBS;

@@ -41,6 +41,7 @@
 
 #include "../../include/navppo.h"
 #include "nav_common.h"
+#include "navsim_device.cuh"
 #include "navsim_math.h"
 #include "ppo_common.cuh"
 #include "tc_common.cuh"
@@ -950,12 +951,36 @@ enum { I_ZFULL = 0, I_EFULL = 4, I_WFULL = 8, I_WFREE = 15, I_ACC = 22, I_XREADY
 static_assert(INF_ZSLOTS * CH <= (int)TM_U, "Z slots must end below the U accumulator");
 
 struct WsInferArgs {
+  static constexpr bool kFused = false;
   InferArgs g;
   const unsigned char* wprep;
   int mode;
   int weights_ready;  // chained launch: `wprep` was written before the predecessor started (not by it): stream it at once
   long long* prof;    // diagnostic: nanosecond timestamps of CTA (0, 0)'s first row owner (navppo_tc_profile), else null
 };
+// The fused rollout: the same kernel keeps its 128 robots for H steps — policy forward, sample, Env.step by the
+// same 512 threads (4 lanes per robot, navsim_device.cuh), next observation straight from shared memory.  Robots are
+// independent, so the CTAs never synchronise with each other and nothing but the rollout rows leaves the SM.
+struct WsFusedArgs : WsInferArgs {
+  static constexpr bool kFused = true;
+  navsim_dev::SimConst c;
+  navsim_dev::SimState st;
+  const float* g_map;
+  const uint16_t* rt_tab;
+  navsim_dev::DevStats* stats;
+  int H;
+  float* obs_rows;     // [H, N, 16]: row t = the observation step t acts on (row 0 filled by the caller)
+  float* next_obs;     // [N, 16]
+  float* rew; uint8_t* done; uint8_t* arrive; uint8_t* trunc;   // [H, N]
+  float* ep_ret; float* ep_path; int32_t* ep_len;               // [H, N] or null
+};
+constexpr uint32_t IOFF_SIM = IOFF_BAR + 256;                  // fused: [map mbarrier 16 B][actions 128 x 8 B][obs tile][map]
+constexpr uint32_t FUSED_MAP_MAX = 8192;
+constexpr uint32_t IOFF_SACT = IOFF_SIM + 16;
+constexpr uint32_t IOFF_SOBS = IOFF_SACT + 128 * 8;
+constexpr uint32_t IOFF_SMAP = IOFF_SOBS + 128 * navsim_dev::kObsPad * 4;
+constexpr uint32_t FUSED_SMEM_BYTES = IOFF_SMAP + FUSED_MAP_MAX;
+constexpr int FUSED_G = 4;                                     // lanes per robot: 128 robots x 4 = the 16 epilogue warps
 __device__ __forceinline__ long long global_ns() {
   long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -963,9 +988,12 @@ __device__ __forceinline__ long long global_ns() {
 }
 #define ISTAMP(k) do { if (ta.prof && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) ta.prof[4096 + (k)] = global_ns(); } while (0)
 
-template <int PASSES>
-__global__ void __launch_bounds__(INF_THREADS, 1) mlp_infer_ws_kernel(WsInferArgs ta) {
+template <int PASSES, class Args>
+__global__ void __launch_bounds__(INF_THREADS, 1) mlp_infer_ws_kernel(Args ta) {
+  constexpr bool FUSED = Args::kFused;
   const InferArgs& a = ta.g;
+  int H = 1;
+  if constexpr (FUSED) H = ta.H;
   const int net = blockIdx.y;
   if (ta.mode == INFER_FORWARD && ((net == 0 && !a.mu) || (net == 1 && !a.v))) return;
   unsigned char* smem = ws_smem;
@@ -985,6 +1013,12 @@ __global__ void __launch_bounds__(INF_THREADS, 1) mlp_infer_ws_kernel(WsInferArg
     for (int i = 0; i < NWSLOT; ++i) { tc::mbar_init(bars + I_WFULL + i, 1); tc::mbar_init(bars + I_WFREE + i, 1); }
     tc::mbar_init(bars + I_ACC, 1);
     tc::mbar_init(bars + I_XREADY, 4);
+    if constexpr (FUSED) {   // the obstacle set: one bulk copy, waited on before the first Env.step
+      uint64_t* map_bar = reinterpret_cast<uint64_t*>(smem + IOFF_SIM);
+      tc::mbar_init(map_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      tma_load(smem + IOFF_SMAP, reinterpret_cast<const unsigned char*>(ta.g_map), navsim_dev::map_bytes_of(ta.c.B, ta.c.S), map_bar);
+    }
   }
   if (warp == 0) tc::tmem_alloc(tmem_slot, TM_COLS);
   for (int i = tid; i < 2 * HID; i += INF_THREADS) sBias[i] = p[(i < HID ? O_B1A : O_B2A - HID) + i];
@@ -1018,6 +1052,23 @@ __global__ void __launch_bounds__(INF_THREADS, 1) mlp_infer_ws_kernel(WsInferArg
       __syncwarp();
       if (lane == 0) mbar_arrive(bar);
     };
+    // fused rollout: this thread is also lane g of robot `slot` (4 lanes per robot)
+    [[maybe_unused]] const int slot = tid >> 2, g = tid & (FUSED_G - 1);
+    [[maybe_unused]] int ai = 0;
+    [[maybe_unused]] bool sim_valid = false, sim_writer = false, goal_dirty = false;
+    [[maybe_unused]] navsim_dev::Agent ag;
+    [[maybe_unused]] navsim_dev::MapView mv;
+    [[maybe_unused]] float* s_obs = reinterpret_cast<float*>(smem + IOFF_SOBS);
+    [[maybe_unused]] float2* s_act = reinterpret_cast<float2*>(smem + IOFF_SACT);
+    if constexpr (FUSED) {
+      const int ai_raw = tile * 128 + slot;
+      sim_valid = ai_raw < ta.c.N;
+      ai = sim_valid ? ai_raw : ta.c.N - 1;            // surplus lanes shadow the last robot and store nothing
+      sim_writer = sim_valid && g == 0;
+      navsim_dev::load_agent(ta.st, ai, &ag);
+      mv = navsim_dev::map_view(reinterpret_cast<const float*>(smem + IOFF_SMAP), ta.c.B, ta.c.S);
+      tc::mbar_wait(reinterpret_cast<uint64_t*>(smem + IOFF_SIM), 0);
+    }
     float x1[X1];
     if (owner) {
       if (si < a.T) {
@@ -1031,6 +1082,10 @@ __global__ void __launch_bounds__(INF_THREADS, 1) mlp_infer_ws_kernel(WsInferArg
 #pragma unroll
         for (int k = 0; k < OBS; ++k) x1[k] = 0.f;
       }
+    }
+#pragma unroll 1
+    for (int t = 0; t < H; ++t) {
+    if (owner) {
       store8<PASSES>(sX, SX_PART, row, 0, x1);
       store8<PASSES>(sX, SX_PART, row, 8, x1 + 8);
       publish(bars + I_XREADY, true);
@@ -1102,12 +1157,13 @@ __global__ void __launch_bounds__(INF_THREADS, 1) mlp_infer_ws_kernel(WsInferArg
 #pragma unroll
           for (int k = 0; k < X1; ++k) { o1 = fmaf(hw[k], y2[k], o1); o2 = fmaf(hw[X1 + 1 + k], y2[k], o2); }
           const float m0 = sigmoidf_(o1), m1 = tanhf(o2);  // net_actor.py:141-142
+          if constexpr (FUSED) if (!valid) s_act[row] = make_float2(0.f, 0.f);
           if (valid) {
             if (ta.mode == INFER_FORWARD) {
               reinterpret_cast<float2*>(a.mu)[si] = make_float2(m0, m1);
             } else if (ta.mode == INFER_ACT) {
               const float var_ = a.dyn ? __uint_as_float(a.dyn[0]) : a.var;
-              const uint32_t draw_ = a.dyn ? a.draw + a.dyn[1] : a.draw;
+              const uint32_t draw_ = (a.dyn ? a.draw + a.dyn[1] : a.draw) + (uint32_t)t;
               float e0, e1;
               if (a.noise_in) {
                 const float2 e = reinterpret_cast<const float2*>(a.noise_in)[si];
@@ -1128,9 +1184,10 @@ __global__ void __launch_bounds__(INF_THREADS, 1) mlp_infer_ws_kernel(WsInferArg
               float a0 = fmaf(sd, e0, m0), a1 = fmaf(sd, e1, m1);       // dist.sample(), ppo.py:698-699
               a0 = fminf(fmaxf(a0, 0.f), 1.f);                          // ppo.py:701
               a1 = fminf(fmaxf(a1, -1.f), 1.f);                         // ppo.py:702
-              reinterpret_cast<float2*>(a.act)[si] = make_float2(a0, a1);
-              a.logp[si] = gauss_logp(a0, a1, m0, m1, var_);            // ppo.py:704 (at the clamped action)
+              reinterpret_cast<float2*>(a.act)[(size_t)t * a.T + si] = make_float2(a0, a1);
+              a.logp[(size_t)t * a.T + si] = gauss_logp(a0, a1, m0, m1, var_);   // ppo.py:704 (at the clamped action)
               if (a.mu) reinterpret_cast<float2*>(a.mu)[si] = make_float2(m0, m1);
+              if constexpr (FUSED) s_act[row] = make_float2(a0, a1);
             } else {
               const float2 av = reinterpret_cast<const float2*>(a.act_in)[si];
               a.logp[si] = gauss_logp(av.x, av.y, m0, m1, a.var);       // ppo.py:734-735
@@ -1139,10 +1196,49 @@ __global__ void __launch_bounds__(INF_THREADS, 1) mlp_infer_ws_kernel(WsInferArg
         }
       }
     }
+    if constexpr (FUSED) {
+      // ------------------------------------------------------------------ Env.step of this CTA's 128 robots
+      named_sync(2, 32 * INF_EWARPS);                 // every row's action is in shared memory
+      const float2 av = s_act[slot];
+      navsim_dev::StepRows rows;
+      {
+        const size_t vo = (size_t)t * ta.c.N;
+        rows.rew = ta.rew + vo; rows.done = ta.done + vo; rows.arrive = ta.arrive + vo;
+        rows.trunc = ta.trunc ? ta.trunc + vo : nullptr;
+        rows.ep_ret = ta.ep_ret ? ta.ep_ret + vo : nullptr;
+        rows.ep_path = ta.ep_path ? ta.ep_path + vo : nullptr;
+        rows.ep_len = ta.ep_len ? ta.ep_len + vo : nullptr;
+      }
+      navsim_dev::agent_step<FUSED_G, NAVSIM_LIDAR_FEATS, false>(
+          ta.c, mv, ta.rt_tab, ta.stats, ag, av.x, av.y, g, ai, (uint64_t)(ta.c.agent_off + ai), sim_valid, sim_writer,
+          s_obs + slot * navsim_dev::kObsPad, nullptr, nullptr, rows, nullptr, goal_dirty);
+      named_sync(2, 32 * INF_EWARPS);                 // every robot's next observation row is in shared memory
+      {
+        // each warp writes out the rows of its own 8 robots as 128-bit stores; the row owners keep theirs for the
+        // next forward pass
+        float* dst = (t + 1 < H) ? ta.obs_rows + (size_t)(t + 1) * ta.c.N * OBS : ta.next_obs;
+        const int r = warp * 8 + (lane >> 2), qq = (lane & 3) * 4;
+        if (tile * 128 + r < ta.c.N) {
+          const float* src = s_obs + r * navsim_dev::kObsPad + qq;
+          reinterpret_cast<float4*>(dst + (size_t)(tile * 128 + r) * OBS)[lane & 3] = make_float4(src[0], src[1], src[2], src[3]);
+        }
+        if (owner) {
+#pragma unroll
+          for (int k = 0; k < OBS; ++k) x1[k] = s_obs[row * navsim_dev::kObsPad + k];
+        }
+      }
+    }
+    }   // step t
+    if constexpr (FUSED) {
+      if (sim_writer) navsim_dev::store_agent(ta.st, ai, ag, goal_dirty);
+      if (blockIdx.x == 0 && tid == 0) atomicAdd(&ta.stats->steps, (unsigned long long)ta.c.N * (unsigned long long)H);
+    }
   } else if (warp == INF_W_TMA) {
     if (lane == 0) {
       int slot = 0;
       uint32_t pfree = (1u << NWSLOT) - 1;
+#pragma unroll 1
+      for (int tt = 0; tt < H; ++tt)
 #pragma unroll 1
       for (int i = 0; i < 4 * NCH; ++i) {       // per block and chunk: [Wa hi | Wa lo], then [Wb hi | Wb lo]
         const int blk = i >> 3, c = (i >> 1) & 3, part = i & 1;
@@ -1164,6 +1260,8 @@ __global__ void __launch_bounds__(INF_THREADS, 1) mlp_infer_ws_kernel(WsInferArg
       tc::mbar_wait(bar, (parity_bits >> bit) & 1);
       parity_bits ^= 1u << bit;
     };
+#pragma unroll 1
+    for (int tt = 0; tt < H; ++tt)
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
       const int blk = pass;
@@ -1235,8 +1333,10 @@ int navppo_tcws_init() {
   NAV_CUDA_TRY(cudaFuncSetAttribute(mlp_grad_ws_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES));
   NAV_CUDA_TRY(cudaFuncSetAttribute(mlp_grad_ws_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES));
   NAV_CUDA_TRY(cudaFuncSetAttribute(mlp_grad_ws_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES));
-  NAV_CUDA_TRY(cudaFuncSetAttribute(mlp_infer_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INF_SMEM_BYTES));
-  NAV_CUDA_TRY(cudaFuncSetAttribute(mlp_infer_ws_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INF_SMEM_BYTES));
+  NAV_CUDA_TRY(cudaFuncSetAttribute(mlp_infer_ws_kernel<1, WsInferArgs>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INF_SMEM_BYTES));
+  NAV_CUDA_TRY(cudaFuncSetAttribute(mlp_infer_ws_kernel<3, WsInferArgs>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INF_SMEM_BYTES));
+  NAV_CUDA_TRY(cudaFuncSetAttribute(mlp_infer_ws_kernel<1, WsFusedArgs>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM_BYTES));
+  NAV_CUDA_TRY(cudaFuncSetAttribute(mlp_infer_ws_kernel<3, WsFusedArgs>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM_BYTES));
   return NAVSIM_OK;
 }
 
@@ -1253,7 +1353,9 @@ int navppo_tcws_prep_launch(const float* params, float* wprep, cudaStream_t s) {
 // kernel that re-tiled them — the weights).
 int navppo_tcws_infer_launch(const ppo::InferArgs& a, int mode, bool both_nets, int passes, const float* wprep, bool chained,
                              bool weights_ready, cudaStream_t s) {
-  WsInferArgs ta{a, reinterpret_cast<const unsigned char*>(wprep), mode, weights_ready ? 1 : 0, g_prof};
+  WsInferArgs ta;
+  ta.g = a; ta.wprep = reinterpret_cast<const unsigned char*>(wprep); ta.mode = mode; ta.weights_ready = weights_ready ? 1 : 0;
+  ta.prof = g_prof;
   cudaLaunchConfig_t lc{};
   lc.gridDim = dim3((a.T + 127) / 128, both_nets ? 2 : 1);
   lc.blockDim = dim3(INF_THREADS);
@@ -1263,8 +1365,31 @@ int navppo_tcws_infer_launch(const ppo::InferArgs& a, int mode, bool both_nets, 
   attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr.val.programmaticStreamSerializationAllowed = 1;
   if (chained) { lc.attrs = &attr; lc.numAttrs = 1; }
-  if (passes == 3) NAV_CUDA_TRY(cudaLaunchKernelEx(&lc, mlp_infer_ws_kernel<3>, ta));
-  else NAV_CUDA_TRY(cudaLaunchKernelEx(&lc, mlp_infer_ws_kernel<1>, ta));
+  if (passes == 3) NAV_CUDA_TRY(cudaLaunchKernelEx(&lc, mlp_infer_ws_kernel<3, WsInferArgs>, ta));
+  else NAV_CUDA_TRY(cudaLaunchKernelEx(&lc, mlp_infer_ws_kernel<1, WsInferArgs>, ta));
+  return NAVSIM_OK;
+}
+
+// The whole step loop of PPO.rollout as ONE launch (weights already re-tiled into `wprep`): returns NAVSIM_EINVAL
+// with `*unsupported = 1` when the simulator is in a configuration the fused kernel does not step (beam count other
+// than 10, compacted-wall maps, noise / wheel-ramp options, start / goal tables) — the caller then chains kernels.
+int navppo_tcws_rollout_launch(navsim* sim, const ppo::InferArgs& a, int H, int passes, const float* wprep, float* obs_rows,
+                               float* next_obs, float* rew, uint8_t* done, uint8_t* arrive, uint8_t* trunc, float* ep_ret,
+                               float* ep_path, int32_t* ep_len, int* unsupported, cudaStream_t s) {
+  navsim_dev::DeviceView dv;
+  if (int rc = navsim_device_view(sim, s, &dv)) return rc;
+  *unsupported = (dv.variant != 0 || dv.c.S > navsim_dev::kCompactWalls || dv.c.B != NAVSIM_LIDAR_FEATS ||
+                  navsim_dev::map_bytes_of(dv.c.B, dv.c.S) > FUSED_MAP_MAX) ? 1 : 0;
+  if (*unsupported) return NAVSIM_EINVAL;
+  WsFusedArgs ta;
+  ta.g = a; ta.wprep = reinterpret_cast<const unsigned char*>(wprep); ta.mode = ppo::INFER_ACT; ta.weights_ready = 0; ta.prof = nullptr;
+  ta.c = dv.c; ta.st = dv.st; ta.g_map = dv.map; ta.rt_tab = dv.rt; ta.stats = dv.stats;
+  ta.H = H; ta.obs_rows = obs_rows; ta.next_obs = next_obs; ta.rew = rew; ta.done = done; ta.arrive = arrive; ta.trunc = trunc;
+  ta.ep_ret = ep_ret; ta.ep_path = ep_path; ta.ep_len = ep_len;
+  const dim3 grid((a.T + 127) / 128, 1);
+  if (passes == 3) mlp_infer_ws_kernel<3, WsFusedArgs><<<grid, INF_THREADS, FUSED_SMEM_BYTES, s>>>(ta);
+  else mlp_infer_ws_kernel<1, WsFusedArgs><<<grid, INF_THREADS, FUSED_SMEM_BYTES, s>>>(ta);
+  NAV_CUDA_TRY(cudaGetLastError());
   return NAVSIM_OK;
 }
 

@@ -517,6 +517,20 @@ __device__ __forceinline__ void agent_step(const SimConst& c, const MapView& mv,
 
 }
 
+// What the fused rollout kernel (navppo_tcws.cu) needs of a simulator handle: filled by navsim_device_view
+// (navsim_kernels.cu), which also runs the handle's call checks and counts the launch.
+struct DeviceView {
+  SimConst c;
+  SimState st;
+  const float* map;        // packed obstacle set (map_bytes_of(c.B, c.S) bytes)
+  const uint16_t* rt;      // bearing table
+  DevStats* stats;
+  int variant;             // 0: the reference's 10-beam sensor (the only one the fused kernel steps)
+};
+
 }  // namespace navsim_dev
+
+struct navsim;
+int navsim_device_view(navsim* h, void* stream, navsim_dev::DeviceView* out);
 
 #endif  // NAVSIM_DEVICE_CUH_

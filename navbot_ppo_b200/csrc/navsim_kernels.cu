@@ -959,6 +959,16 @@ int navsim_step_ex(navsim_t* h, const float* act_dev, const navsim_step_out* out
 
 }  // extern "C"
 
+// The device side of a handle for the fused rollout kernel (internal: navppo_rollout_ex)
+int navsim_device_view(navsim* h, void* stream, navsim_dev::DeviceView* out) {
+  if (int rc = check_ready(h)) return rc;
+  if (int rc = begin_device_call(h, (cudaStream_t)stream)) return rc;
+  out->c = h->c; out->st = h->st; out->map = h->d_map; out->rt = h->d_rt; out->stats = h->d_stats;
+  out->variant = variant_of(h);
+  h->launches++;
+  return NAVSIM_OK;
+}
+
 // navsim_step_ex as a programmatic dependent launch (internal: navppo_rollout_ex chains it behind the policy kernel)
 int navsim_step_chained(navsim_t* h, const float* act_dev, const navsim_step_out* out, void* stream) {
   if (int rc = check_ready(h)) return rc;

@@ -233,3 +233,38 @@ def test_rollout_log_probs_are_bit_identical_to_what_the_update_recomputes(prec)
     _, m = _grad(h, flat, obs[perm].contiguous(), act[perm].contiguous(), lp[perm].contiguous(), adv, rtg, T, var)
     assert m[_capi.M_APPROX_KL] == 0.0 and m[_capi.M_CLIP_FRAC] == 0.0
     assert abs(m[_capi.M_ACTOR_LOSS] + float(adv.double().mean())) < 1e-6        # every surrogate is exactly 1 * A
+
+
+def test_one_launch_fused_rollout_equals_the_kernel_by_kernel_rollout(tmp_path):
+    """A tensor-core handle runs PPO.rollout's whole step loop as ONE launch (each CTA keeps 128 robots for all H
+    steps: policy forward on tcgen05, sampling, Env.step by the same threads).  Every rollout buffer, the simulator
+    state it leaves behind and the episode statistics are bit-identical to the chain of policy / step kernels
+    (NAVPPO_ROLLOUT_FUSED=0), for a robot count that leaves the last tile ragged, episodes that end inside the
+    horizon, rollout after rollout."""
+    import os
+
+    def make(fused, lr):
+        if not fused:
+            os.environ["NAVPPO_ROLLOUT_FUSED"] = "0"
+        try:
+            env = VecEnv(434, map="stage_2", seed=3, max_episode_steps=25)
+            return PPO(NetActor, NetCritic, env, 16, 2, timesteps_per_batch=434 * 40, max_timesteps_per_episode=25,
+                       n_updates_per_iteration=1, lr=lr, output_dir=str(tmp_path / ("f" if fused else "c")), method_name="r",
+                       seed=5, verbose=False, precision=_capi.PREC_BF16X3)
+        finally:
+            os.environ.pop("NAVPPO_ROLLOUT_FUSED", None)
+    a, b = make(True, 3e-4), make(False, 3.0001e-4)       # (the learning rate keys the handle cache; a rollout ignores it)
+    b.flat.copy_(a.flat)
+    for it in range(3):
+        if it == 2:
+            a._decay_cov(); b._decay_cov()
+        ra, rb = a.rollout([0, 0], 0), b.rollout([0, 0], 0)
+        torch.cuda.synchronize()
+        for x, y in zip(ra[:4], rb[:4]):
+            assert torch.equal(x, y)
+        for name in ("_b_rew", "_b_flags", "_b_epret", "_b_eppath", "_b_eplen", "_b_term", "_next_obs"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), name
+        assert np.array_equal(ra[4], rb[4]) and ra[5] == rb[5] and ra[5]["ep_count"] > 0
+        for f in (_capi.F_X, _capi.F_Y):
+            assert np.array_equal(a.env.get_state(f), b.env.get_state(f))
+    assert a.env.launch_count < b.env.launch_count        # one simulator-side launch per rollout instead of H

@@ -1,5 +1,5 @@
-"""Rollout A/B: the fused rollout (CUDA graph of policy + step kernels) with and without programmatic dependent
-launches and with the fp32 / tensor-core policy kernel — identical buffers where the arithmetic is the same, and
+"""Rollout A/B: the one-launch fused rollout kernel, the CUDA graph of policy + step kernels with and without
+programmatic dependent launches, and the fp32 policy kernel — identical buffers where the arithmetic is the same, and
 the time per rollout.
 
     python tools/rollout_check.py [agents] [horizon]
@@ -48,7 +48,8 @@ def main():
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
     H = int(sys.argv[2]) if len(sys.argv) > 2 else 128
     out = {}
-    for name, env in (("tc+chained", {}), ("tc", {"NAVPPO_ROLLOUT_CHAIN": "0"}), ("fp32 policy kernel", {"NAVPPO_TC_INFER": "0"})):
+    for name, env in (("fused", {}), ("tc+chained", {"NAVPPO_ROLLOUT_FUSED": "0"}),
+                      ("tc", {"NAVPPO_ROLLOUT_FUSED": "0", "NAVPPO_ROLLOUT_CHAIN": "0"}), ("fp32 policy kernel", {"NAVPPO_TC_INFER": "0"})):
         r = subprocess.run([sys.executable, __file__, "--child", str(N), str(H)], env={**os.environ, **env}, capture_output=True,
                            text=True, timeout=600)
         line = [l for l in r.stdout.splitlines() if l.startswith("RESULT")]
@@ -59,8 +60,8 @@ def main():
         out[name] = h
         print(f"{name:20s} rollout {N} x {H}: best {best} ms, median {med} ms  ({N * H / (float(med) * 1e-3):.3e} env-steps/s)  digest {h}",
               flush=True)
-    same = out["tc+chained"] == out["tc"]
-    print("chained == plain launches (bit-identical batch):", same)
+    same = out["tc+chained"] == out["tc"] == out["fused"]
+    print("fused == chained == plain launches (bit-identical batch):", same)
     return 0 if same else 1
 
 
