@@ -57,7 +57,7 @@ def main():
     tiles = (T + 127) // 128
     per_cta = -(-tiles // 74)
     print(f"T={T}: {tiles} tiles, CTA (0,0) walks {per_cta}; cycles per tile by role and category")
-    for name, base, labels in (("epilogue warp 0 (row owner)", 0, EPI), ("epilogue warp 4", 8, EPI), ("MMA thread", 16, MMA),
+    for name, base, labels in (("epilogue warp 0 (row owner)", 0, EPI), ("epilogue warp 4", 8, EPI), ("consuming MMA warp (U, dW, GX)", 16, MMA),
                                ("flush warp 8", 24, FL)):
         tot = pc[base:base + 8].sum()
         print(f"  {name}: total {tot / per_cta:9.0f}")
