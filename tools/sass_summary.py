@@ -1,5 +1,5 @@
 """Per-kernel SASS mnemonic counts of the in-tree library (cuobjdump -sass): the evidence that the tensor-core
-kernels are tcgen05 / TMEM / TMA code and that the peer-memory Adam reads through multimem.
+kernels are tcgen05 / TMEM / TMA code and that the multicast Adam variant reads through multimem (LDGMC).
 
     python tools/sass_summary.py > profiles/r02_sass_summary.txt
 """
@@ -10,7 +10,7 @@ import subprocess
 import sys
 
 LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "navbot_ppo_b200", "libnavbot_b200.so")
-WATCH = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTCATOMSWS", "UBLKCP", "SYNCS", "ELECT", "MULTIMEM", "FADD2", "FMUL2", "FFMA2",
+WATCH = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTCATOMSWS", "UBLKCP", "SYNCS", "ELECT", "LDGMC", "FADD2", "FMUL2", "FFMA2",
          "HMMA", "FFMA", "RED", "ATOM", "LDG", "STG", "LDS", "STS", "SHFL", "ACQBULK", "USETMAXREG", "STL", "LDL"]
 
 
@@ -31,7 +31,7 @@ def main():
     demangle = subprocess.run(["c++filt"], input="\n".join(kernels), capture_output=True, text=True).stdout.splitlines()
     print(f"# cuobjdump -sass {os.path.relpath(LIB)}: arch {', '.join(arch)}; instruction counts per kernel (static)")
     print("# UTCHMMA = tcgen05.mma, UTCBAR = tcgen05.commit, LDTM / STTM = tcgen05.ld / st, UBLKCP = cp.async.bulk (TMA),")
-    print("# SYNCS = mbarrier ops, MULTIMEM = multimem.ld_reduce (NVLS), FADD2 / FMUL2 = packed fp32x2")
+    print("# SYNCS = mbarrier ops, LDGMC = multimem.ld_reduce (NVLS), FADD2 / FMUL2 = packed fp32x2")
     for name, c in zip(demangle, kernels.values()):
         short = re.sub(r"\(anonymous namespace\)::|<unnamed>::", "", name)
         short = re.sub(r"\((?:[^()]|\([^()]*\))*\)$", "", short)
