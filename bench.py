@@ -527,15 +527,19 @@ def main():
         "value_policy_step": {"value": value_policy_step, "unit": "env-steps/s", "us_per_launch": policy_step_us,
                               "note": "actions from a device tensor, ONE navsim_step launch per env step (no fusion over "
                                       "steps): the simulator's share of a policy-driven rollout"},
-        "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N * 8 * H,
+        "e2e": {"value": e2e_async_value, "unit": "env-steps/s", "h2d_bytes_per_step": N * 8 * H,
                 "d2h_bytes_per_step": N * (64 + 4 + 3) * H,
-                "api": "navsim_step_host via VecEnv.step_host: host actions in, host obs/reward/flags out, every env step; "
-                       "caller buffers page-locked (VecEnv.alloc_host_buffers): the kernel reads the actions and writes the "
-                       "observations in host memory over PCIe (zero-copy), reward/flags via a mapped block",
-                "async_pipelined_value": e2e_async_value,
-                "async_api": "navsim_step_host_async / navsim_wait (VecEnv.step_host_async / wait): pipeline of depth 4, "
-                             "observations through the copy engine under the next step's kernel, four host buffer sets",
-                "pageable_buffers_value": e2e_pageable},
+                "api": "navsim_step_host_async / navsim_wait (VecEnv.step_host_async / wait), the host entry point for a "
+                       "caller that keeps several steps in flight: EVERY env step takes its actions from page-locked host "
+                       "memory and delivers obs / reward / flags to page-locked host memory (four buffer sets, 4 steps in "
+                       "flight; the kernel reads the actions over PCIe, the observations take the copy engine under the "
+                       "next step's kernel); the timed loop waits for every step's results",
+                "blocking_value": e2e_value,
+                "blocking_api": "navsim_step_host via VecEnv.step_host: the same buffers, one step at a time (launch, "
+                                "zero-copy reads / writes over PCIe, stream synchronisation per step)",
+                "pageable_buffers_value": e2e_pageable,
+                "d2h_link_note": "tools/pcie_d2h.py on the same box class: 42.6 GB/s for one step's 581,632 B, i.e. at most "
+                                 "6.0e8 env-steps/s for 8192 robots; the async loop is bound by its ~7 driver calls per step"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "roofline_sweep": sweep,
