@@ -437,11 +437,15 @@ struct navsim {
   float* d_obs2[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_kernel[4] = {nullptr, nullptr, nullptr, nullptr}, ev_copy[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t async_issued = 0, async_waited = 0;
-  int async_mode = 1;            // NAVSIM_ASYNC_OBS: 1 "dma" (default) observations through the copy engine under the next
-                                 // step's kernel, actions read over PCIe by the kernel; 0 "dma_act" actions staged by a
-                                 // host-to-device copy too; 2 "stores" the kernel reads / writes every host buffer itself.
-                                 // Measured per step of 8192 robots: 21.0 / 28.9 / 22.6 us — the loop is bound by the
-                                 // host-side driver calls (each extra call costs more than the PCIe reads it saves)
+  // (one instantiated CUDA graph per slot {actions in -> kernel -> results home}, launched alternately into two streams,
+  // was measured too: 20.9 us per step of 8192 robots against 17.5 for the plain form below — graph launches add
+  // device-side latency to a chain this short — and is not kept)
+  int async_mode = 1;            // NAVSIM_ASYNC_OBS: 1 "dma" (default) the step's results leave through the copy engine
+                                 // under the next step's kernel, the kernel reads the actions over PCIe; 0 "dma_act"
+                                 // actions staged by a host-to-device copy too; 2 "stores" the kernel reads / writes
+                                 // every host buffer itself.  Measured per step of 8192 robots (tools/time_async.py):
+                                 // 17.5 / 24.2 / 22.6 us; the host spends ~7 us issuing and ~10 us waiting: the loop is
+                                 // bound by the device-side chain kernel -> kernel, which includes the PCIe action reads
   std::vector<std::pair<const void*, void*>> alias_cache;   // host pointer -> device alias (null: not page-locked)
   // GoalSpawnSampler tables (navsim_set_sampler) and the host copy of the packed map they are cast against
   double *d_starts = nullptr, *d_goals = nullptr;
@@ -794,7 +798,7 @@ int navsim_destroy(navsim_t* h) {
   if (h->d_rew) cudaFree(h->d_rew);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-  for (int k = 1; k < 4; ++k)
+  for (int k = 0; k < 4; ++k)
     if (h->d_obs2[k]) cudaFree(h->d_obs2[k]);
   for (int k = 0; k < 4; ++k) {
     if (h->ev_kernel[k]) cudaEventDestroy(h->ev_kernel[k]);
@@ -806,6 +810,7 @@ int navsim_destroy(navsim_t* h) {
 
 int navsim_set_map(navsim_t* h, const double* seg_host, int32_t num_segments, int32_t flags) {
   if (!h || !seg_host) return fail(NAVSIM_EINVAL, "null argument");
+  if (int rc = navsim_wait(h, 0)) return rc;
   if (num_segments < 1) return fail(NAVSIM_EINVAL, "a map needs at least one segment");
   const int B = h->c.B;
   const size_t bytes = map_bytes_of(B, num_segments);
@@ -895,6 +900,7 @@ int navsim_set_sampler(navsim_t* h, const double* starts_host, int32_t n_starts,
   if (!h || !starts_host || !goals_host) return fail(NAVSIM_EINVAL, "null argument");
   if (!h->d_map) return fail(NAVSIM_EINVAL, "navsim_set_map has not been called");
   if (h->cfg.sampler_mode != 1) return fail(NAVSIM_EINVAL, "the handle was not created with sampler_mode = 1");
+  if (int rc = navsim_wait(h, 0)) return rc;
   if (n_starts < 1 || n_starts > NAVSIM_MAX_TABLE || n_goals < 1 || n_goals > NAVSIM_MAX_TABLE)
     return fail(NAVSIM_EINVAL, "table sizes must be in 1..NAVSIM_MAX_TABLE");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
@@ -1141,8 +1147,8 @@ int64_t navsim_step_host_async(navsim_t* h, const float* act_host, float* obs_ho
     const char* mode = getenv("NAVSIM_ASYNC_OBS");
     h->async_mode = (mode && std::string(mode) == "stores") ? 2 : (mode && std::string(mode) == "dma_act") ? 0 : 1;
     CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    h->d_obs2[0] = h->d_obs;
-    for (int k = 1; k < NAVSIM_ASYNC_DEPTH; ++k) CUDA_TRY(cudaMalloc(&h->d_obs2[k], N * NAVSIM_OBS_DIM * sizeof(float)));
+    // per slot one device block laid out obs | rew | done | arrive | trunc (the layout of VecEnv.alloc_host_buffers)
+    for (int k = 0; k < NAVSIM_ASYNC_DEPTH; ++k) CUDA_TRY(cudaMalloc(&h->d_obs2[k], N * (NAVSIM_OBS_DIM * sizeof(float) + 4 + 3)));
     for (int k = 0; k < NAVSIM_ASYNC_DEPTH; ++k) {
       CUDA_TRY(cudaEventCreateWithFlags(&h->ev_kernel[k], cudaEventDisableTiming));
       CUDA_TRY(cudaEventCreateWithFlags(&h->ev_copy[k], cudaEventDisableTiming));
@@ -1171,6 +1177,27 @@ int64_t navsim_step_host_async(navsim_t* h, const float* act_host, float* obs_ho
     return fail(NAVSIM_EINVAL, "navsim_step_host_async needs page-locked buffers (cudaHostAlloc / cudaHostRegister / pin_memory)");
   const int k = (int)(h->async_issued & (NAVSIM_ASYNC_DEPTH - 1));
   cudaStream_t s = h->own_stream;
+  // copy-engine modes: the kernel leaves the whole step in the slot's device block (a kernel that stores reward and
+  // flags into host memory itself issues tens of thousands of 1- and 4-byte PCIe writes and lasts ~20 us for 8192
+  // robots); the block goes home in ONE copy when the caller's arrays are laid out the same way, else array by array
+  unsigned char* blk = reinterpret_cast<unsigned char*>(h->d_obs2[k]);
+  float* b_obs = reinterpret_cast<float*>(blk);
+  float* b_rew = reinterpret_cast<float*>(blk + N * NAVSIM_OBS_DIM * sizeof(float));
+  uint8_t* b_done = blk + N * (NAVSIM_OBS_DIM * sizeof(float) + 4);
+  uint8_t* b_arrive = b_done + N;
+  uint8_t* b_trunc = b_arrive + N;
+  const bool one_block = reinterpret_cast<unsigned char*>(rew_host) == reinterpret_cast<unsigned char*>(obs_host) + (b_rew - b_obs) * sizeof(float) &&
+                         done_host == reinterpret_cast<uint8_t*>(rew_host) + 4 * N && arrive_host == done_host + N &&
+                         (!trunc_host || trunc_host == arrive_host + N);
+  auto copy_home = [&](cudaStream_t cs) -> cudaError_t {
+    if (one_block) return cudaMemcpyAsync(obs_host, blk, N * (NAVSIM_OBS_DIM * sizeof(float) + 4 + (trunc_host ? 3 : 2)), cudaMemcpyDeviceToHost, cs);
+    cudaError_t e = cudaMemcpyAsync(obs_host, b_obs, N * NAVSIM_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rew_host, b_rew, N * sizeof(float), cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(done_host, b_done, N, cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(arrive_host, b_arrive, N, cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess && trunc_host) e = cudaMemcpyAsync(trunc_host, b_trunc, N, cudaMemcpyDeviceToHost, cs);
+    return e;
+  };
   if (h->async_mode == 2) {
     // the kernel reads the actions and stores the observation rows in the caller's page-locked buffers itself: one
     // launch + one event per step, but the kernel then lasts as long as its PCIe traffic
@@ -1186,11 +1213,11 @@ int64_t navsim_step_host_async(navsim_t* h, const float* act_host, float* obs_ho
     CUDA_TRY(cudaMemcpyAsync(h->d_act, act_host, N * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
     act_dev = h->d_act;
   }
-  if (int rc = launch_step(h, make_io(act_dev, h->d_obs2[k], rew_dev, done_dev, arrive_dev, trunc_dev, 0, 0), s, false, 0, 1))
+  if (int rc = launch_step(h, make_io(act_dev, b_obs, b_rew, b_done, b_arrive, b_trunc, 0, 0), s, false, 0, 1))
     return rc;
   CUDA_TRY(cudaEventRecord(h->ev_kernel[k], s));
   CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_kernel[k], 0));
-  CUDA_TRY(cudaMemcpyAsync(obs_host, h->d_obs2[k], N * NAVSIM_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+  CUDA_TRY(copy_home(h->copy_stream));
   CUDA_TRY(cudaEventRecord(h->ev_copy[k], h->copy_stream));
   return ++h->async_issued;
 }

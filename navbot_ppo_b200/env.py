@@ -183,9 +183,13 @@ class VecEnv:
         """Page-locked host arrays for step_host(): dict(act, obs, rew, done, arrive, trunc).  With
         these the library DMAs straight from / into the caller's memory (no staging copy)."""
         n = self.num_envs
-        mk = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()  # noqa: E731
-        return dict(act=mk((n, 2), torch.float32), obs=mk((n, self.obs_dim), torch.float32), rew=mk((n,), torch.float32),
-                    done=mk((n,), torch.uint8), arrive=mk((n,), torch.uint8), trunc=mk((n,), torch.uint8))
+        # the outputs are views of ONE page-locked block laid out obs | rew | done | arrive | trunc: the asynchronous
+        # step then returns a whole step's results with a single device-to-host copy
+        block = torch.empty(n * (4 * self.obs_dim + 4 + 3), dtype=torch.uint8).pin_memory().numpy()
+        o0, r0, f0 = 0, 4 * self.obs_dim * n, (4 * self.obs_dim + 4) * n
+        act = torch.empty((n, 2), dtype=torch.float32).pin_memory().numpy()
+        return dict(act=act, obs=block[o0:r0].view(np.float32).reshape(n, self.obs_dim), rew=block[r0:f0].view(np.float32),
+                    done=block[f0:f0 + n], arrive=block[f0 + n:f0 + 2 * n], trunc=block[f0 + 2 * n:f0 + 3 * n], _block=block)
 
     def step_host(self, actions: np.ndarray, out: dict | None = None):
         """Env.step with HOST buffers: actions[N,2] float32 in, (obs, rew, done, arrive, trunc) numpy

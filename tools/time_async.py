@@ -20,16 +20,24 @@ def child(N, steps):
         sb["act"][:] = rng.uniform(0, 1, sb["act"].shape).astype(np.float32)
     env.reset_host()
 
+    acc = [0.0, 0.0]
+
     def run(n):
         tickets = []
         for i in range(n):
             if len(tickets) == depth:
+                ta = time.perf_counter()
                 env.wait(tickets.pop(0))
+                acc[1] += time.perf_counter() - ta
             sb = sets[i % depth]
+            ta = time.perf_counter()
             tickets.append(env.step_host_async(sb["act"], sb))
+            acc[0] += time.perf_counter() - ta
         env.wait(0)
     run(50)
+    acc[0] = acc[1] = 0.0
     t0 = time.perf_counter(); run(steps); dt = time.perf_counter() - t0
+    print(f"  host time per step: {acc[0] / steps * 1e6:.2f} us inside step_host_async, {acc[1] / steps * 1e6:.2f} us inside wait", flush=True)
     chk = float(sum(np.asarray(sb["obs"], dtype=np.float64).sum() for sb in sets))
     print(f"RESULT {N * steps / dt:.4e} {dt / steps * 1e6:.2f} {chk:.6f}", flush=True)
 
@@ -39,11 +47,12 @@ def main():
         return child(int(sys.argv[2]), int(sys.argv[3]))
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 4000
-    for name, env in (("copy engine for obs, kernel reads host actions (default)", {}),
+    for name, env in (("results home in one copy, kernel reads host actions (default)", {}),
                       ("copy engines for actions + obs", {"NAVSIM_ASYNC_OBS": "dma_act"}),
                       ("kernel reads / stores host buffers", {"NAVSIM_ASYNC_OBS": "stores"})):
         r = subprocess.run([sys.executable, __file__, "--child", str(N), str(steps)], env={**os.environ, **env}, capture_output=True,
                            text=True, timeout=600)
+        print("\n".join(l for l in r.stdout.splitlines() if l.startswith("  host time")))
         line = [l for l in r.stdout.splitlines() if l.startswith("RESULT")]
         if not line:
             print(name, "FAILED", r.stdout[-1500:], r.stderr[-1500:])
