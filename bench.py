@@ -532,15 +532,15 @@ def main():
                 "api": "navsim_step_host_async / navsim_wait (VecEnv.step_host_async / wait), the host entry point for a "
                        "caller that keeps several steps in flight: EVERY env step takes its actions from page-locked host "
                        "memory and delivers obs / reward / flags to page-locked host memory (four buffer sets, 4 steps in "
-                       "flight; the kernel reads the actions over PCIe, the step's results go home in one copy-engine "
-                       "transfer under the next step's kernel); the timed loop waits for every step's results",
+                       "flight; the actions are staged by a host-to-device copy under the previous step's kernel, the step's "
+                       "results go home in one copy-engine transfer under the next step's kernel); the timed loop waits "
+                       "for every step's results",
                 "blocking_value": e2e_value,
                 "blocking_api": "navsim_step_host via VecEnv.step_host: the same buffers, one step at a time (launch, "
                                 "zero-copy reads / writes over PCIe, stream synchronisation per step)",
                 "pageable_buffers_value": e2e_pageable,
                 "d2h_link_note": "tools/pcie_d2h.py on the same box class: 42.6 GB/s for one step's 581,632 B, i.e. at most "
-                                 "6.0e8 env-steps/s for 8192 robots; the async loop is bound by the device-side chain kernel -> kernel "
-                                 "(tools/time_async.py)"},
+                                 "6.0e8 env-steps/s for 8192 robots (tools/time_async.py has the host-side split)"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "roofline_sweep": sweep,

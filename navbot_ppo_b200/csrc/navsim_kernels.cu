@@ -440,12 +440,17 @@ struct navsim {
   // (one instantiated CUDA graph per slot {actions in -> kernel -> results home}, launched alternately into two streams,
   // was measured too: 20.9 us per step of 8192 robots against 17.5 for the plain form below — graph launches add
   // device-side latency to a chain this short — and is not kept)
-  int async_mode = 1;            // NAVSIM_ASYNC_OBS: 1 "dma" (default) the step's results leave through the copy engine
-                                 // under the next step's kernel, the kernel reads the actions over PCIe; 0 "dma_act"
-                                 // actions staged by a host-to-device copy too; 2 "stores" the kernel reads / writes
-                                 // every host buffer itself.  Measured per step of 8192 robots (tools/time_async.py):
-                                 // 17.5 / 24.2 / 22.6 us; the host spends ~7 us issuing and ~10 us waiting: the loop is
-                                 // bound by the device-side chain kernel -> kernel, which includes the PCIe action reads
+  int async_mode = 4;            // NAVSIM_ASYNC_OBS: 4 "dma_ahead" (default) the actions are staged by a host-to-device
+                                 // copy on their own stream (it runs under the previous step's kernel) and the step's
+                                 // results leave in one copy under the next step's kernel; 1 "dma" the kernel reads
+                                 // the actions over PCIe instead; 0 "dma_act" the action copy sits in the kernel's
+                                 // stream; 2 "stores" the kernel reads / writes every host buffer itself.  Measured per
+                                 // step of 8192 robots (tools/time_async.py): 15.7 / 18.3 / 24.2 / 22.6 us.  In the
+                                 // default form the host spends ~10 us issuing and ~5 us waiting per step; the link
+                                 // would allow 13.7 us (tools/pcie_d2h.py)
+  cudaStream_t h2d_stream = nullptr;                          // mode 4: actions staged one step ahead
+  cudaEvent_t ev_h2d[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* d_act2[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<std::pair<const void*, void*>> alias_cache;   // host pointer -> device alias (null: not page-locked)
   // GoalSpawnSampler tables (navsim_set_sampler) and the host copy of the packed map they are cast against
   double *d_starts = nullptr, *d_goals = nullptr;
@@ -798,8 +803,12 @@ int navsim_destroy(navsim_t* h) {
   if (h->d_rew) cudaFree(h->d_rew);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-  for (int k = 0; k < 4; ++k)
+  if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+  for (int k = 0; k < 4; ++k) {
     if (h->d_obs2[k]) cudaFree(h->d_obs2[k]);
+    if (h->d_act2[k]) cudaFree(h->d_act2[k]);
+    if (h->ev_h2d[k]) cudaEventDestroy(h->ev_h2d[k]);
+  }
   for (int k = 0; k < 4; ++k) {
     if (h->ev_kernel[k]) cudaEventDestroy(h->ev_kernel[k]);
     if (h->ev_copy[k]) cudaEventDestroy(h->ev_copy[k]);
@@ -1145,7 +1154,13 @@ int64_t navsim_step_host_async(navsim_t* h, const float* act_host, float* obs_ho
   const size_t N = (size_t)h->c.N;
   if (!h->copy_stream) {   // first use: second stream, second device observation buffer, events
     const char* mode = getenv("NAVSIM_ASYNC_OBS");
-    h->async_mode = (mode && std::string(mode) == "stores") ? 2 : (mode && std::string(mode) == "dma_act") ? 0 : 1;
+    h->async_mode = (mode && std::string(mode) == "stores") ? 2 : (mode && std::string(mode) == "dma_act") ? 0
+                    : (mode && std::string(mode) == "dma") ? 1 : 4;
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+    for (int k2 = 0; k2 < NAVSIM_ASYNC_DEPTH; ++k2) {
+      CUDA_TRY(cudaMalloc(&h->d_act2[k2], N * 2 * sizeof(float)));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_h2d[k2], cudaEventDisableTiming));
+    }
     CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     // per slot one device block laid out obs | rew | done | arrive | trunc (the layout of VecEnv.alloc_host_buffers)
     for (int k = 0; k < NAVSIM_ASYNC_DEPTH; ++k) CUDA_TRY(cudaMalloc(&h->d_obs2[k], N * (NAVSIM_OBS_DIM * sizeof(float) + 4 + 3)));
@@ -1212,6 +1227,12 @@ int64_t navsim_step_host_async(navsim_t* h, const float* act_host, float* obs_ho
     // actions through the copy engine too
     CUDA_TRY(cudaMemcpyAsync(h->d_act, act_host, N * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
     act_dev = h->d_act;
+  } else if (h->async_mode == 4) {
+    // ... on their own stream, so that the copy runs under the previous step's kernel
+    CUDA_TRY(cudaMemcpyAsync(h->d_act2[k], act_host, N * 2 * sizeof(float), cudaMemcpyHostToDevice, h->h2d_stream));
+    CUDA_TRY(cudaEventRecord(h->ev_h2d[k], h->h2d_stream));
+    CUDA_TRY(cudaStreamWaitEvent(s, h->ev_h2d[k], 0));
+    act_dev = h->d_act2[k];
   }
   if (int rc = launch_step(h, make_io(act_dev, b_obs, b_rew, b_done, b_arrive, b_trunc, 0, 0), s, false, 0, 1))
     return rc;

@@ -47,7 +47,8 @@ def main():
         return child(int(sys.argv[2]), int(sys.argv[3]))
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 4000
-    for name, env in (("results home in one copy, kernel reads host actions (default)", {}),
+    for name, env in (("actions staged one step ahead, results home in one copy (default)", {}),
+                      ("kernel reads host actions, results home in one copy", {"NAVSIM_ASYNC_OBS": "dma"}),
                       ("copy engines for actions + obs", {"NAVSIM_ASYNC_OBS": "dma_act"}),
                       ("kernel reads / stores host buffers", {"NAVSIM_ASYNC_OBS": "stores"})):
         r = subprocess.run([sys.executable, __file__, "--child", str(N), str(steps)], env={**os.environ, **env}, capture_output=True,
@@ -58,7 +59,7 @@ def main():
             print(name, "FAILED", r.stdout[-1500:], r.stderr[-1500:])
             return 1
         _, v, us, chk = line[0].split()
-        print(f"{name:58s} {N} robots: {v} env-steps/s, {us} us per step, checksum {chk}")
+        print(f"{name:68s} {N} robots: {v} env-steps/s, {us} us per step, checksum {chk}")
     return 0
 
 
