@@ -109,7 +109,14 @@ int navppo_evaluate(navppo_t* h, const float* params, const float* obs, const fl
  * act[H,N,2], logp[H,N], rew[H,N], done/arrive/trunc[H,N] are the time-major rollout buffers;
  * ep_return[H,N] / ep_path[H,N] (both or neither, may be NULL) receive, at the step that ends an
  * episode, its return and path length (the per-episode csv of ppo.py:739-746).
- * Action noise: Philox counter draw0 + t (see navppo_act). */
+ * Action noise: Philox counter draw0 + t (see navppo_act).
+ * How it is enqueued depends on the handle: NAVPPO_FP32 -> 2 H launches (policy kernel, step kernel); a tensor-core
+ * precision -> ONE persistent launch in which every CTA keeps 128 robots for all H steps (policy forward on tcgen05,
+ * sampling, Env.step by the same threads) when the simulator runs the reference's 10-beam sensor on a map of at most
+ * 32 walls, else the tensor-core policy kernel and the step kernel chained as programmatic dependent launches.  All
+ * forms of one precision return bit-identical buffers.  A handle of a tensor-core precision runs navppo_forward /
+ * navppo_act / navppo_evaluate on the tensor cores as well (same products in the same order as the gradient kernel's
+ * forward half: the log-prob navppo_grad recomputes for a sample is bit-identical to the one stored here). */
 int navppo_rollout(navppo_t* h, navsim_t* sim, const float* params, int32_t H, double var, uint64_t seed,
                    int64_t agent_id_offset, uint32_t draw0, float* obs, float* next_obs, float* act, float* logp, float* rew,
                    uint8_t* done, uint8_t* arrive, uint8_t* trunc, float* ep_return, float* ep_path, void* stream);

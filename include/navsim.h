@@ -170,7 +170,10 @@ int navsim_step_host(navsim_t* h, const float* act_host, float* obs_host, float*
  * a ticket (1, 2, 3, ..; negative = error) at once; navsim_wait(h, ticket) blocks until that step's outputs are in
  * the caller's buffers (ticket 0: every step issued so far).  At most NAVSIM_ASYNC_DEPTH steps may be in flight, so
  * a caller cycles through that many sets of output buffers and prepares later steps while earlier observations
- * cross PCIe.  All buffers must be page-locked.  Stream rules for ALL entry points: device entry points run on the
+ * cross PCIe.  All buffers must be page-locked.  The actions are staged by a host-to-device copy under the previous
+ * step's kernel; the step's results go home in ONE device-to-host copy under the next step's kernel when the output
+ * arrays are one block laid out obs[N,16] | rew[N] | done[N] | arrive[N] | trunc[N] (VecEnv.alloc_host_buffers), else
+ * array by array.  Stream rules for ALL entry points: device entry points run on the
  * caller's stream, host entry points on streams the handle owns; the library orders the two kinds against each other
  * (a host call first waits for the last caller stream used, a device call waits for asynchronous host steps still
  * in flight), so they can be mixed on one handle without explicit synchronisation. */
