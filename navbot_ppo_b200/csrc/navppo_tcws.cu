@@ -131,11 +131,11 @@ constexpr uint32_t OFF_RED = OFF_BIAS + 2 * HID * 4;        // head / bias-b gra
 constexpr uint32_t OFF_PAR = OFF_RED + 4 * 128 * 4;         // fc2 biases and head weights, 128 floats
 constexpr int P_B1B = 0, P_B2B = OBS, P_HEAD = OBS + X1;    // offsets inside that block
 constexpr uint32_t OFF_BAR = OFF_PAR + 128 * 4;             // mbarriers, tmem base
-constexpr uint32_t WS_SMEM_BYTES = OFF_BAR + 384;           // 228,224 B of the 232,448 B a CTA may have
+constexpr uint32_t WS_SMEM_BYTES = OFF_BAR + 384;   // (34 mbarriers + the TMEM base)           // 228,224 B of the 232,448 B a CTA may have
 
 // mbarrier indices
 enum { B_ZFULL = 0, B_EFULL = 4, B_SFREE = 8, B_WFULL = 12, B_WFREE = 19, B_DWFULL = 26, B_DWFREE = 28,
-       B_GZFREE = 30, B_ACC = 31, B_XREADY = 32, B_COUNT = 33 };
+       B_GZFREE = 30, B_ACC = 31, B_XREADY = 32, B_GZFULL = 33, B_COUNT = 34 };
 
 // TMEM columns: 256 columns of product ring (forward: four 64-column slots of Z; backward: two 128-column slots
 // of Z^T | GH^T), two weight-gradient accumulator buffers (dWa 48 | dWb 32 columns each), U and GX
@@ -342,6 +342,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
     for (int i = 0; i < 2; ++i) { tc::mbar_init(bars + B_DWFULL + i, 1); tc::mbar_init(bars + B_DWFREE + i, 4); }
     for (int i = 0; i < NWSLOT; ++i) { tc::mbar_init(bars + B_WFULL + i, 1); tc::mbar_init(bars + B_WFREE + i, 1); }
     tc::mbar_init(bars + B_GZFREE, 1);
+    tc::mbar_init(bars + B_GZFULL, 16);     // 8 epilogue warps x the 2 sample halves of a chunk
     tc::mbar_init(bars + B_ACC, 1);
     tc::mbar_init(bars + B_XREADY, 4);
   }
@@ -490,7 +491,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
               tc::tmem_st16(tz + 80, gl);
             }
             PT(3);
+            tc::tmem_st_wait();
+            publish(bars + B_EFULL + s, false);                // the weight-gradient products may start
             if (blk) {
+              // ... while GZ^T goes to shared memory for GX (issued once both halves of the chunk are there): the
+              // wait for GX of the previous chunk no longer holds up the weight-gradient products of this unit
               if (sh == 0) {   // GX of the previous chunk has finished reading the tile
                 tc::mbar_wait(bars + B_GZFREE, pgz); pgz ^= 1;
               }
@@ -501,9 +506,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
                 st_granule(sGZT, scol + 8 * c8, gh + 4 * c8);
                 if (PASSES == 3) st_granule(sGZT + SGZ_PART, scol + 8 * c8, gl + 4 * c8);
               }
+              tc::fence_smem_to_async();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bars + B_GZFULL);
             }
-            tc::tmem_st_wait();
-            publish(bars + B_EFULL + s, blk != 0);
           }
           PT(fwd ? 2 : 3);
         }
@@ -808,7 +814,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
                      aWF = tc::smem_u32(smem + OFF_WF);
       constexpr uint32_t RG = ROWG >> 4;
       const Opnd GZTm{aGZT >> 4, SGZ_PART >> 4, 8, RG, 16};   // GZ^T tile read as A = GZ: rows = K = hidden units
-      uint32_t pe = 0, pw = 0, pdfree = 0x3, px = 0;
+      uint32_t pe = 0, pw = 0, pdfree = 0x3, px = 0, pgzf = 0;
       int wslot = 0;          // weight ring slot of the next load in sequence
       auto next_slot = [](int s) { return s == NWSLOT - 1 ? 0 : s + 1; };
       auto wait_bar = [&](uint64_t* bar, uint32_t& parity_bits, int bit) {
@@ -874,28 +880,34 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
               }
               tc::fence_after_sync();
               if (elect_one()) {
-                if (sh == 1 && blk) {   // GX += GZ Wa over the chunk's 128 hidden units: both operands MN-major (rows = K).
-                  // First: the next chunk's epilogue waits for the GZ^T tile
+                // dWa += GZ^T [X | 1], dWbT += H^T GU over the unit's 64 samples: A in tensor memory, B MN-major
+                const Opnd Xs{(aX >> 4) + 64 * sh, SX_PART >> 4, 8, RG, 16};
+                const Opnd GUs{(aGU >> 4) + 64 * sh, SGU_PART >> 4, 8, RG, 16};
+                const uint32_t slot = tmem + TM_ZG + sh * 128, d = tmem + TM_DW + b * 80;
+                gemm_ts<PASSES>(d, slot + 64, Xs, id_dwa, sh > 0);
+                gemm_ts<PASSES>(d + 48, slot, GUs, id_dwb, sh > 0);
+                PT(7);
+                if (u + 2 < 2 * NCH) commit(bars + B_SFREE + sh);
+                if (sh == 1) commit(bars + B_DWFULL + b);
+                if (!blk && u == 2 * NCH - 1) commit(bars + B_ACC);       // the tile is complete
+              }
+              __syncwarp();
+              if (sh == 1 && blk) {
+                // GX += GZ Wa over the chunk's 128 hidden units once both halves of GZ^T are in shared memory: both
+                // operands MN-major (rows = K)
+                tc::mbar_wait(bars + B_GZFULL, pgzf); pgzf ^= 1;
+                tc::fence_after_sync();
+                if (elect_one()) {
                   const uint32_t w = aWF + sa * WSLOT;
                   const Opnd Wa_m{w >> 4, cp >> 4, 8, CH, 16};
                   gemm<PASSES, 8>(tmem + TM_GX, GZTm, Wa_m, id_gx, c > 0);
                   PT(6);
                   commit(bars + B_GZFREE);
                   commit(bars + B_WFREE + sa);
+                  if (u == 2 * NCH - 1) commit(bars + B_ACC);             // GX is complete
                 }
-                {   // dWa += GZ^T [X | 1], dWbT += H^T GU over the unit's 64 samples: A in tensor memory, B MN-major
-                  const Opnd Xs{(aX >> 4) + 64 * sh, SX_PART >> 4, 8, RG, 16};
-                  const Opnd GUs{(aGU >> 4) + 64 * sh, SGU_PART >> 4, 8, RG, 16};
-                  const uint32_t slot = tmem + TM_ZG + sh * 128, d = tmem + TM_DW + b * 80;
-                  gemm_ts<PASSES>(d, slot + 64, Xs, id_dwa, sh > 0);
-                  gemm_ts<PASSES>(d + 48, slot, GUs, id_dwb, sh > 0);
-                  PT(7);
-                  if (u + 2 < 2 * NCH) commit(bars + B_SFREE + sh);
-                  if (sh == 1) commit(bars + B_DWFULL + b);
-                  if (u == 2 * NCH - 1) commit(bars + B_ACC);             // GX / the tile is complete
-                }
+                __syncwarp();
               }
-              __syncwarp();
             }
           }
         }
