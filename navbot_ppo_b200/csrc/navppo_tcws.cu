@@ -728,7 +728,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
       const uint32_t aX = tc::smem_u32(sX), aGU = tc::smem_u32(sGU), aWF = tc::smem_u32(smem + OFF_WF);
       constexpr uint32_t RG = ROWG >> 4;
       const Opnd Xk{aX >> 4, SX_PART >> 4, RG, 8, 2 * RG};   // K-major: rows = samples are the M / N index
-      uint32_t pw = 0, psf = 0, px = 0;
+      uint32_t pw = 0, psf = 0, px = 0, pacc = 0;
+      bool first_pass = true;
       int wslot = 0;          // weight ring slot of the next load in sequence
       auto next_slot = [](int s) { return s == NWSLOT - 1 ? 0 : s + 1; };
       auto wait_bar = [&](uint64_t* bar, uint32_t& parity_bits, int bit) {
@@ -740,8 +741,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
         for (int pass = 0; pass < 4; ++pass) {
           const int blk = pass_block(pass);
           const int IN = blk ? X1 : OBS;
-          tc::mbar_wait(bars + B_XREADY, px); px ^= 1;    // the pass's input tile (X or GU) is published
+          if (!first_pass) { tc::mbar_wait(bars + B_ACC, pacc); pacc ^= 1; }   // the previous pass has left the TMEM ring
+          first_pass = false;
           if (pass < 2) {
+            tc::mbar_wait(bars + B_XREADY, px); px ^= 1;  // the pass's input tile X is published
             // ============================================================== forward: half-chunks of 64 hidden units
             const uint32_t wp = wpart(IN);
             const uint32_t id_z = tc::make_idesc_bf16(128, HC, 0, 0);
@@ -780,14 +783,40 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
               }
               if (u >= 2) wait_bar(bars + B_SFREE + sh, psf, sh);         // dW of unit u - 2 has read the slot
               tc::fence_after_sync();
+              // Z^T = Wa X^T and GH^T = Wb^T GU^T of unit u = (chunk u / 2, sample half u % 2) into ring slot u & 1.
+              // Z^T of the first two units only needs X, which has been there since the forward pass: it is issued
+              // while the row owners still work on GU (the pass boundary), GH^T follows once GU is published
+              const uint32_t wa = aWF + sa * WSLOT, wb = aWF + sb * WSLOT;
+              const Opnd Wa_k{wa >> 4, cp >> 4, CH, 8, 2 * CH};                               // rows = hidden units = M
+              const Opnd Wb_m{wb >> 4, cp >> 4, 8, (uint32_t)IN, 16};                         // rows = K = output features
+              const Opnd Xs{(aX >> 4) + 64 * sh, SX_PART >> 4, RG, 8, 2 * RG};                // the 64 sample rows = N
+              const Opnd GUs{(aGU >> 4) + 64 * sh, SGU_PART >> 4, RG, 8, 2 * RG};
+              const uint32_t d = tmem + TM_ZG + sh * 128;
+              if (u < 2) {
+                if (elect_one()) {
+                  if (blk) gemm<PASSES, 2, true>(d, Wa_k, Xs, id_zt, false);
+                  else gemm<PASSES, 1, true>(d, Wa_k, Xs, id_zt, false);
+                }
+                __syncwarp();
+                if (u == 0) continue;
+                tc::mbar_wait(bars + B_XREADY, px); px ^= 1;              // GU is published
+                tc::fence_after_sync();
+                if (elect_one()) {
+                  const Opnd GU0{aGU >> 4, SGU_PART >> 4, RG, 8, 2 * RG};
+                  const uint32_t d0 = tmem + TM_ZG;
+                  if (blk) gemm<PASSES, 2, true>(d0 + 64, Wb_m, GU0, id_ght, false);
+                  else gemm<PASSES, 1, true>(d0 + 64, Wb_m, GU0, id_ght, false);
+                  commit(bars + B_ZFULL + 0);
+                  if (blk) gemm<PASSES, 2, true>(d + 64, Wb_m, GUs, id_ght, false);
+                  else gemm<PASSES, 1, true>(d + 64, Wb_m, GUs, id_ght, false);
+                  commit(bars + B_ZFULL + 1);
+                  commit(bars + B_WFREE + sb);                        // last reader of Wb; block 1 has no GX: of Wa too
+                  if (!blk) commit(bars + B_WFREE + sa);
+                }
+                __syncwarp();
+                continue;
+              }
               if (elect_one()) {
-                // Z^T = Wa X^T and GH^T = Wb^T GU^T of unit u = (chunk u / 2, sample half u % 2) into ring slot u & 1
-                const uint32_t wa = aWF + sa * WSLOT, wb = aWF + sb * WSLOT;
-                const Opnd Wa_k{wa >> 4, cp >> 4, CH, 8, 2 * CH};                               // rows = hidden units = M
-                const Opnd Wb_m{wb >> 4, cp >> 4, 8, (uint32_t)IN, 16};                         // rows = K = output features
-                const Opnd Xs{(aX >> 4) + 64 * sh, SX_PART >> 4, RG, 8, 2 * RG};                // the 64 sample rows = N
-                const Opnd GUs{(aGU >> 4) + 64 * sh, SGU_PART >> 4, RG, 8, 2 * RG};
-                const uint32_t d = tmem + TM_ZG + sh * 128;
                 if (blk) {
                   gemm<PASSES, 2, true>(d, Wa_k, Xs, id_zt, false);
                   gemm<PASSES, 2, true>(d + 64, Wb_m, GUs, id_ght, false);
