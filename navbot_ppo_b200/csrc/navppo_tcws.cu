@@ -432,32 +432,38 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
       for (int pass = 0; pass < 4; ++pass) {
         const int blk = pass_block(pass);
         const bool fwd = pass < 2;
-        // -------------------------------------------------------------- the 8 half-chunks of this pass
+        // -------------------------------------------------------------- the steps of this pass: 4 chunks of 128 hidden
+        // units (forward) / 8 units = chunk x sample half (backward), through the two 128-column ring slots
 #pragma unroll 1
-        for (int h = 0; h < NHC; ++h) {
-          const int s = fwd ? (h & 3) : (h & 1);
+        for (int h = 0; h < (fwd ? NCH : 2 * NCH); ++h) {
+          const int s = h & 1;
           PT(5);
-          tc::mbar_wait(bars + B_ZFULL + s, (pz >> s) & 1); pz ^= 1u << s;    // Z (and GH) of half-chunk h are in TMEM
+          tc::mbar_wait(bars + B_ZFULL + s, (pz >> s) & 1); pz ^= 1u << s;    // Z (and GH) of step h are in TMEM
           tc::fence_after_sync();
           PT(0);
-          const uint32_t tz = trow + TM_ZG + s * (fwd ? 64 : 128) + ch * 32;
           if (fwd) {
-            // half-chunk h of 64 hidden units; lane = sample row.  H = lrelu(Z + ba), written back over the
-            // columns this warp just read as the A operand of U += H Wb^T: [hi: 16 packed columns | lo: 16]
-            const float* sBa = sBias + blk * HID + h * HC + ch * 32;
-            float v[32];
-            tc::tmem_ld16_nowait(tz, v);
-            tc::tmem_ld16_nowait(tz + 16, v + 16);
-            tc::tmem_ld_wait();
-            uint32_t hi[16], lo[16];
+            // chunk h of 128 hidden units; lane = sample row; this warp's 64 columns in two rounds of 32.
+            // H = lrelu(Z + ba), written back over the columns just read as the A operand of U += H Wb^T:
+            // per 32 columns [hi: 16 packed columns | lo: 16]
 #pragma unroll
-            for (int i4 = 0; i4 < 8; ++i4)
-              tc::bias_lrelu_split4(v + 4 * i4, *reinterpret_cast<const float4*>(sBa + 4 * i4), LEAK, hi + 2 * i4, lo + 2 * i4);
-            tc::tmem_st16(tz, hi);
-            if (PASSES == 3) tc::tmem_st16(tz + 16, lo);
+            for (int r2 = 0; r2 < 2; ++r2) {
+              const uint32_t tz = trow + TM_ZG + s * 128 + ch * 64 + r2 * 32;
+              const float* sBa = sBias + blk * HID + h * CH + ch * 64 + r2 * 32;
+              float v[32];
+              tc::tmem_ld16_nowait(tz, v);
+              tc::tmem_ld16_nowait(tz + 16, v + 16);
+              tc::tmem_ld_wait();
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int i4 = 0; i4 < 8; ++i4)
+                tc::bias_lrelu_split4(v + 4 * i4, *reinterpret_cast<const float4*>(sBa + 4 * i4), LEAK, hi + 2 * i4, lo + 2 * i4);
+              tc::tmem_st16(tz, hi);
+              if (PASSES == 3) tc::tmem_st16(tz + 16, lo);
+            }
             tc::tmem_st_wait();
             publish(bars + B_EFULL + s, false);
           } else {
+            const uint32_t tz = trow + TM_ZG + s * 128 + ch * 32;
             // unit h = (chunk c of 128 hidden units, half sh of 64 samples), TRANSPOSED: lane = hidden unit, columns
             // = samples.  H^T = lrelu(z), GZ^T = GH^T * lrelu'(z), z = Z^T + ba, written back over Z^T / GH^T as the
             // A operands of the weight-gradient products; block 2 also leaves GZ^T in shared memory for GX.
@@ -707,17 +713,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
 #pragma unroll 1
         for (int pass = 0; pass < 4; ++pass) {
           const int blk = pass_block(pass);
-          if (pass < 2) {      // forward: one half-chunk blob per slot
-            const uint32_t bytes = wblob(blk ? X1 : OBS);
+          // a chunk blob (128 hidden units) as two slots, [Wa hi | Wa lo] then [Wb hi | Wb lo], forward and backward
+          const uint32_t half = 2 * cpart(blk ? X1 : OBS);
 #pragma unroll 1
-            for (int h = 0; h < NHC; ++h) load(wblob_g + wblob_off(blk, h), bytes);
-          } else {             // backward: a chunk blob as two slots, [Wa hi | Wa lo] then [Wb hi | Wb lo]
-            const uint32_t half = 2 * cpart(blk ? X1 : OBS);
-#pragma unroll 1
-            for (int c = 0; c < NCH; ++c) {
-              load(wblob_g + cblob_off(blk, c), half);
-              load(wblob_g + cblob_off(blk, c) + half, half);
-            }
+          for (int c = 0; c < NCH; ++c) {
+            load(wblob_g + cblob_off(blk, c), half);
+            load(wblob_g + cblob_off(blk, c) + half, half);
           }
         }
       }
@@ -745,25 +746,28 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
           first_pass = false;
           if (pass < 2) {
             tc::mbar_wait(bars + B_XREADY, px); px ^= 1;  // the pass's input tile X is published
-            // ============================================================== forward: half-chunks of 64 hidden units
-            const uint32_t wp = wpart(IN);
-            const uint32_t id_z = tc::make_idesc_bf16(128, HC, 0, 0);
+            // ============================================================== forward: chunks of 128 hidden units
+            const uint32_t cp = cpart(IN);
+            const uint32_t id_z = tc::make_idesc_bf16(128, CH, 0, 0);
 #pragma unroll 1
-            for (int h = 0; h < NHC; ++h) {
-              const int s = h & 3;
-              if (h >= 4) wait_bar(bars + B_SFREE + s, psf, s);           // U of half-chunk h - 4 has read the slot
-              wait_bar(bars + B_WFULL + wslot, pw, wslot);
+            for (int c = 0; c < NCH; ++c) {
+              const int s = c & 1;
+              const int sa = wslot, sb = next_slot(sa);                   // the chunk's [Wa] load; [Wb] is the consumer's
+              wslot = next_slot(sb);
+              if (c >= 2) wait_bar(bars + B_SFREE + s, psf, s);           // U of chunk c - 2 has read the slot
+              wait_bar(bars + B_WFULL + sa, pw, sa);
+              pw ^= 1u << sb;
               tc::fence_after_sync();
               if (elect_one()) {
-                // Z of half-chunk h into ring slot h & 3: A = X (K-major), B = Wa (rows = hidden units, K-major), K = IN
-                const uint32_t w = aWF + wslot * WSLOT;
-                const Opnd Wk{w >> 4, wp >> 4, HC, 8, 2 * HC};
-                if (blk) gemm<PASSES, 2>(tmem + TM_ZG + s * 64, Xk, Wk, id_z, false);
-                else gemm<PASSES, 1>(tmem + TM_ZG + s * 64, Xk, Wk, id_z, false);
+                // Z of chunk c into ring slot c & 1: A = X (K-major), B = Wa (rows = the chunk's hidden units, K-major), K = IN
+                const uint32_t w = aWF + sa * WSLOT;
+                const Opnd Wk{w >> 4, cp >> 4, CH, 8, 2 * CH};
+                if (blk) gemm<PASSES, 2>(tmem + TM_ZG + s * 128, Xk, Wk, id_z, false);
+                else gemm<PASSES, 1>(tmem + TM_ZG + s * 128, Xk, Wk, id_z, false);
                 commit(bars + B_ZFULL + s);
+                commit(bars + B_WFREE + sa);                              // Z is the only reader of the [Wa] load
               }
               __syncwarp();
-              wslot = next_slot(wslot);
             }
           } else {
             // ============================================================== backward: chunks of 128 hidden units x halves
@@ -861,29 +865,31 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_grad_ws_kernel(WsGradArgs t
           tc::mbar_wait(bars + B_XREADY, px); px ^= 1;    // the pass's input tile (X or GU) is published
           PT(0);
           if (pass < 2) {
-            const uint32_t wp = wpart(IN);
+            const uint32_t cp = cpart(IN);
             const uint32_t id_u = tc::make_idesc_bf16(128, IN, 0, 0);
 #pragma unroll 1
-            for (int h = 0; h < NHC; ++h) {
-              const int s = h & 3;
+            for (int c = 0; c < NCH; ++c) {
+              const int s = c & 1;
+              const int sa = wslot, sb = next_slot(sa);                  // the chunk's [Wb] load is the second one
+              wslot = next_slot(sb);
               PT(4);
-              wait_bar(bars + B_EFULL + s, pe, s);                       // H of half-chunk h sits packed in the slot
+              wait_bar(bars + B_EFULL + s, pe, s);                       // H of chunk c sits packed in the slot
               PT(1);
-              wait_bar(bars + B_WFULL + wslot, pw, wslot);               // (long complete: Z of the half-chunk read the same load)
+              pw ^= 1u << sa;
+              wait_bar(bars + B_WFULL + sb, pw, sb);
               tc::fence_after_sync();
               PT(2);
               if (elect_one()) {
-                // U += H Wb^T: A = H (tensor memory), B = Wb (rows = output features, K-major)
-                const uint32_t w = aWF + wslot * WSLOT;
-                const Opnd Wbk{(w + 2 * wp) >> 4, wp >> 4, (uint32_t)IN, 8, 2u * IN};
-                gemm_ts<PASSES>(tmem + TM_U, tmem + TM_ZG + s * 64, Wbk, id_u, h > 0);
+                // U += H Wb^T over the chunk's 128 hidden units: A = H (tensor memory), B = Wb (rows = output features, K-major)
+                const uint32_t w = aWF + sb * WSLOT;
+                const Opnd Wbk{w >> 4, cp >> 4, (uint32_t)IN, 8, 2u * IN};
+                gemm_ts<PASSES, false, 8>(tmem + TM_U, tmem + TM_ZG + s * 128, Wbk, id_u, c > 0);
                 PT(6);
-                commit(bars + B_WFREE + wslot);
-                if (h + 4 < NHC) commit(bars + B_SFREE + s);
-                if (h == NHC - 1) commit(bars + B_ACC);                   // U is complete
+                commit(bars + B_WFREE + sb);
+                if (c + 2 < NCH) commit(bars + B_SFREE + s);
+                if (c == NCH - 1) commit(bars + B_ACC);                   // U is complete
               }
               __syncwarp();
-              wslot = next_slot(wslot);
             }
           } else {
             const uint32_t cp = cpart(IN);
