@@ -18,8 +18,8 @@
 //               because one thread's waits, descriptor moves and commits were the longest chain of the tile
 //   warp 13     one thread streams pre-tiled weights through one TMA ring of 7 x 16 KB slots
 //
-// Forward (per block, half-chunks of 64 hidden units, 4-slot TMEM ring of 64 columns):
-//     Z = X Wa^T  [128 samples x 64]  (operands in shared memory)
+// Forward (per block, chunks of 128 hidden units, 2-slot TMEM ring of 128 columns):
+//     Z = X Wa^T  [128 samples x 128]  (operands in shared memory)
 //     H = lrelu(Z + ba) -> packed over Z;   U += H Wb^T  (A = H in tensor memory)
 // Backward (per block, chunks of 128 hidden units x halves of 64 samples, TRANSPOSED: lane = hidden unit; 2-slot
 // TMEM ring of 128 columns):
@@ -53,29 +53,21 @@ using namespace ppo;
 extern __shared__ __align__(128) unsigned char ws_smem[];
 
 // ----------------------------------------------------------------------------------------
-// Pre-split, pre-tiled weights: per network 8 half-chunk blobs of block 1 then 8 of block 2, each
+// Pre-split, pre-tiled weights: per network 4 chunk blobs (128 hidden units) of block 1 then 4 of block 2, each
 //   [Wa hi | Wa lo | Wb hi | Wb lo]
-// Wa tile: rows = hidden unit j (64), columns = input feature (IN);  Wb tile: rows = output feature o
-// (IN), columns = hidden unit j (64) — the bf16 row-block format of tc_common.cuh.
+// Wa tile: rows = hidden unit j (128), columns = input feature (IN);  Wb tile: rows = output feature o (IN), columns
+// = hidden unit j (128) — the bf16 row-block format of tc_common.cuh.  The same blob serves the forward pass
+// (Z = X Wa^T reads the Wa tile K-major, U += H Wb^T the Wb tile K-major) and, through the other descriptor strides,
+// the transposed backward pass.
 // ----------------------------------------------------------------------------------------
-constexpr int HC = 64;                                    // hidden units per half-chunk
-constexpr int NHC = HID / HC;                             // 8
-__host__ __device__ constexpr uint32_t wpart(int IN) { return (uint32_t)(HC * IN * 2); }
-__host__ __device__ constexpr uint32_t wblob(int IN) { return 4u * wpart(IN); }
-constexpr uint32_t WS_FWD_BLOB = NHC * (wblob(OBS) + wblob(X1));   // 196,608 B
-__host__ __device__ constexpr uint32_t wblob_off(int block2, int h) {
-  return block2 ? NHC * wblob(OBS) + (uint32_t)h * wblob(X1) : (uint32_t)h * wblob(OBS);
-}
-// ... followed by 4 chunk blobs (128 hidden units) of block 1 then 4 of block 2 for the backward pass,
-//   [Wa hi | Wa lo | Wb hi | Wb lo], Wa tile: rows = hidden unit (128), Wb tile: rows = output feature (IN)
 constexpr int CH = 128;
 constexpr int NCH = HID / CH;                              // 4
 __host__ __device__ constexpr uint32_t cpart(int IN) { return (uint32_t)(CH * IN * 2); }
 __host__ __device__ constexpr uint32_t cblob(int IN) { return 4u * cpart(IN); }
 __host__ __device__ constexpr uint32_t cblob_off(int block2, int c) {
-  return WS_FWD_BLOB + (block2 ? NCH * cblob(OBS) + (uint32_t)c * cblob(X1) : (uint32_t)c * cblob(OBS));
+  return block2 ? NCH * cblob(OBS) + (uint32_t)c * cblob(X1) : (uint32_t)c * cblob(OBS);
 }
-constexpr uint32_t WS_NET_BLOB = WS_FWD_BLOB + NCH * (cblob(OBS) + cblob(X1));   // 393,216 B
+constexpr uint32_t WS_NET_BLOB = NCH * (cblob(OBS) + cblob(X1));   // 196,608 B
 
 __global__ void ws_prep_weights_kernel(const float* __restrict__ params, unsigned char* __restrict__ wprep) {
   const int net = blockIdx.y;
@@ -86,26 +78,17 @@ __global__ void ws_prep_weights_kernel(const float* __restrict__ params, unsigne
     const int IN = block2 ? X1 : OBS;
     const int r = block2 ? t - HID * OBS : t;
     const int j = r / IN, i = r % IN;              // fc1: hidden unit j, input feature i
-    const int h = j / HC, jl = j % HC;
-    unsigned char* blob = out + wblob_off(block2, h);
-    const uint32_t wp = wpart(IN);
-    uint16_t hi, lo;
-    tc::split_bf16(p[(block2 ? O_W2A : O_W1A) + j * IN + i], &hi, &lo);
-    *reinterpret_cast<uint16_t*>(blob + tc::rb16_off(HC, jl, i)) = hi;
-    *reinterpret_cast<uint16_t*>(blob + wp + tc::rb16_off(HC, jl, i)) = lo;
-    // fc2 [IN][512]: element (o = i, j)
-    tc::split_bf16(p[(block2 ? O_W2B : O_W1B) + i * HID + j], &hi, &lo);
-    *reinterpret_cast<uint16_t*>(blob + 2 * wp + tc::rb16_off(IN, i, jl)) = hi;
-    *reinterpret_cast<uint16_t*>(blob + 3 * wp + tc::rb16_off(IN, i, jl)) = lo;
-    // the same two weights in the chunk blobs of the backward pass
     const int c = j / CH, jc = j % CH;
     unsigned char* cb = out + cblob_off(block2, c);
     const uint32_t cp = cpart(IN);
-    *reinterpret_cast<uint16_t*>(cb + 2 * cp + tc::rb16_off(IN, i, jc)) = hi;
-    *reinterpret_cast<uint16_t*>(cb + 3 * cp + tc::rb16_off(IN, i, jc)) = lo;
+    uint16_t hi, lo;
     tc::split_bf16(p[(block2 ? O_W2A : O_W1A) + j * IN + i], &hi, &lo);
     *reinterpret_cast<uint16_t*>(cb + tc::rb16_off(CH, jc, i)) = hi;
     *reinterpret_cast<uint16_t*>(cb + cp + tc::rb16_off(CH, jc, i)) = lo;
+    // fc2 [IN][512]: element (o = i, j)
+    tc::split_bf16(p[(block2 ? O_W2B : O_W1B) + i * HID + j], &hi, &lo);
+    *reinterpret_cast<uint16_t*>(cb + 2 * cp + tc::rb16_off(IN, i, jc)) = hi;
+    *reinterpret_cast<uint16_t*>(cb + 3 * cp + tc::rb16_off(IN, i, jc)) = lo;
   }
 }
 
@@ -120,10 +103,10 @@ constexpr uint32_t SGZ_PART = (128 / 8) * ROWG;             // 32 KB: GZ^T of on
 constexpr uint32_t OFF_SX = 0;
 constexpr uint32_t OFF_SGU = OFF_SX + 2 * SX_PART;          // 24 KB
 constexpr uint32_t OFF_SGZT = OFF_SGU + 2 * SGU_PART;       // 40 KB
-// One weight ring for both directions: 7 slots of 16 KB.  A forward half-chunk blob takes one slot; a backward
-// chunk blob takes two ([Wa hi | Wa lo] and [Wb hi | Wb lo]), so every pass consumes exactly 8 slots and the
-// producer runs up to 7 slots (5 forward steps, 3 backward chunks) ahead of the products.
-constexpr uint32_t WSLOT = wblob(X1);                       // 16 KB
+// One weight ring for both directions: 7 slots of 16 KB.  A chunk blob takes two slots ([Wa hi | Wa lo] and
+// [Wb hi | Wb lo]), so every pass consumes exactly 8 slots and the producer runs up to 7 slots (3 chunks) ahead of
+// the products.
+constexpr uint32_t WSLOT = 2 * cpart(X1);                   // 16 KB: half a chunk blob of block 2
 constexpr int NWSLOT = 7;
 constexpr uint32_t OFF_WF = OFF_SGZT + 2 * SGZ_PART;        // 104 KB: the ring
 constexpr uint32_t OFF_BIAS = OFF_WF + NWSLOT * WSLOT;      // 216 KB: fc1 biases of both blocks, 2 x 512 floats
@@ -137,8 +120,8 @@ constexpr uint32_t WS_SMEM_BYTES = OFF_BAR + 384;   // (34 mbarriers + the TMEM 
 enum { B_ZFULL = 0, B_EFULL = 4, B_SFREE = 8, B_WFULL = 12, B_WFREE = 19, B_DWFULL = 26, B_DWFREE = 28,
        B_GZFREE = 30, B_ACC = 31, B_XREADY = 32, B_GZFULL = 33, B_COUNT = 34 };
 
-// TMEM columns: 256 columns of product ring (forward: four 64-column slots of Z; backward: two 128-column slots
-// of Z^T | GH^T), two weight-gradient accumulator buffers (dWa 48 | dWb 32 columns each), U and GX
+// TMEM columns: product ring of two 128-column slots (forward: Z of a chunk; backward: Z^T | GH^T of a unit), two
+// weight-gradient accumulator buffers (dWa 48 | dWb 32 columns each), U and GX
 constexpr uint32_t TM_ZG = 0;
 constexpr uint32_t TM_DW = 256;      // buffer b at + 80 b: dWa at + 0, dWb at + 48
 constexpr uint32_t TM_U = 416;       // 32 columns
