@@ -669,17 +669,27 @@ __global__ void __launch_bounds__(GM) mlp_grad_kernel(GradArgs a) {
 // metric partials.
 __global__ void grad_reduce_kernel(const float* __restrict__ gpart, const double* __restrict__ mpart, int rows,
                                    float inv_n, float* __restrict__ grad, double* __restrict__ metrics) {
+  // thread = one element of the KERNEL layout (the rows are read as coalesced lines; the two transposed fc2 regions
+  // are un-transposed by the single scattered store), rows added in order, eight loads in flight
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < NAVPPO_FLAT) {
     const int net = i >= NAVPPO_CRITIC_OFFSET;
-    const int li = i - (net ? NAVPPO_CRITIC_OFFSET : 0);
+    const int k = i - (net ? NAVPPO_CRITIC_OFFSET : 0);
     const int n = net ? NAVPPO_CRITIC_PARAMS : NAVPPO_ACTOR_PARAMS;
     float t = 0.f;
-    if (li < n) {
-      const float* col = gpart + (size_t)net * rows * NET_ROW + klayout(li);
-      for (int r = 0; r < rows; ++r) t += col[(size_t)r * NET_ROW];
+    if (k < n) {
+      const float* col = gpart + (size_t)net * rows * NET_ROW + k;
+      int r = 0;
+      for (; r + 8 <= rows; r += 8) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = col[(size_t)(r + q) * NET_ROW];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += v[q];
+      }
+      for (; r < rows; ++r) t += col[(size_t)r * NET_ROW];
     }
-    grad[i] = t;
+    grad[(net ? NAVPPO_CRITIC_OFFSET : 0) + (k < n ? klayout_inv(k) : k)] = t;
   }
   if (blockIdx.x == 0 && threadIdx.x < 4) {
     const int q = threadIdx.x;

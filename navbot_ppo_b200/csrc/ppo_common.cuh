@@ -39,6 +39,12 @@ __host__ __device__ inline int klayout(int i) {
   if (i >= O_W2B && i < O_B2B) { const int r = i - O_W2B; return O_W2B + (r % HID) * X1 + r / HID; }
   return i;
 }
+// kernel-layout index -> canonical index (the inverse of klayout)
+__host__ __device__ inline int klayout_inv(int k) {
+  if (k >= O_W1B && k < O_B1B) { const int r = k - O_W1B; return O_W1B + (r % OBS) * HID + r / OBS; }
+  if (k >= O_W2B && k < O_B2B) { const int r = k - O_W2B; return O_W2B + (r % X1) * HID + r / X1; }
+  return k;
+}
 constexpr int NET_ROW = NAVPPO_CRITIC_OFFSET;  // 50304: padded length of one network's vector
 
 __device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : LEAK * x; }
