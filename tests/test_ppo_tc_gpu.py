@@ -268,3 +268,30 @@ def test_one_launch_fused_rollout_equals_the_kernel_by_kernel_rollout(tmp_path):
         for f in (_capi.F_X, _capi.F_Y):
             assert np.array_equal(a.env.get_state(f), b.env.get_state(f))
     assert a.env.launch_count < b.env.launch_count        # one simulator-side launch per rollout instead of H
+
+
+def test_rollout_on_a_map_the_fused_kernel_does_not_step_falls_back_to_the_kernel_chain(tmp_path):
+    """House map (208 walls: compacted wall lists, 16 lanes per robot): the fused rollout kernel declines, and the
+    tensor-core policy kernel + step kernel chained as programmatic dependent launches return the same batch as the
+    two kernels launched plainly (NAVPPO_ROLLOUT_CHAIN=0)."""
+    import os
+
+    def make(chain, lr):
+        if not chain:
+            os.environ["NAVPPO_ROLLOUT_CHAIN"] = "0"
+        try:
+            env = VecEnv(300, map="house", seed=4, max_episode_steps=30)
+            return PPO(NetActor, NetCritic, env, 16, 2, timesteps_per_batch=300 * 24, max_timesteps_per_episode=30,
+                       n_updates_per_iteration=1, lr=lr, output_dir=str(tmp_path / ("p" if chain else "q")), method_name="r",
+                       seed=6, verbose=False, precision=_capi.PREC_BF16X3)
+        finally:
+            os.environ.pop("NAVPPO_ROLLOUT_CHAIN", None)
+    a, b = make(True, 3.0002e-4), make(False, 3.0003e-4)
+    b.flat.copy_(a.flat)
+    for _ in range(2):
+        ra, rb = a.rollout([0, 0], 0), b.rollout([0, 0], 0)
+        torch.cuda.synchronize()
+        for x, y in zip(ra[:4], rb[:4]):
+            assert torch.equal(x, y)
+        assert torch.equal(a._b_rew, b._b_rew) and torch.equal(a._b_flags, b._b_flags)
+    assert a.env.launch_count == b.env.launch_count >= 24         # a step launch per env step was captured: not the fused kernel
