@@ -39,7 +39,7 @@ BYTES_SURVEY = 150
 BYTES_SURVEY_FP64_POSE = 174
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full`
 # capture of the same kernel and shape (profiles/README.md names the file); keyed by (N, H)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {(8192, 128): 741632 + 17151488}   # profiles/r02z_step_8192_fused_ncu.csv
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {(8192, 128): 748544 + 17474048}   # profiles/r02z_step_8192_fused_ncu.csv
 
 
 # FP32 work of one env-step on the house map by beam count: (fadd + fmul + 2 ffma) thread-level instruction counts of
@@ -152,6 +152,24 @@ def cpu_port_throughput(n_agents: int, seconds: float, threads: int, chunk: int 
     return n_agents * steps / dt, steps, dt
 
 
+def tensor_roofline(useful_tflops, precision):
+    """The update against the measured bf16 tensor peak (sustained: the kernel runs for ~175 ms): `useful` = the
+    fp32-equivalent network flops per second the update delivers, `executed` = the bf16 MMA flops behind them (three
+    passes per product in bf16x3: lo*hi + hi*lo + hi*hi), without the padding of the skinny products."""
+    if precision == "fp32":
+        return None
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, src = 1353.6, "fallback (this pool's sustained cuBLAS bf16 figure)"
+    if os.path.exists(p):
+        d = json.load(open(p))
+        peak, src = float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", peak))), "measured (MEASURED_PEAKS.json, sustained)"
+    executed = useful_tflops * (3.0 if precision == "bf16x3" else 1.0)
+    return {"bound": "tensor", "useful": useful_tflops, "executed": executed, "peak": peak, "unit": "TFLOP/s",
+            "frac_useful": useful_tflops / peak, "frac_executed": executed / peak, "peak_source": src,
+            "note": "K = 16 / 32 and N = 16 .. 128 on every product: the MMAs are operand-fetch bound and the epilogues "
+                    "(bias, LeakyReLU, bf16 hi | lo split) are CUDA-core work of the same order (DESIGN.md 6)"}
+
+
 def training_bench(args, torch, dist, dev, rank, world, barrier):
     """env-steps/s of (ii) the rollout and (iii) the whole PPO iteration at N agents x H steps per GPU."""
     import tempfile
@@ -194,6 +212,7 @@ def training_bench(args, torch, dist, dev, rank, world, barrier):
             "rollout_ms": ro_ms, "update_ms": up_ms, "iteration_ms": tot_ms, "epochs": args.epochs, "horizon": H,
             "samples_per_gpu": N * H, "precision": args.precision_one, "episode_csv": False,
             "update_tflops_per_gpu": flops / (up_ms * 1e-3) / 1e12,
+            "update_tensor_roofline": tensor_roofline(flops / (up_ms * 1e-3) / 1e12, args.precision_one),
             "final_actor_loss": float(res["actor_losses"][-1]), "final_critic_loss": float(res["critic_losses"][-1]),
             "sim_launches_per_iteration": int(launches_per_iter)}
 
