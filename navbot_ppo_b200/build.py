@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers += [os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include"))]
-    objs = []
+    objs, jobs = [], []
     for src, extra in UNITS:
         spath = os.path.join(CSRC, src)
         if not os.path.exists(spath):
@@ -64,13 +64,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
         stamp = opath + ".cmd"                       # a changed command line (flags) rebuilds too
         same_cmd = os.path.exists(stamp) and open(stamp).read() == " ".join(cmd)
         if force or not same_cmd or _stale(opath, [spath] + headers):
-            if verbose:
-                cmd.insert(1, "-Xptxas=-v")
-                print(" ".join(cmd), flush=True)
-            subprocess.run(cmd, check=True)
-            with open(stamp, "w") as f:
-                f.write(" ".join(c for c in cmd if c != "-Xptxas=-v"))
+            jobs.append((cmd, stamp))
         objs.append(opath)
+
+    def compile_unit(job):
+        cmd, stamp = job
+        run = [cmd[0], "-Xptxas=-v", *cmd[1:]] if verbose else cmd
+        if verbose:
+            print(" ".join(run), flush=True)
+        subprocess.run(run, check=True)
+        with open(stamp, "w") as f:
+            f.write(" ".join(cmd))
+
+    if jobs:                                         # the translation units compile side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=len(jobs)) as pool:
+            list(pool.map(compile_unit, jobs))
     if force or _stale(LIB, objs):
         cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "--cudart", "static", "-Xlinker", "--no-undefined",
                "-lpthread", "-ldl", "-lrt"]
