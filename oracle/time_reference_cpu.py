@@ -35,6 +35,10 @@ def main():
     ap.add_argument("--batch", type=int, default=5000)
     ap.add_argument("--epochs", type=int, default=50)
     ap.add_argument("--out", default="")
+    ap.add_argument("--procs", type=int, default=0,
+                    help="also run P independent processes of the Env.step-only loop side by side (one robot each, pinned "
+                         "to one core each) and report their aggregate env-steps/s")
+    ap.add_argument("--env-only", action="store_true", help="(internal) only the Env.step loop; prints its seconds")
     args = ap.parse_args()
     if not fake_ros.reference_available():
         raise SystemExit("reference sources not found")
@@ -63,6 +67,21 @@ def main():
         if d or a or (t % 500 == 499):
             ref.reset(); past = np.zeros(2); n_ep += 1
     env_dt = time.perf_counter() - t0
+    if args.env_only:
+        print(f"ENV_ONLY {env_dt:.6f}")
+        return
+    multi = None
+    if args.procs > 1:
+        import subprocess
+        cpus = sorted(os.sched_getaffinity(0))
+        t0 = time.perf_counter()
+        ps = [subprocess.Popen(["taskset", "-c", str(cpus[i % len(cpus)]), sys.executable, os.path.abspath(__file__), "--env-only",
+                                "--env-steps", str(args.env_steps)], stdout=subprocess.PIPE, text=True) for i in range(args.procs)]
+        secs = [float([l for l in p_.communicate()[0].splitlines() if l.startswith("ENV_ONLY")][0].split()[1]) for p_ in ps]
+        wall = time.perf_counter() - t0
+        multi = {"processes": args.procs, "cpus_available": len(cpus), "steps_per_process": args.env_steps,
+                 "loop_seconds_min_max": [min(secs), max(secs)], "wall_seconds_including_imports": wall,
+                 "aggregate_env_steps_per_s": sum(args.env_steps / s_ for s_ in secs)}
     # ---- PPO.rollout + the update of one learn() iteration
     with tempfile.TemporaryDirectory() as tmp, contextlib.redirect_stdout(io.StringIO()):
         agent = ppo_mod.PPO(net_actor.NetActor, net_critic.NetCritic, fake_ros.RefEnv(seg, seed=0).env, 16, 2,
@@ -80,6 +99,7 @@ def main():
         "cores": 1, "torch_threads": 1, "host_cpus": os.cpu_count(),
         "env_step_only": {"steps": args.env_steps, "seconds": env_dt, "env_steps_per_s": args.env_steps / env_dt,
                           "us_per_step": 1e6 * env_dt / args.env_steps},
+        "env_step_only_P_processes": multi,
         "learn_iteration": {"timesteps_per_batch": args.batch, "epochs": args.epochs, "seconds": learn_dt,
                             "rollout_seconds": rollout_t, "update_seconds": update_t,
                             "rollout_env_steps_per_s": args.batch / rollout_t if rollout_t == rollout_t else None,
