@@ -383,12 +383,11 @@ def main():
         sb["act"][:] = hb["act"]
 
     def pipelined(nsteps):
-        tickets = []
         for i in range(nsteps):
-            if len(tickets) == depth:
-                env.wait(tickets.pop(0))                # the oldest step's obs / reward / flags are in host memory
             sb = sets[i % depth]
-            tickets.append(env.step_host_async(sb["act"], sb))
+            # one library call per env step: enqueue step i, return once step i - 3's obs / reward / flags are in host
+            # memory (in the buffer set the next call overwrites)
+            env.step_host_pipelined(sb["act"], sb)
         env.wait(0)
 
     pipelined(8)
@@ -548,8 +547,9 @@ def main():
                                       "steps): the simulator's share of a policy-driven rollout"},
         "e2e": {"value": e2e_async_value, "unit": "env-steps/s", "h2d_bytes_per_step": N * 8 * H,
                 "d2h_bytes_per_step": N * (64 + 4 + 3) * H,
-                "api": "navsim_step_host_async / navsim_wait (VecEnv.step_host_async / wait), the host entry point for a "
-                       "caller that keeps several steps in flight: EVERY env step takes its actions from page-locked host "
+                "api": "navsim_step_host_pipelined (VecEnv.step_host_pipelined = navsim_step_host_async + navsim_wait of a steady "
+                       "pipeline in one call), the host entry point for a caller that keeps several steps in flight: EVERY "
+                       "env step takes its actions from page-locked host "
                        "memory and delivers obs / reward / flags to page-locked host memory (four buffer sets, 4 steps in "
                        "flight; the actions are staged by a host-to-device copy under the previous step's kernel, the step's "
                        "results go home in one copy-engine transfer under the next step's kernel); the timed loop waits "

@@ -181,6 +181,12 @@ int navsim_step_host(navsim_t* h, const float* act_host, float* obs_host, float*
 int64_t navsim_step_host_async(navsim_t* h, const float* act_host, float* obs_host, float* rew_host,
                                uint8_t* done_host, uint8_t* arrive_host, uint8_t* trunc_host);
 int navsim_wait(navsim_t* h, int64_t ticket);
+/* The two calls of a steady pipeline in one: enqueue a step like navsim_step_host_async, then block until the step
+ * issued NAVSIM_ASYNC_DEPTH - 1 calls earlier has delivered its outputs (nothing to wait for during the first calls).
+ * A caller cycling through NAVSIM_ASYNC_DEPTH buffer sets therefore finds, when call t returns, the results of step
+ * t - (NAVSIM_ASYNC_DEPTH - 1) in the set the NEXT call will overwrite.  Returns the new step's ticket. */
+int64_t navsim_step_host_pipelined(navsim_t* h, const float* act_host, float* obs_host, float* rew_host,
+                                   uint8_t* done_host, uint8_t* arrive_host, uint8_t* trunc_host);
 
 /* The one-robot calling convention of the reference, Env.step(action, past_action) /
  * Env.reset() followed by reads of env.position / env.goal_position / env.past_distance

@@ -84,6 +84,7 @@ NAVSIM_SYMBOLS = {
     "navsim_step_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "navsim_step_host_async": (_i64, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "navsim_wait": (ctypes.c_int, [_vp, _i64]),
+    "navsim_step_host_pipelined": (_i64, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "navsim_step_host_ex": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "navsim_reset_host_ex": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "navsim_step_scripted": (ctypes.c_int, [_vp, _i32, _u64, _vp, _vp, _vp, _vp, _vp]),

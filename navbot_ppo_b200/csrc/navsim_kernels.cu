@@ -1243,6 +1243,15 @@ int64_t navsim_step_host_async(navsim_t* h, const float* act_host, float* obs_ho
   return ++h->async_issued;
 }
 
+int64_t navsim_step_host_pipelined(navsim_t* h, const float* act_host, float* obs_host, float* rew_host, uint8_t* done_host,
+                                   uint8_t* arrive_host, uint8_t* trunc_host) {
+  const int64_t t = navsim_step_host_async(h, act_host, obs_host, rew_host, done_host, arrive_host, trunc_host);
+  if (t < 0) return t;
+  if (t >= NAVSIM_ASYNC_DEPTH)
+    if (int rc = navsim_wait(h, t - (NAVSIM_ASYNC_DEPTH - 1))) return rc;
+  return t;
+}
+
 int navsim_wait(navsim_t* h, int64_t ticket) {
   if (!h) return fail(NAVSIM_EINVAL, "null handle");
   if (ticket < 0 || ticket > h->async_issued) return fail(NAVSIM_EINVAL, "unknown ticket");

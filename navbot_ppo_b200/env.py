@@ -97,6 +97,7 @@ class VecEnv:
         self._host_ptr_key, self._host_ptrs, self._host_keepalive = None, None, None
         self._step_host_fn = L.navsim_step_host
         self._step_async_fn, self._async_ptrs, self._async_keepalive = L.navsim_step_host_async, {}, None
+        self._step_pipelined_fn = L.navsim_step_host_pipelined
 
     def set_sampler(self, starts, goals):
         """GoalSpawnSampler tables: starts [n, 3] (x, y, yaw), goals [n, 2] (navsim_set_sampler)."""
@@ -226,6 +227,24 @@ class VecEnv:
             self._async_ptrs[key] = ptrs
             self._async_keepalive = (actions, out)
         t = self._step_async_fn(self._h, *ptrs)
+        if t < 0:
+            _capi.check(int(t))
+        return int(t)
+
+    def step_host_pipelined(self, actions: np.ndarray, out: dict) -> int:
+        """step_host_async + the wait of a steady pipeline in ONE library call: enqueues the step, then blocks until the
+        step issued three calls earlier has delivered its results — with four buffer sets used in turn, those are in
+        the set the next call will overwrite (navsim_step_host_pipelined).  Returns the new step's ticket."""
+        key = (id(actions), id(out))
+        ptrs = self._async_ptrs.get(key)
+        if ptrs is None:
+            ptrs = tuple(int(x.__array_interface__["data"][0]) for x in (actions, out["obs"], out["rew"], out["done"],
+                                                                          out["arrive"], out["trunc"]))
+            if len(self._async_ptrs) > 8:
+                self._async_ptrs.clear()
+            self._async_ptrs[key] = ptrs
+            self._async_keepalive = (actions, out)
+        t = self._step_pipelined_fn(self._h, *ptrs)
         if t < 0:
             _capi.check(int(t))
         return int(t)

@@ -559,3 +559,33 @@ def test_async_host_steps_equal_blocking_host_steps_and_mix_with_device_calls():
     np.testing.assert_array_equal(obs_d.cpu().numpy(), o2)
     np.testing.assert_array_equal(o_h, b.step_host(np.full((n, 2), 0.5, np.float32))[0])
     np.testing.assert_array_equal(a.get_state(_capi.F_X), b.get_state(_capi.F_X))
+
+
+def test_pipelined_host_step_delivers_the_step_issued_three_calls_earlier():
+    """navsim_step_host_pipelined = step_host_async + the wait of a steady pipeline in one call: when call t returns,
+    the results of step t - 3 sit in the buffer set the next call will overwrite, equal to the blocking call's."""
+    n = 2500
+    a, b = VecEnv(n, map="stage_1", seed=8, max_episode_steps=25), VecEnv(n, map="stage_1", seed=8, max_episode_steps=25)
+    depth = 4
+    sets = [a.alloc_host_buffers() for _ in range(depth)]
+    ref = b.alloc_host_buffers()
+    np.testing.assert_array_equal(a.reset_host(), b.reset_host())
+    checked = 0
+    steps = 30
+    for t in range(steps):
+        hb = sets[t % depth]
+        hb["act"][:] = binding.scripted_actions(5, 0, t, n)
+        assert a.step_host_pipelined(hb["act"], hb) == t + 1
+        if t >= depth - 1:                                   # step t - 3 is complete: its set is the next one in turn
+            t_old = t - (depth - 1)
+            ref["act"][:] = binding.scripted_actions(5, 0, t_old, n)
+            b.step_host(ref["act"], out=ref)
+            for key in ("obs", "rew", "done", "arrive", "trunc"):
+                np.testing.assert_array_equal(sets[(t + 1) % depth][key], ref[key], err_msg=f"{key} t={t_old}")
+            checked += 1
+    a.wait(0)
+    for t_old in range(steps - (depth - 1), steps):
+        ref["act"][:] = binding.scripted_actions(5, 0, t_old, n)
+        b.step_host(ref["act"], out=ref)
+        np.testing.assert_array_equal(sets[t_old % depth]["obs"], ref["obs"])
+    assert checked == steps - (depth - 1)

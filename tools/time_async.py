@@ -22,6 +22,15 @@ def child(N, steps):
 
     acc = [0.0, 0.0]
 
+    def run_one_call(n):
+        for i in range(n):
+            sb = sets[i % depth]
+            env.step_host_pipelined(sb["act"], sb)
+        env.wait(0)
+    run_one_call(50)
+    t0 = time.perf_counter(); run_one_call(steps); dt1 = time.perf_counter() - t0
+    print(f"  one library call per step (step_host_pipelined): {N * steps / dt1:.4e} env-steps/s, {dt1 / steps * 1e6:.2f} us per step", flush=True)
+
     def run(n):
         tickets = []
         for i in range(n):
@@ -53,7 +62,7 @@ def main():
                       ("kernel reads / stores host buffers", {"NAVSIM_ASYNC_OBS": "stores"})):
         r = subprocess.run([sys.executable, __file__, "--child", str(N), str(steps)], env={**os.environ, **env}, capture_output=True,
                            text=True, timeout=600)
-        print("\n".join(l for l in r.stdout.splitlines() if l.startswith("  host time")))
+        print("\n".join(l for l in r.stdout.splitlines() if l.startswith("  ")))
         line = [l for l in r.stdout.splitlines() if l.startswith("RESULT")]
         if not line:
             print(name, "FAILED", r.stdout[-1500:], r.stderr[-1500:])
