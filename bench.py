@@ -39,7 +39,7 @@ BYTES_SURVEY = 150
 BYTES_SURVEY_FP64_POSE = 174
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full`
 # capture of the same kernel and shape (profiles/README.md names the file); keyed by (N, H)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {(8192, 128): 748544 + 17474048}   # profiles/r02z_step_8192_fused_ncu.csv
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {(8192, 128): 741632 + 18013952}   # profiles/r02z_step_8192_fused_ncu.csv
 
 
 # FP32 work of one env-step on the house map by beam count: (fadd + fmul + 2 ffma) thread-level instruction counts of
