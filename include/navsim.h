@@ -222,6 +222,8 @@ int navsim_get_state(navsim_t* h, int32_t field, void* host_out);
 int navsim_set_state(navsim_t* h, int32_t field, const void* host_in);
 
 int navsim_get_stats(navsim_t* h, navsim_stats* out, int32_t clear);
+/* Zero the episode statistics in stream order (no read-back, no synchronisation). */
+int navsim_clear_stats(navsim_t* h, void* stream);
 int navsim_num_agents(const navsim_t* h);
 /* Lanes per agent the step kernel runs with (cfg.lanes_per_agent, or the library's choice). */
 int navsim_lanes_per_agent(const navsim_t* h);

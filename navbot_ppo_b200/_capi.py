@@ -93,6 +93,7 @@ NAVSIM_SYMBOLS = {
     "navsim_get_state": (ctypes.c_int, [_vp, _i32, _vp]),
     "navsim_set_state": (ctypes.c_int, [_vp, _i32, _vp]),
     "navsim_get_stats": (ctypes.c_int, [_vp, ctypes.POINTER(NavsimStats), _i32]),
+    "navsim_clear_stats": (ctypes.c_int, [_vp, _vp]),
     "navsim_num_agents": (ctypes.c_int, [_vp]),
     "navsim_launch_count": (_i64, [_vp]),
     "navsim_lanes_per_agent": (ctypes.c_int, [_vp]),

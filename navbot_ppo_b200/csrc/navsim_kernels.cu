@@ -1328,6 +1328,13 @@ int navsim_get_stats(navsim_t* h, navsim_stats* out, int32_t clear) {
   return NAVSIM_OK;
 }
 
+int navsim_clear_stats(navsim_t* h, void* stream) {
+  if (!h) return fail(NAVSIM_EINVAL, "null handle");
+  if (int rc = begin_device_call(h, (cudaStream_t)stream)) return rc;
+  CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, sizeof(DevStats), (cudaStream_t)stream));
+  return NAVSIM_OK;
+}
+
 int navsim_num_agents(const navsim_t* h) { return h ? h->c.N : 0; }
 
 int navsim_lanes_per_agent(const navsim_t* h) { return h ? lanes_of(h) : 0; }

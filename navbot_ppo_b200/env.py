@@ -268,6 +268,10 @@ class VecEnv:
         _capi.check(_capi.lib().navsim_get_stats(self._h, ctypes.byref(s), 1 if clear else 0))
         return s
 
+    def clear_stats(self) -> None:
+        """Zero the episode statistics in stream order (no read-back, no synchronisation)."""
+        _capi.check(_capi.lib().navsim_clear_stats(self._h, _stream_ptr(self.device)))
+
     @property
     def lanes_per_agent(self) -> int:
         """GPU lanes cooperating on one agent's step (chosen by the library from N unless requested)."""

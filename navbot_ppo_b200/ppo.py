@@ -381,7 +381,7 @@ class PPO:
         sp = _stream(self.device)
         if t_so_far > 50000 and self.cov_mat[0][0] >= 0.1:   # ppo.py:694-695, once per rollout (episode starts)
             self._decay_cov()
-        env.stats(clear=True)
+        env.clear_stats()                                    # in stream order: no read-back, no synchronisation
         if self.continue_episodes and getattr(self, "_rollouts_done", 0) > 0:
             self._b_obs[0].copy_(self._next_obs)                                 # episodes run on across rollouts
         else:
